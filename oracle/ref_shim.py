@@ -1,0 +1,89 @@
+"""Import the UNMODIFIED reference modules from /root/reference (TEST INFRASTRUCTURE ONLY).
+
+Used only in the authoring container (the GPU box has no /root/reference): by
+``tests/golden/make_golden.py`` to generate the committed golden vectors and by the
+``not gpu`` tests that compare the oracle with the live reference when it is present.
+
+The reference imports two packages that are not installed here; they are replaced by empty
+shims *before* import, nothing in the reference is edited:
+
+* ``matplotlib`` / ``matplotlib.pyplot`` (utils/utils.py:3 imports it, never used on this path)
+* ``tqdm.notebook.tqdm`` (utils/training.py:6; needs ipywidgets) -> pass-through iterator with a
+  no-op ``set_postfix`` (utils/training.py:60 calls it)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("UNET_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "unet", "unet.py"))
+
+
+class _PassThroughTqdm:
+    def __init__(self, iterable=None, *a, **k):
+        self._it = iterable
+
+    def __iter__(self):
+        return iter(self._it)
+
+    def set_postfix(self, *a, **k):
+        pass
+
+    def update(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
+
+
+def _install_shims():
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except Exception:
+            m = types.ModuleType("matplotlib")
+            p = types.ModuleType("matplotlib.pyplot")
+            m.pyplot = p
+            sys.modules["matplotlib"] = m
+            sys.modules["matplotlib.pyplot"] = p
+    import tqdm.notebook as tn
+    tn.tqdm = _PassThroughTqdm
+
+
+def load():
+    """Returns a namespace with the reference's hot-path symbols (raises if unavailable)."""
+    if not available():
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    _install_shims()
+    # the reference's top-level packages are called `unet` and `utils`; import them under the
+    # reference root without leaving it on sys.path for the rest of the process
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")
+             or k == "unet" or k.startswith("unet.")}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        import importlib
+        ns = types.SimpleNamespace()
+        ns.unet_mod = importlib.import_module("unet.unet")
+        ns.loss_mod = importlib.import_module("utils.weighted_loss")
+        ns.metrics_mod = importlib.import_module("utils.MetricsHistory")
+        try:
+            ns.training_mod = importlib.import_module("utils.training")
+        except Exception as e:  # torchvision etc. missing
+            ns.training_mod = None
+            ns.training_error = e
+        ns.unet = ns.unet_mod.unet
+        ns.WeightedDiceCELoss = ns.loss_mod.WeightedDiceCELoss
+        ns.WeightedMemoryEfficientDiceLoss = ns.loss_mod.WeightedMemoryEfficientDiceLoss
+        ns.MetricsHistory = ns.metrics_mod.MetricsHistory
+        return ns
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "unet" or k.startswith("unet.")]:
+            # keep reference modules reachable only through `ns`
+            sys.modules.pop(k)
+        sys.modules.update(saved)
