@@ -1,0 +1,207 @@
+"""ctypes binding of libunetk.so (the C ABI declared in include/unetk.h).
+
+Host-side plumbing only: device memory comes from PyTorch's allocator and is passed as raw pointers,
+kernels are enqueued on torch's current CUDA stream.  There is no CPU path and no fallback: if the
+shared library is missing or the tensors are not CUDA tensors the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libunetk.so")
+
+F32, BF16 = 0, 1
+ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+MODE_1X1, MODE_3X3, MODE_CONVT, MODE_CONVT_GATHER = 0, 1, 2, 3
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class Tensor(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("ld", C.c_int32), ("dtype", C.c_int32)]
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", Tensor), ("w", C.c_void_p), ("y", Tensor), ("mode", C.c_int32), ("algo", C.c_int32),
+                ("bias", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p)]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [("u", Tensor), ("s", Tensor), ("dw", C.c_void_p), ("mode", C.c_int32), ("algo", C.c_int32)]
+
+
+class BnFinalizeArgs(C.Structure):
+    _fields_ = [("sum", C.c_void_p), ("sumsq", C.c_void_p), ("count", C.c_int64), ("c", C.c_int32),
+                ("training", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p)]
+
+
+class BnBwdArgs(C.Structure):
+    _fields_ = [("z", Tensor), ("dy", Tensor), ("dpool", Tensor), ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("mean", C.c_void_p), ("invstd", C.c_void_p), ("sums", C.c_void_p), ("dz", Tensor),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
+class DiceCeArgs(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("target", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32),
+                ("w", C.c_int32), ("class_weights", C.c_void_p), ("has_ignore", C.c_int32), ("ignore_index", C.c_int64),
+                ("dice_weight", C.c_float), ("ce_weight", C.c_float), ("smooth", C.c_float), ("accum", C.c_void_p),
+                ("coef", C.c_void_p), ("loss", C.c_void_p), ("status", C.c_void_p), ("grad_out", C.c_void_p),
+                ("dlogits", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises loudly when it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA extension first "
+                "(python -m image_segmentation_b200._build, or __graft_entry__.build()). There is no fallback path.")
+        l = C.CDLL(LIB_PATH)
+        l.unetk_version.restype = C.c_int
+        l.unetk_last_error.restype = C.c_char_p
+        vp = C.c_void_p
+        P = C.POINTER
+        sigs = {
+            "unetk_device_query": [P(C.c_int32), P(C.c_int32), P(C.c_int32)],
+            "unetk_im2col3x3_first": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(Tensor), vp],
+            "unetk_permute3": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_int64] * 6 + [vp],
+            "unetk_conv": [P(ConvArgs), vp],
+            "unetk_wgrad": [P(WgradArgs), vp],
+            "unetk_channel_sum": [P(Tensor), vp, vp],
+            "unetk_bn_stats": [P(Tensor), vp, vp, vp],
+            "unetk_bn_finalize": [P(BnFinalizeArgs), vp],
+            "unetk_bn_relu_apply": [P(Tensor), vp, vp, P(Tensor), P(Tensor), vp],
+            "unetk_bn_relu_bwd_reduce": [P(BnBwdArgs), vp],
+            "unetk_bn_relu_bwd_apply": [P(BnBwdArgs), vp],
+            "unetk_head_fprop": [P(Tensor), vp, vp, C.c_int32, vp, vp],
+            "unetk_head_bwd": [vp, P(Tensor), vp, C.c_int32, P(Tensor), vp, vp, vp],
+            "unetk_dice_ce_fwd": [P(DiceCeArgs), vp],
+            "unetk_dice_ce_bwd": [P(DiceCeArgs), vp],
+            "unetk_argmax_confusion": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp],
+        }
+        for name, argtypes in sigs.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+EXPORTED_SYMBOLS = (
+    "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_im2col3x3_first", "unetk_permute3",
+    "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
+    "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
+    "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion",
+)
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libunetk: " + lib().unetk_last_error().decode(errors="replace"))
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("image_segmentation_b200 runs on CUDA tensors only (no CPU fallback); got device "
+                               + str(t.device))
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def nhwc(t: Optional[torch.Tensor]) -> Tensor:
+    """unetk_tensor for a [N,H,W,C] torch view whose pixels are `ld` elements apart (channel slices allowed)."""
+    if t is None:
+        return Tensor(None, 0, 0, 0, 0, 0, 0)
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    if c > 1 and sc != 1:
+        raise ValueError("channels must be contiguous")
+    ld = sw if w > 1 else (sh // w if h > 1 else (sn // (h * w) if n > 1 else c))
+    if (w > 1 and sw != ld) or (h > 1 and sh != ld * w) or (n > 1 and sn != ld * w * h):
+        raise ValueError(f"not a pixel-major NHWC view: shape {tuple(t.shape)} stride {t.stride()}")
+    return Tensor(t.data_ptr(), n, h, w, c, ld, _DTYPES[t.dtype])
+
+
+# ---- thin wrappers ------------------------------------------------------------------------------
+def im2col3x3_first(x_nchw: torch.Tensor, out: torch.Tensor):
+    n, cin, h, w = x_nchw.shape
+    check(lib().unetk_im2col3x3_first(x_nchw.data_ptr(), n, cin, h, w, C.byref(nhwc(out)), stream_ptr()))
+
+
+def permute3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_strides):
+    check(lib().unetk_permute3(src.data_ptr(), dst.data_ptr(), _DTYPES[dst.dtype], dims[0], dims[1], dims[2],
+                               src_strides[0], src_strides[1], src_strides[2],
+                               dst_strides[0], dst_strides[1], dst_strides[2], stream_ptr()))
+
+
+def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO):
+    a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo, ptr(bias), ptr(stat_sum), ptr(stat_sumsq))
+    check(lib().unetk_conv(C.byref(a), stream_ptr()))
+
+
+def wgrad(u, s, dw, mode, algo=ALGO_AUTO):
+    a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo)
+    check(lib().unetk_wgrad(C.byref(a), stream_ptr()))
+
+
+def channel_sum(t, out):
+    check(lib().unetk_channel_sum(C.byref(nhwc(t)), out.data_ptr(), stream_ptr()))
+
+
+def bn_stats(z, s, ss):
+    check(lib().unetk_bn_stats(C.byref(nhwc(z)), s.data_ptr(), ss.data_ptr(), stream_ptr()))
+
+
+def bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
+                scale, shift, mean, invstd):
+    a = BnFinalizeArgs(ptr(s), ptr(ss), count, c, 1 if training else 0, ptr(gamma), ptr(beta), ptr(conv_bias),
+                       ptr(running_mean), ptr(running_var), ptr(nbt), momentum, eps, ptr(scale), ptr(shift),
+                       ptr(mean), ptr(invstd))
+    check(lib().unetk_bn_finalize(C.byref(a), stream_ptr()))
+
+
+def bn_relu_apply(z, scale, shift, a, pooled=None):
+    check(lib().unetk_bn_relu_apply(C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(), C.byref(nhwc(a)),
+                                    C.byref(nhwc(pooled)), stream_ptr()))
+
+
+def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta):
+    a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
+                  ptr(dgamma), ptr(dbeta))
+    s = stream_ptr()
+    check(lib().unetk_bn_relu_bwd_reduce(C.byref(a), s))
+    check(lib().unetk_bn_relu_bwd_apply(C.byref(a), s))
+
+
+def head_fprop(a, w, b, dout, logits):
+    check(lib().unetk_head_fprop(C.byref(nhwc(a)), w.data_ptr(), ptr(b), dout, logits.data_ptr(), stream_ptr()))
+
+
+def head_bwd(dlogits, a, w, dout, da, dw, db):
+    check(lib().unetk_head_bwd(dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
+                               dw.data_ptr(), ptr(db), stream_ptr()))
+
+
+def argmax_confusion(pred, label, n, c, h, w, counts, argmax_out, status):
+    check(lib().unetk_argmax_confusion(pred.data_ptr(), label.data_ptr(), n, c, h, w, counts.data_ptr(),
+                                       ptr(argmax_out), status.data_ptr(), stream_ptr()))

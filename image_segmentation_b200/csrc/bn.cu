@@ -1,0 +1,465 @@
+// BatchNorm(train) + ReLU + MaxPool2x2 forward/backward as bandwidth kernels (NHWC, 8 channels per thread).
+//
+// Reference call sites replaced: unet/unet.py:17-18,20-21 (BatchNorm2d + ReLU inside DoubleConvReLU) and
+// unet/unet.py:40 (MaxPool2d(2,2) in Down) together with their autograd backward
+// (native_batch_norm_backward, threshold_backward, max_pool2d_with_indices_backward).
+//
+// Roofline: HBM.  Algorithmic bytes per element (T = storage type):
+//   stats            read z                                  1*sizeof(T)
+//   apply(+pool)     read z, write a (+ pooled/4)            2*sizeof(T) (+ sizeof(T)/4)
+//   bwd reduce       read z, dy (+ dpool/4)                  2*sizeof(T) (+ sizeof(T)/4)
+//   bwd apply        read z, dy (+ dpool/4), write dz        3*sizeof(T) (+ sizeof(T)/4)
+#include "common.cuh"
+
+namespace unetk {
+
+constexpr int kThreads = 256;
+
+// largest power of two <= 32 dividing cg
+static int choose_cgb(int cg) {
+  int b = 32;
+  while (b > 1 && (cg % b) != 0) b >>= 1;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions: block = rows x CGB channel-groups; smem reduce across rows; double atomics
+// ------------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NQ][8], int cgb, int row, int lane_g, int rows,
+                                                     int cg0, double* const (&out)[NQ]) {
+  extern __shared__ float red[];  // [NQ][rows][cgb*8]
+  const int width = cgb * 8;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[(q * rows + row) * width + lane_g * 8 + i] = acc[q][i];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NQ * width; idx += blockDim.x) {
+    const int q = idx / width, ch = idx % width;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[(q * rows + r) * width + ch];
+    atomicAdd(out[q] + (size_t)cg0 * 8 + ch, (double)s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const T* __restrict__ z, int64_t npix, int ld, int cgb,
+                                                            int pix_per_block, double* __restrict__ sum,
+                                                            double* __restrict__ sumsq) {
+  const int rows = kThreads / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int cg0 = blockIdx.x * cgb;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_block;
+  const int64_t p1 = min(p0 + (int64_t)pix_per_block, npix);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  for (int64_t p = p0 + row; p < p1; p += rows) {
+    float v[8];
+    load8(z + p * ld + (size_t)(cg0 + lane_g) * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += v[i];
+      acc[1][i] = fmaf(v[i], v[i], acc[1][i]);
+    }
+  }
+  double* const outs[2] = {sum, sumsq};
+  block_channel_reduce<2>(acc, cgb, row, lane_g, rows, cg0, outs);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(unetk_bn_finalize_args a) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && a.training && a.num_batches_tracked) *a.num_batches_tracked += 1;
+  if (c >= a.c) return;
+  const float g = a.gamma[c], b = a.beta[c];
+  const float cb = a.conv_bias ? a.conv_bias[c] : 0.f;
+  if (a.training) {
+    const double m = a.sum[c] / (double)a.count;
+    double var = a.sumsq[c] / (double)a.count - m * m;
+    if (var < 0.0) var = 0.0;
+    const double istd = 1.0 / sqrt(var + (double)a.eps);
+    const float sc = (float)((double)g * istd);
+    a.scale[c] = sc;
+    a.shift[c] = (float)((double)b - m * (double)g * istd);
+    a.mean[c] = (float)m;
+    a.invstd[c] = (float)istd;
+    if (a.running_mean) {
+      // PyTorch: running = (1-momentum)*running + momentum*batch; variance uses the unbiased estimate
+      const double unb = a.count > 1 ? var * ((double)a.count / (double)(a.count - 1)) : var;
+      a.running_mean[c] = (float)((1.0 - a.momentum) * a.running_mean[c] + a.momentum * (m + cb));
+      a.running_var[c] = (float)((1.0 - a.momentum) * a.running_var[c] + a.momentum * unb);
+    }
+  } else {
+    const float istd = rsqrtf(a.running_var[c] + a.eps);
+    const float sc = g * istd;
+    a.scale[c] = sc;
+    a.shift[c] = fmaf(cb - a.running_mean[c], sc, b);
+    if (a.mean) a.mean[c] = a.running_mean[c] - cb;
+    if (a.invstd) a.invstd[c] = istd;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(kThreads)
+    bn_relu_apply_kernel(const T* __restrict__ z, int zld, const float* __restrict__ scale,
+                         const float* __restrict__ shift, T* __restrict__ a, int ald, T* __restrict__ pooled, int pld,
+                         int n, int h, int w, int cg) {
+  // work item = (pixel or 2x2 window, channel group)
+  const int hh = POOL ? h / 2 : h, ww = POOL ? w / 2 : w;
+  const int64_t total = (int64_t)n * hh * ww * cg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    int64_t p = i / cg;
+    float sc[8], sh[8];
+    load8(scale + g * 8, sc);
+    load8(shift + g * 8, sh);
+    if (!POOL) {
+      float v[8];
+      load8(z + p * zld + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+      store8(a + p * ald + g * 8, v);
+    } else {
+      const int x = (int)(p % ww);
+      p /= ww;
+      const int y = (int)(p % hh);
+      const int img = (int)(p / hh);
+      float mx[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx[k] = 0.f;  // ReLU output is >= 0
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t pix = ((int64_t)img * h + (2 * y + (q >> 1))) * w + (2 * x + (q & 1));
+        float v[8];
+        load8(z + pix * zld + g * 8, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+          mx[k] = fmaxf(mx[k], v[k]);
+        }
+        store8(a + pix * ald + g * 8, v);
+      }
+      store8(pooled + (((int64_t)img * hh + y) * ww + x) * pld + g * 8, mx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: dy = (dA_full + routed pool grad) * [a > 0]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct BwdSrc {
+  const T* z; int zld;
+  const T* dy; int dyld;      // may be null
+  const T* dp; int dpld;      // may be null (POOL variants only)
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  int n, h, w, cg;
+};
+
+// computes, for one full-resolution pixel, the masked gradient dy[8] and xhat[8]
+template <typename T>
+__device__ __forceinline__ void bwd_pixel(const BwdSrc<T>& s, int64_t pix, int g, const float (&sc)[8],
+                                          const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
+                                          const float (&extra)[8], bool has_extra, float (&dy)[8], float (&xh)[8]) {
+  float zv[8];
+  load8(s.z + pix * s.zld + g * 8, zv);
+  float d[8];
+  if (s.dy) {
+    load8(s.dy + pix * s.dyld + g * 8, d);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+    const float gsum = has_extra ? d[k] + extra[k] : d[k];
+    dy[k] = act > 0.f ? gsum : 0.f;
+    xh[k] = (zv[k] - mu[k]) * is[k];
+  }
+}
+
+// for a 2x2 window: which of the 4 positions receives the pooled gradient (first max in scan order)
+template <typename T>
+__device__ __forceinline__ void window_argmax(const BwdSrc<T>& s, int img, int y, int x, int g, const float (&sc)[8],
+                                              const float (&sh)[8], int (&arg)[8]) {
+  float best[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    best[k] = -INFINITY;
+    arg[k] = 0;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+    float zv[8];
+    load8(s.z + pix * s.zld + g * 8, zv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+      if (act > best[k]) {
+        best[k] = act;
+        arg[k] = q;
+      }
+    }
+  }
+}
+
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(kThreads)
+    bn_bwd_reduce_kernel(BwdSrc<T> s, int cgb, int items_per_block, double* __restrict__ s1, double* __restrict__ s2) {
+  const int rows = kThreads / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int cg0 = blockIdx.x * cgb;
+  const int g = cg0 + lane_g;
+  const int hh = POOL ? s.h / 2 : s.h, ww = POOL ? s.w / 2 : s.w;
+  const int64_t nitems = (int64_t)s.n * hh * ww;
+  const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
+  const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
+  float sc[8], sh[8], mu[8], is[8];
+  load8(s.scale + g * 8, sc);
+  load8(s.shift + g * 8, sh);
+  load8(s.mean + g * 8, mu);
+  load8(s.invstd + g * 8, is);
+  float acc[2][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
+  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t it = i0 + row; it < i1; it += rows) {
+    if (!POOL) {
+      float dy[8], xh[8];
+      bwd_pixel<T>(s, it, g, sc, sh, mu, is, zero8, false, dy, xh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[0][k] += dy[k];
+        acc[1][k] = fmaf(dy[k], xh[k], acc[1][k]);
+      }
+    } else {
+      const int x = (int)(it % ww);
+      const int y = (int)((it / ww) % hh);
+      const int img = (int)(it / ((int64_t)ww * hh));
+      int arg[8];
+      window_argmax<T>(s, img, y, x, g, sc, sh, arg);
+      float dp[8];
+      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+        float extra[8], dy[8], xh[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) extra[k] = arg[k] == q ? dp[k] : 0.f;
+        bwd_pixel<T>(s, pix, g, sc, sh, mu, is, extra, true, dy, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[0][k] += dy[k];
+          acc[1][k] = fmaf(dy[k], xh[k], acc[1][k]);
+        }
+      }
+    }
+  }
+  double* const outs[2] = {s1, s2};
+  block_channel_reduce<2>(acc, cgb, row, lane_g, rows, cg0, outs);
+}
+
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(kThreads)
+    bn_bwd_apply_kernel(BwdSrc<T> s, const double* __restrict__ s1, const double* __restrict__ s2, double inv_count,
+                        T* __restrict__ dz, int dzld, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int hh = POOL ? s.h / 2 : s.h, ww = POOL ? s.w / 2 : s.w;
+  const int64_t total = (int64_t)s.n * hh * ww * s.cg;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < s.cg * 8; c += blockDim.x) {
+      if (dgamma) dgamma[c] = (float)s2[c];
+      if (dbeta) dbeta[c] = (float)s1[c];
+    }
+  }
+  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % s.cg);
+    const int64_t it = i / s.cg;
+    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+    load8(s.scale + g * 8, sc);
+    load8(s.shift + g * 8, sh);
+    load8(s.mean + g * 8, mu);
+    load8(s.invstd + g * 8, is);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      m1[k] = (float)(s1[g * 8 + k] * inv_count);
+      m2[k] = (float)(s2[g * 8 + k] * inv_count);
+    }
+    if (!POOL) {
+      float dy[8], xh[8], o[8];
+      bwd_pixel<T>(s, it, g, sc, sh, mu, is, zero8, false, dy, xh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
+      store8(dz + it * dzld + g * 8, o);
+    } else {
+      const int x = (int)(it % ww);
+      const int y = (int)((it / ww) % hh);
+      const int img = (int)(it / ((int64_t)ww * hh));
+      int arg[8];
+      window_argmax<T>(s, img, y, x, g, sc, sh, arg);
+      float dp[8];
+      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+        float extra[8], dy[8], xh[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) extra[k] = arg[k] == q ? dp[k] : 0.f;
+        bwd_pixel<T>(s, pix, g, sc, sh, mu, is, extra, true, dy, xh);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
+        store8(dz + pix * dzld + g * 8, o);
+      }
+    }
+  }
+}
+
+static int grid_for(int64_t total_threads) {
+  const int64_t blocks = (total_threads + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+template <typename T>
+static BwdSrc<T> make_src(const unetk_bn_bwd_args* a) {
+  BwdSrc<T> s;
+  s.z = (const T*)a->z.ptr; s.zld = a->z.ld;
+  s.dy = (const T*)a->dy.ptr; s.dyld = a->dy.ld;
+  s.dp = (const T*)a->dpool.ptr; s.dpld = a->dpool.ld;
+  s.scale = a->scale; s.shift = a->shift; s.mean = a->mean; s.invstd = a->invstd;
+  s.n = a->z.n; s.h = a->z.h; s.w = a->z.w; s.cg = a->z.c / 8;
+  return s;
+}
+
+static int check_bwd(const unetk_bn_bwd_args* a) {
+  UNETK_REQUIRE(a != nullptr, "bn_bwd: null args");
+  UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
+  UNETK_REQUIRE(a->dy.ptr || a->dpool.ptr, "bn_bwd: need dy and/or dpool");
+  if (a->dy.ptr) {
+    UNETK_REQUIRE(tensor_ok(a->dy) && vec8_ok(a->dy) && a->dy.dtype == a->z.dtype && a->dy.n == a->z.n &&
+                      a->dy.h == a->z.h && a->dy.w == a->z.w && a->dy.c == a->z.c, "bn_bwd: dy shape/dtype mismatch");
+  }
+  if (a->dpool.ptr) {
+    UNETK_REQUIRE(tensor_ok(a->dpool) && vec8_ok(a->dpool) && a->dpool.dtype == a->z.dtype && a->dpool.n == a->z.n &&
+                      a->dpool.h * 2 == a->z.h && a->dpool.w * 2 == a->z.w && a->dpool.c == a->z.c,
+                  "bn_bwd: dpool must be [N,H/2,W/2,C]");
+  }
+  UNETK_REQUIRE(a->scale && a->shift && a->mean && a->invstd && a->sums, "bn_bwd: null statistics");
+  return UNETK_OK;
+}
+
+}  // namespace unetk
+
+using namespace unetk;
+
+extern "C" {
+
+int unetk_bn_stats(const unetk_tensor* z, double* sum, double* sumsq, void* stream) {
+  UNETK_REQUIRE(z && sum && sumsq, "bn_stats: null argument");
+  UNETK_REQUIRE(tensor_ok(*z) && vec8_ok(*z), "bn_stats: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
+  const int cg = z->c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
+  const int64_t npix = pixels(*z);
+  int ppb = rows * 32;
+  const int64_t nb = (npix + ppb - 1) / ppb;
+  UNETK_REQUIRE(nb <= 65535 * 16, "bn_stats: tensor too large");
+  if (nb > 65535) ppb *= 16;
+  dim3 grid(cg / cgb, (unsigned)((npix + ppb - 1) / ppb));
+  const size_t smem = (size_t)2 * rows * cgb * 8 * sizeof(float);
+  UNETK_DISPATCH_DTYPE(z->dtype, T, {
+    bn_stats_kernel<T><<<grid, kThreads, smem, (cudaStream_t)stream>>>((const T*)z->ptr, npix, z->ld, cgb, ppb, sum, sumsq);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream) {
+  UNETK_REQUIRE(a && a->c > 0 && a->gamma && a->beta && a->scale && a->shift, "bn_finalize: null argument");
+  if (a->training) {
+    UNETK_REQUIRE(a->sum && a->sumsq && a->count > 0 && a->mean && a->invstd, "bn_finalize: training needs sum/sumsq/count/mean/invstd");
+  } else {
+    UNETK_REQUIRE(a->running_mean && a->running_var, "bn_finalize: eval needs running statistics");
+  }
+  bn_finalize_kernel<<<(a->c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
+                        const unetk_tensor* pooled, void* stream) {
+  UNETK_REQUIRE(z && a && scale && shift, "bn_relu_apply: null argument");
+  UNETK_REQUIRE(tensor_ok(*z) && vec8_ok(*z) && tensor_ok(*a) && vec8_ok(*a), "bn_relu_apply: bad z/a tensor");
+  UNETK_REQUIRE(a->dtype == z->dtype && a->n == z->n && a->h == z->h && a->w == z->w && a->c == z->c,
+                "bn_relu_apply: a must match z");
+  const bool pool = pooled && pooled->ptr;
+  if (pool) {
+    UNETK_REQUIRE(tensor_ok(*pooled) && vec8_ok(*pooled) && pooled->dtype == z->dtype && pooled->n == z->n &&
+                      pooled->h * 2 == z->h && pooled->w * 2 == z->w && pooled->c == z->c,
+                  "bn_relu_apply: pooled must be [N,H/2,W/2,C]");
+  }
+  const int cg = z->c / 8;
+  const int64_t items = pixels(*z) / (pool ? 4 : 1) * cg;
+  const int grid = grid_for(items);
+  UNETK_DISPATCH_DTYPE(z->dtype, T, {
+    if (pool)
+      bn_relu_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, (T*)pooled->ptr, pooled->ld, z->n, z->h, z->w, cg);
+    else
+      bn_relu_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, nullptr, 0, z->n, z->h, z->w, cg);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream) {
+  int rc = check_bwd(a);
+  if (rc) return rc;
+  const bool pool = a->dpool.ptr != nullptr;
+  const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
+  const int64_t nitems = pixels(a->z) / (pool ? 4 : 1);
+  int ipb = rows * (pool ? 8 : 32);
+  if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
+  UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_reduce: tensor too large");
+  dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));
+  const size_t smem = (size_t)2 * rows * cgb * 8 * sizeof(float);
+  double* s1 = a->sums;
+  double* s2 = a->sums + a->z.c;
+  UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
+    BwdSrc<T> s = make_src<T>(a);
+    if (pool)
+      bn_bwd_reduce_kernel<T, true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2);
+    else
+      bn_bwd_reduce_kernel<T, false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream) {
+  int rc = check_bwd(a);
+  if (rc) return rc;
+  UNETK_REQUIRE(tensor_ok(a->dz) && vec8_ok(a->dz) && a->dz.dtype == a->z.dtype && a->dz.n == a->z.n &&
+                    a->dz.h == a->z.h && a->dz.w == a->z.w && a->dz.c == a->z.c, "bn_bwd_apply: dz must match z");
+  const bool pool = a->dpool.ptr != nullptr;
+  const int cg = a->z.c / 8;
+  const int64_t items = pixels(a->z) / (pool ? 4 : 1) * cg;
+  const int grid = grid_for(items);
+  const double inv_count = 1.0 / (double)pixels(a->z);
+  const double* s1 = a->sums;
+  const double* s2 = a->sums + a->z.c;
+  UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
+    BwdSrc<T> s = make_src<T>(a);
+    if (pool)
+      bn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
+    else
+      bn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+}

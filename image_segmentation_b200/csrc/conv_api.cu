@@ -1,0 +1,127 @@
+// unetk_conv / unetk_wgrad / unetk_channel_sum: argument validation and dispatch between the fp32 parity tier
+// (CUDA-core kernels) and the bf16 throughput tier (TMA + tcgen05 kernels).  There is no CPU path.
+#include "conv_internal.cuh"
+
+namespace unetk {
+
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ t, int64_t npix, int ld, int c,
+                                                          int pix_per_block, float* __restrict__ out) {
+  // block = 256/cgb pixel rows x cgb channel groups (8 channels each)
+  extern __shared__ float red[];
+  const int cg = c / 8;
+  int cgb = 32;
+  while (cgb > 1 && (cg % cgb) != 0) cgb >>= 1;
+  const int rows = 256 / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int g = blockIdx.x * cgb + lane_g;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_block, p1 = min(p0 + (int64_t)pix_per_block, npix);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int64_t p = p0 + row; p < p1; p += rows) {
+    float v[8];
+    load8(t + p * ld + (size_t)g * 8, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+  const int width = cgb * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[row * width + lane_g * 8 + i] = acc[i];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < width; ch += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[r * width + ch];
+    atomicAdd(out + (size_t)blockIdx.x * width + ch, s);
+  }
+}
+
+}  // namespace unetk
+
+using namespace unetk;
+
+extern "C" {
+
+int unetk_conv(const unetk_conv_args* a, void* stream) {
+  UNETK_REQUIRE(a != nullptr, "conv: null args");
+  UNETK_REQUIRE(tensor_ok(a->x) && tensor_ok(a->y) && a->w, "conv: bad x/y/w");
+  UNETK_REQUIRE(a->x.dtype == a->y.dtype, "conv: x and y must share a dtype");
+  UNETK_REQUIRE(a->mode >= 0 && a->mode <= 3, "conv: mode must be 0..3");
+  ConvGeom g;
+  g.cin = a->x.c;
+  g.cout = a->y.c;
+  g.cout_total = a->y.c;
+  g.taps = a->mode == 0 ? 1 : (a->mode == 1 ? 9 : (a->mode == 2 ? 1 : 4));
+  if (a->mode <= 1) {
+    UNETK_REQUIRE(a->y.n == a->x.n && a->y.h == a->x.h && a->y.w == a->x.w, "conv: y must have x's spatial shape");
+    g.rows_n = a->y.n; g.rows_h = a->y.h; g.rows_w = a->y.w;
+  } else if (a->mode == 2) {
+    UNETK_REQUIRE(a->y.n == a->x.n && a->y.h == 2 * a->x.h && a->y.w == 2 * a->x.w, "conv(T fprop): y must be [N,2h,2w,Cout]");
+    g.cout_total = 4 * a->y.c;
+    g.rows_n = a->x.n; g.rows_h = a->x.h; g.rows_w = a->x.w;
+  } else {
+    UNETK_REQUIRE(a->y.n == a->x.n && 2 * a->y.h == a->x.h && 2 * a->y.w == a->x.w, "conv(T dgrad): x must be [N,2h,2w,C]");
+    g.rows_n = a->y.n; g.rows_h = a->y.h; g.rows_w = a->y.w;
+  }
+  UNETK_REQUIRE((a->stat_sum == nullptr) == (a->stat_sumsq == nullptr), "conv: stat_sum and stat_sumsq come together");
+  UNETK_REQUIRE(!(a->stat_sum && a->mode >= 2), "conv: statistics only for modes 0/1");
+
+  int algo = a->algo;
+  if (algo == UNETK_ALGO_AUTO) algo = a->x.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  if (algo == UNETK_ALGO_TC) {
+    const char* why = "";
+    if (!tc_conv_supported(a, g, &why)) {
+      set_error("conv: tcgen05 path does not support this problem: %s", why);
+      return UNETK_ERR_UNSUPPORTED;
+    }
+    return tc_conv(a, g, (cudaStream_t)stream);
+  }
+  UNETK_REQUIRE(algo == UNETK_ALGO_SIMT, "conv: unknown algo %d", algo);
+  int rc = simt_conv(a, g, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (a->stat_sum) return unetk_bn_stats(&a->y, a->stat_sum, a->stat_sumsq, stream);
+  return UNETK_OK;
+}
+
+int unetk_wgrad(const unetk_wgrad_args* a, void* stream) {
+  UNETK_REQUIRE(a != nullptr, "wgrad: null args");
+  UNETK_REQUIRE(tensor_ok(a->u) && tensor_ok(a->s) && a->dw, "wgrad: bad u/s/dw");
+  UNETK_REQUIRE(a->u.dtype == a->s.dtype, "wgrad: u and s must share a dtype");
+  UNETK_REQUIRE(a->mode >= 0 && a->mode <= 2, "wgrad: mode must be 0..2");
+  const int taps = a->mode == 0 ? 1 : (a->mode == 1 ? 9 : 4);
+  if (a->mode <= 1)
+    UNETK_REQUIRE(a->s.n == a->u.n && a->s.h == a->u.h && a->s.w == a->u.w, "wgrad: u and s must share a spatial shape");
+  else
+    UNETK_REQUIRE(a->s.n == a->u.n && a->s.h == 2 * a->u.h && a->s.w == 2 * a->u.w, "wgrad(mode 2): s must be [N,2h,2w,C]");
+  int algo = a->algo;
+  if (algo == UNETK_ALGO_AUTO) algo = a->u.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  if (algo == UNETK_ALGO_TC) {
+    const char* why = "";
+    if (!tc_wgrad_supported(a, taps, &why)) {
+      set_error("wgrad: tcgen05 path does not support this problem: %s", why);
+      return UNETK_ERR_UNSUPPORTED;
+    }
+    return tc_wgrad(a, taps, (cudaStream_t)stream);
+  }
+  UNETK_REQUIRE(algo == UNETK_ALGO_SIMT, "wgrad: unknown algo %d", algo);
+  return simt_wgrad(a, taps, (cudaStream_t)stream);
+}
+
+int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream) {
+  UNETK_REQUIRE(t && out, "channel_sum: null argument");
+  UNETK_REQUIRE(tensor_ok(*t) && vec8_ok(*t), "channel_sum: t must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
+  const int cg = t->c / 8;
+  int cgb = 32;
+  while (cgb > 1 && (cg % cgb) != 0) cgb >>= 1;
+  const int rows = 256 / cgb;
+  const int64_t npix = pixels(*t);
+  int ppb = rows * 32;
+  if ((npix + ppb - 1) / ppb > 65535) ppb *= 16;
+  UNETK_REQUIRE((npix + ppb - 1) / ppb <= 65535, "channel_sum: tensor too large");
+  dim3 grid(cg / cgb, (unsigned)((npix + ppb - 1) / ppb));
+  const size_t smem = (size_t)rows * cgb * 8 * sizeof(float);
+  UNETK_DISPATCH_DTYPE(t->dtype, T, {
+    channel_sum_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)t->ptr, npix, t->ld, t->c, ppb, out);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+}

@@ -1,0 +1,667 @@
+// bf16 implicit-GEMM contractions on the 5th-generation tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill = conv padding) -> shared-memory ring
+//   -> tcgen05.mma (one issuing thread, fp32 accumulators in TMEM, double buffered)
+//   -> tcgen05.ld epilogue (bias, bf16 rounding, BatchNorm batch statistics, NHWC / convT-scatter stores).
+//
+// Persistent, warp-specialised CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+//
+// Reference call sites replaced: unet/unet.py:16,19 (Conv2d 3x3 p1 forward, and its data gradient with the
+// flipped/transposed weight pack), unet/unet.py:59 (ConvTranspose2d k2 s2 forward / data gradient), and the
+// filter-gradient half of convolution_backward for both (tc_wgrad).
+//
+// Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * rows * K * N_total.
+#include <mutex>
+
+#include "conv_internal.cuh"
+#include "tc_common.cuh"
+
+namespace unetk {
+namespace tc {
+
+// =================================================================================================
+// host helpers
+// =================================================================================================
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_act_map(CUtensorMap* map, const unetk_tensor& t, int pw, int ph, int nb, int step, int oh, int ow) {
+  EncodeTiledFn enc = get_encode_fn();
+  UNETK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = 2;
+  char* base = static_cast<char*>(t.ptr) + ((int64_t)oh * t.w + ow) * t.ld * es;
+  cuuint64_t dims[4] = {(cuuint64_t)t.c, (cuuint64_t)(t.w / step), (cuuint64_t)(t.h / step), (cuuint64_t)t.n};
+  cuuint64_t strides[3] = {(cuuint64_t)step * t.ld * es, (cuuint64_t)step * t.w * t.ld * es,
+                           (cuuint64_t)t.h * t.w * t.ld * es};
+  cuuint32_t box[4] = {64, (cuuint32_t)pw, (cuuint32_t)ph, (cuuint32_t)nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation) failed with CUresult %d (dims %d,%d,%d,%d ld %d box %d,%d,%d)", (int)r,
+              t.c, t.w / step, t.h / step, t.n, t.ld, pw, ph, nb);
+    return UNETK_ERR_CUDA;
+  }
+  return UNETK_OK;
+}
+
+int make_mat_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  UNETK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)k * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(matrix) failed with CUresult %d (rows %lld k %lld box %d)", (int)r, (long long)rows,
+              (long long)k, box_rows);
+    return UNETK_ERR_CUDA;
+  }
+  return UNETK_OK;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+PixelTile choose_pixel_tile(int n, int h, int w) {
+  PixelTile t;
+  t.pw = pow2_floor(w) < 16 ? pow2_floor(w) : 16;
+  const int max_ph = 128 / t.pw;
+  t.ph = pow2_floor(h) < max_ph ? pow2_floor(h) : max_ph;
+  t.nb = 128 / (t.pw * t.ph);
+  t.tiles_w = (w + t.pw - 1) / t.pw;
+  t.tiles_h = (h + t.ph - 1) / t.ph;
+  t.tiles_n = (n + t.nb - 1) / t.nb;
+  return t;
+}
+
+// =================================================================================================
+// forward-family kernel: y[rows, N] = A[rows, K] * B[N, K]^T, both operands K-major in shared memory
+// =================================================================================================
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                  // bf16 elements per K step = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
+constexpr int kNumThreads = 256;
+constexpr int kMaxStatChannels = 1024;
+
+struct ConvParams {
+  CUtensorMap map_a[4];
+  CUtensorMap map_b;
+  int mode, taps, chunks_per_tap;
+  int pw, ph, nb, tiles_w, tiles_h;
+  int num_m_tiles, num_n_tiles;
+  int n, h, w;          // grid of the GEMM rows
+  __nv_bfloat16* y;
+  int yld, cout;        // cout = channels of y (mode 2: N_total = 4*cout)
+  const float* bias;
+  double* stat_sum;
+  double* stat_sumsq;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  // ring | stats (2 x 1024 floats) | barriers | tmem ptr
+  static constexpr int kStatsOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kStatsOff + 2 * kMaxStatChannels * 4;
+  static constexpr int kSmemBytes = kBarOff + (2 * kStages + 4) * 8 + 16 + 1024;  // + slack for 1024B alignment
+};
+
+// warp-level "transpose reduce": on return lane L holds sum over the 32 lanes of v[L]
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* stat_s1 = reinterpret_cast<float*>(smem + Cfg::kStatsOff);
+  float* stat_s2 = stat_s1 + kMaxStatChannels;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int ksteps = p.taps * p.chunks_per_tap;
+  const bool do_stats = p.stat_sum != nullptr;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_a[0]);
+    prefetch_tensormap(&p.map_b);
+    if (p.mode == 3) {
+      prefetch_tensormap(&p.map_a[1]);
+      prefetch_tensormap(&p.map_a[2]);
+      prefetch_tensormap(&p.map_a[3]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  if (do_stats)
+    for (int i = threadIdx.x; i < 2 * kMaxStatChannels; i += kNumThreads) stat_s1[i] = 0.f;
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
+        for (int s = 0; s < ksteps; ++s) {
+          const int t = s / p.chunks_per_tap, chunk = s % p.chunks_per_tap;
+          int dh = 0, dw = 0, mi = 0;
+          if (p.mode == 1) {
+            dh = t / 3 - 1;
+            dw = t % 3 - 1;
+          } else if (p.mode == 3) {
+            mi = t;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_4d(sa, &p.map_a[mi], &full_bar[stage], chunk * kBlockK, w0 + dw, h0 + dh, n0);
+          tma_load_2d(sb, &p.map_b, &full_bar[stage], s * kBlockK, n_tile * BLOCK_N);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int s = 0; s < ksteps; ++s) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t da = make_smem_desc(sa, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;  // TMEM lane quadrant
+    const int row = q * 32 + lane;
+    const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int x = tw * p.pw + pw_i, y = th * p.ph + ph_i, img = tn * p.nb + nb_i;
+      const bool valid = x < p.w && y < p.h && img < p.n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int col0 = n_tile * BLOCK_N;
+      // destination pixel
+      int64_t opix;
+      int ch0;
+      if (p.mode == 2) {
+        const int quad = col0 / p.cout;
+        ch0 = col0 % p.cout;
+        opix = ((int64_t)img * (2 * p.h) + 2 * y + (quad >> 1)) * (2 * p.w) + 2 * x + (quad & 1);
+      } else {
+        ch0 = col0;
+        opix = ((int64_t)img * p.h + y) * p.w + x;
+      }
+      __nv_bfloat16* dst = p.y + opix * p.yld + ch0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float f = __uint_as_float(r[j]);
+          if (p.bias) f += __ldg(p.bias + ch0 + c * 32 + j);
+          v[j] = f;
+        }
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        if (valid) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+        if (do_stats) {
+          // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
+          float s1[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = valid ? __uint_as_float(packed[j] << 16) : 0.f;
+            const float hi = valid ? __uint_as_float(packed[j] & 0xffff0000u) : 0.f;
+            s1[2 * j] = lo;
+            s1[2 * j + 1] = hi;
+            s2[2 * j] = lo * lo;
+            s2[2 * j + 1] = hi * hi;
+          }
+          const float t1 = warp_transpose_reduce(s1, lane);
+          const float t2 = warp_transpose_reduce(s2, lane);
+          atomicAdd(&stat_s1[ch0 + c * 32 + lane], t1);
+          atomicAdd(&stat_s2[ch0 + c * 32 + lane], t2);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (do_stats) {
+    for (int i = threadIdx.x; i < p.cout; i += kNumThreads) {
+      const float a = stat_s1[i], b = stat_s2[i];
+      if (a != 0.f || b != 0.f) {
+        atomicAdd(p.stat_sum + i, (double)a);
+        atomicAdd(p.stat_sumsq + i, (double)b);
+      }
+    }
+  }
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// =================================================================================================
+// weight-gradient kernel: dw[cu, t, cs] += sum_pixels U[p, cu] * S[gather(p, t), cs]
+// both operands MN-major in shared memory (rows = pixels = K, 64-channel slabs of 128 B)
+// =================================================================================================
+struct WgradParams {
+  CUtensorMap map_u;
+  CUtensorMap map_s[4];
+  int mode, taps;
+  int pw, ph, nb, tiles_w, tiles_h;
+  int num_ptiles;          // pixel tiles (K blocks of 128 pixels)
+  int ptiles_per_split, splits;
+  int cu_tiles, cs_tiles;  // output tiles of BM x BN
+  int cu, cs;
+  float* dw;
+};
+
+template <int BM_SLABS, int BN_SLABS>
+struct WgradCfg {
+  static constexpr int BLOCK_N = BN_SLABS * 64;
+  static constexpr int kUBytes = BM_SLABS * kABytes;
+  static constexpr int kSBytes = BN_SLABS * kABytes;
+  static constexpr int kStageBytes = kUBytes + kSBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kBarOff + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+template <int BM_SLABS, int BN_SLABS>
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BM_SLABS, BN_SLABS>;
+  constexpr int BLOCK_N = Cfg::BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item = (cu tile, cs tile, tap, split)
+  const int num_items = p.cu_tiles * p.cs_tiles * p.taps * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_u);
+    prefetch_tensormap(&p.map_s[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // item decoding shared by all roles: split fastest so that concurrently running CTAs share operand tiles in L2
+  auto decode = [&](int item, int& cu_t, int& cs_t, int& tap, int& split) {
+    split = item % p.splits;
+    int r = item / p.splits;
+    tap = r % p.taps;
+    r /= p.taps;
+    cs_t = r % p.cs_tiles;
+    cu_t = r / p.cs_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int cu_t, cs_t, tap, split;
+        decode(item, cu_t, cs_t, tap, split);
+        int dh = 0, dw = 0, mi = 0;
+        if (p.mode == 1) {
+          dh = tap / 3 - 1;
+          dw = tap % 3 - 1;
+        } else if (p.mode == 2) {
+          mi = tap;
+        }
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tw = pt % p.tiles_w, th = (pt / p.tiles_w) % p.tiles_h, tn = pt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* su = smem + stage * Cfg::kStageBytes;
+          uint8_t* ss = su + Cfg::kUBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+          for (int i = 0; i < BM_SLABS; ++i)
+            tma_load_4d(su + i * kABytes, &p.map_u, &full_bar[stage], (cu_t * BM_SLABS + i) * 64, w0, h0, n0);
+#pragma unroll
+          for (int i = 0; i < BN_SLABS; ++i)
+            tma_load_4d(ss + i * kABytes, &p.map_s[mi], &full_bar[stage], (cs_t * BN_SLABS + i) * 64, w0 + dw, h0 + dh, n0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 128 always; with a single 64-channel slab the descriptor's slab stride is 0 and rows 64..127 of the
+      // accumulator duplicate rows 0..63 (ignored by the epilogue)
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      constexpr uint32_t lbo_a = BM_SLABS == 2 ? kABytes : 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int cu_t, cs_t, tap, split;
+        decode(item, cu_t, cs_t, tap, split);
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t su = smem_u32(smem + stage * Cfg::kStageBytes);
+          // MN-major, 128B swizzle: 8 K-rows x 128 B atoms, SBO = 1024 (next 8 pixels), LBO = next 64-channel slab
+          const uint64_t da = make_smem_desc(su, lbo_a, 1024);
+          const uint64_t db = make_smem_desc(su + Cfg::kUBytes, kABytes, 1024);
+#pragma unroll
+          for (int k = 0; k < kTileM / 16; ++k) {
+            // 16 pixels = 16 rows of 128 B = 2048 bytes: +128 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int cu_t, cs_t, tap, split;
+      decode(item, cu_t, cs_t, tap, split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int cu_idx = cu_t * (BM_SLABS * 64) + row;
+      const bool valid = row < BM_SLABS * 64 && cu_idx < p.cu;
+      float* dst = p.dw + ((int64_t)cu_idx * p.taps + tap) * p.cs + cs_t * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(r[j]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <typename K>
+static int set_smem_attr(K kernel, int bytes) {
+  UNETK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return UNETK_OK;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const ConvParams& p, cudaStream_t stream) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N>, Cfg::kSmemBytes);
+  if (attr_rc) return attr_rc;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  tc_conv_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+template <int BM_SLABS, int BN_SLABS>
+static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BM_SLABS, BN_SLABS>;
+  static int attr_rc = set_smem_attr(tc_wgrad_kernel<BM_SLABS, BN_SLABS>, Cfg::kSmemBytes);
+  if (attr_rc) return attr_rc;
+  const int items = p.cu_tiles * p.cs_tiles * p.taps * p.splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  tc_wgrad_kernel<BM_SLABS, BN_SLABS><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+}  // namespace tc
+
+// =================================================================================================
+// dispatcher-facing entry points
+// =================================================================================================
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char** why) {
+  if (a->x.dtype != UNETK_BF16) { *why = "bf16 only"; return false; }
+  if (g.cin % 64 != 0) { *why = "Cin must be a multiple of 64"; return false; }
+  if (g.cout % 64 != 0) { *why = "Cout must be a multiple of 64"; return false; }
+  if (a->x.ld % 8 != 0 || a->y.ld % 8 != 0 || !aligned16(a->x.ptr) || !aligned16(a->y.ptr) || !aligned16(a->w)) {
+    *why = "pointers must be 16B aligned and pixel strides multiples of 8";
+    return false;
+  }
+  if (a->stat_sum && g.cout > tc::kMaxStatChannels) { *why = "statistics support at most 1024 channels"; return false; }
+  return true;
+}
+
+int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
+  using namespace tc;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  const PixelTile pt = choose_pixel_tile(g.rows_n, g.rows_h, g.rows_w);
+  int rc;
+  if (a->mode == 3) {
+    for (int t = 0; t < 4; ++t)
+      if ((rc = make_act_map(&p.map_a[t], a->x, pt.pw, pt.ph, pt.nb, 2, t >> 1, t & 1))) return rc;
+  } else {
+    if ((rc = make_act_map(&p.map_a[0], a->x, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+  }
+  // N tile: the widest of 256/128/64 that divides the channel count of one output slice
+  const int nslice = g.cout;  // mode 2: a tile must stay inside one (a,b) quadrant
+  const int block_n = nslice % 256 == 0 ? 256 : (nslice % 128 == 0 ? 128 : 64);
+  const int64_t ktotal = (int64_t)g.taps * g.cin;
+  if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, block_n))) return rc;
+  p.mode = a->mode;
+  p.taps = g.taps;
+  p.chunks_per_tap = g.cin / 64;
+  p.pw = pt.pw; p.ph = pt.ph; p.nb = pt.nb; p.tiles_w = pt.tiles_w; p.tiles_h = pt.tiles_h;
+  UNETK_REQUIRE(pt.num_tiles() * (g.cout_total / block_n) < (1LL << 31), "conv(tc): too many tiles");
+  p.num_m_tiles = (int)pt.num_tiles();
+  p.num_n_tiles = g.cout_total / block_n;
+  p.n = g.rows_n; p.h = g.rows_h; p.w = g.rows_w;
+  p.y = static_cast<__nv_bfloat16*>(a->y.ptr);
+  p.yld = a->y.ld;
+  p.cout = g.cout;
+  p.bias = a->bias;
+  p.stat_sum = a->stat_sum;
+  p.stat_sumsq = a->stat_sumsq;
+  if (block_n == 256) return launch_conv<256>(p, stream);
+  if (block_n == 128) return launch_conv<128>(p, stream);
+  return launch_conv<64>(p, stream);
+}
+
+bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
+  (void)taps;
+  if (a->u.dtype != UNETK_BF16) { *why = "bf16 only"; return false; }
+  if (a->u.c % 64 != 0 || a->s.c % 64 != 0) { *why = "channel counts must be multiples of 64"; return false; }
+  if (a->u.ld % 8 != 0 || a->s.ld % 8 != 0 || !aligned16(a->u.ptr) || !aligned16(a->s.ptr)) {
+    *why = "pointers must be 16B aligned and pixel strides multiples of 8";
+    return false;
+  }
+  return true;
+}
+
+int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
+  using namespace tc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  const PixelTile pt = choose_pixel_tile(a->u.n, a->u.h, a->u.w);
+  int rc;
+  if ((rc = make_act_map(&p.map_u, a->u, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+  if (a->mode == 2) {
+    for (int t = 0; t < 4; ++t)
+      if ((rc = make_act_map(&p.map_s[t], a->s, pt.pw, pt.ph, pt.nb, 2, t >> 1, t & 1))) return rc;
+  } else {
+    if ((rc = make_act_map(&p.map_s[0], a->s, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+  }
+  const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1;
+  const int bn_slabs = a->s.c % 128 == 0 ? 2 : 1;
+  p.mode = a->mode;
+  p.taps = taps;
+  p.pw = pt.pw; p.ph = pt.ph; p.nb = pt.nb; p.tiles_w = pt.tiles_w; p.tiles_h = pt.tiles_h;
+  UNETK_REQUIRE(pt.num_tiles() < (1LL << 30), "wgrad(tc): too many pixel tiles");
+  p.num_ptiles = (int)pt.num_tiles();
+  p.cu = a->u.c; p.cs = a->s.c;
+  p.cu_tiles = a->u.c / (64 * bm_slabs);
+  p.cs_tiles = a->s.c / (64 * bn_slabs);
+  const int64_t out_tiles = (int64_t)p.cu_tiles * p.cs_tiles * taps;
+  // split the pixel reduction until there are ~2 waves of work items, but keep >= 4 pixel tiles per item
+  int64_t splits = (2LL * sm_count() + out_tiles - 1) / out_tiles;
+  const int64_t max_splits = (p.num_ptiles + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.ptiles_per_split = (int)((p.num_ptiles + splits - 1) / splits);
+  p.splits = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
+  p.dw = a->dw;
+  if (bm_slabs == 2 && bn_slabs == 2) return launch_wgrad<2, 2>(p, stream);
+  if (bm_slabs == 2 && bn_slabs == 1) return launch_wgrad<2, 1>(p, stream);
+  if (bm_slabs == 1 && bn_slabs == 2) return launch_wgrad<1, 2>(p, stream);
+  return launch_wgrad<1, 1>(p, stream);
+}
+
+}  // namespace unetk

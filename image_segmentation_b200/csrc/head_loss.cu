@@ -1,0 +1,426 @@
+// 1x1 classifier head, fused weighted Dice + cross-entropy loss, and argmax/confusion-count metrics.
+//
+// Reference call sites replaced:
+//   unet/unet.py:91                      nn.Conv2d(64, dout, 1) forward/backward
+//   utils/weighted_loss.py:36-98,163     softmax, scatter_ one-hot, Dice sums, clip, weighted mean, cross_entropy
+//   utils/MetricsHistory.py:65-86        argmax, one_hot x2, four masked sums, four .cpu() copies per image
+//
+// Roofline: HBM.  Algorithmic bytes per pixel:
+//   head fprop   cin*sizeof(T) + 4*dout                 head bwd   2*cin*sizeof(T) (two passes) + cin*sizeof(T) + 4*dout
+//   loss fwd     4*C + 8                                loss bwd   8*C + 8
+//   metrics      4*C + 8
+#include "common.cuh"
+
+namespace unetk {
+
+constexpr int kMaxClasses = 8;
+constexpr int kMaxHeadCin = 256;
+
+// ------------------------------------------------------------------------------------------------
+// head
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_fprop_kernel(const T* __restrict__ a, int ld, int cin, int64_t npix,
+                                                         int64_t hw, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int dout,
+                                                         float* __restrict__ logits) {
+  __shared__ float ws[kMaxClasses * kMaxHeadCin];
+  __shared__ float bs[kMaxClasses];
+  for (int i = threadIdx.x; i < dout * cin; i += blockDim.x) ws[i] = w[i];
+  if (threadIdx.x < dout) bs[threadIdx.x] = b ? b[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    float acc[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) acc[k] = k < dout ? bs[k] : 0.f;
+    for (int g = 0; g < cin / 8; ++g) {
+      float v[8];
+      load8(a + p * ld + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        if (k < dout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k] = fmaf(v[j], ws[k * cin + g * 8 + j], acc[k]);
+        }
+      }
+    }
+    const int64_t img = p / hw, off = p % hw;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < dout) logits[(img * dout + k) * hw + off] = acc[k];
+  }
+}
+
+// da[p, ci] = sum_k dl[p,k] w[k,ci];  db[k] += sum_p dl[p,k]
+template <typename T>
+__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dl, int64_t npix, int64_t hw,
+                                                            const float* __restrict__ w, int dout, int cin,
+                                                            T* __restrict__ da, int ld, float* __restrict__ db) {
+  __shared__ float ws[kMaxClasses * kMaxHeadCin];
+  for (int i = threadIdx.x; i < dout * cin; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  float bsum[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) bsum[k] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t img = p / hw, off = p % hw;
+    float g[kMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      g[k] = k < dout ? dl[(img * dout + k) * hw + off] : 0.f;
+      bsum[k] += g[k];
+    }
+    for (int gidx = 0; gidx < cin / 8; ++gidx) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxClasses; ++k) {
+        if (k < dout) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(g[k], ws[k * cin + gidx * 8 + j], o[j]);
+        }
+      }
+      store8(da + p * ld + gidx * 8, o);
+    }
+  }
+  if (db) {
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < dout) {
+        const float s = warp_sum(bsum[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(db + k, s);
+      }
+    }
+  }
+}
+
+// dw[k, ci] += sum_p dl[p,k] a[p,ci]; block = lanes x cin threads
+template <typename T>
+__global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __restrict__ dl, const T* __restrict__ a,
+                                                              int ld, int cin, int64_t npix, int64_t hw, int dout,
+                                                              int pix_per_block, float* __restrict__ dw) {
+  __shared__ float red[256 * kMaxClasses];
+  const int lanes = blockDim.x / cin;
+  const int ci = threadIdx.x % cin, lane = threadIdx.x / cin;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p1 = min(p0 + (int64_t)pix_per_block, npix);
+  float acc[kMaxClasses];
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
+  for (int64_t p = p0 + lane; p < p1; p += lanes) {
+    const float av = to_f(a[p * ld + ci]);
+    const int64_t img = p / hw, off = p % hw;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < dout) acc[k] = fmaf(dl[(img * dout + k) * hw + off], av, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) red[k * 256 + threadIdx.x] = acc[k];
+  __syncthreads();
+  if (lane == 0) {
+    for (int k = 0; k < dout; ++k) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[k * 256 + l * cin + ci];
+      atomicAdd(dw + k * cin + ci, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dice + CE
+// ------------------------------------------------------------------------------------------------
+struct Softmax {
+  float p[kMaxClasses];
+  float logp_y;
+};
+
+__device__ __forceinline__ void pixel_softmax(const float* __restrict__ logits, int64_t base, int64_t hw, int c, int y,
+                                              Softmax& s) {
+  float x[kMaxClasses];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    x[k] = k < c ? logits[base + k * hw] : -INFINITY;
+    m = fmaxf(m, x[k]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    s.p[k] = k < c ? expf(x[k] - m) : 0.f;
+    sum += s.p[k];
+  }
+  const float inv = 1.f / sum;
+  float xy = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    s.p[k] *= inv;
+    if (k == y) xy = x[k];
+  }
+  s.logp_y = xy - m - logf(sum);
+}
+
+__global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args a) {
+  const int c = a.c;
+  const int64_t hw = (int64_t)a.h * a.w, npix = (int64_t)a.n * hw;
+  float I[kMaxClasses], P[kMaxClasses], G[kMaxClasses], cen = 0.f, ced = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) I[k] = P[k] = G[k] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t yl = a.target[p];
+    if (yl < 0 || yl >= c) {
+      atomicOr(a.status, 1);
+      continue;
+    }
+    const int y = (int)yl;
+    const int64_t img = p / hw, off = p % hw;
+    Softmax s;
+    pixel_softmax(a.logits, img * c * hw + off, hw, c, y, s);
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      // utils/weighted_loss.py:50-58: with C == 1 the reference uses y.float() itself as the "one-hot"
+      const float oh = c == 1 ? (float)y : (k == y ? 1.f : 0.f);
+      if (k < c) {
+        P[k] += s.p[k];
+        I[k] = fmaf(s.p[k], oh, I[k]);
+        G[k] += oh;
+      }
+    }
+    const bool valid = !(a.has_ignore && yl == a.ignore_index);
+    if (valid) {
+      const float wy = a.class_weights ? a.class_weights[y] : 1.f;
+      cen = fmaf(-s.logp_y, wy, cen);
+      ced += wy;
+    }
+  }
+  __shared__ float red[8][3 * kMaxClasses + 2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < kMaxClasses; ++k) {
+    const float i = warp_sum(I[k]), pp = warp_sum(P[k]), g = warp_sum(G[k]);
+    if (lane == 0) {
+      red[warp][k] = i;
+      red[warp][kMaxClasses + k] = pp;
+      red[warp][2 * kMaxClasses + k] = g;
+    }
+  }
+  cen = warp_sum(cen);
+  ced = warp_sum(ced);
+  if (lane == 0) {
+    red[warp][3 * kMaxClasses] = cen;
+    red[warp][3 * kMaxClasses + 1] = ced;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * kMaxClasses + 2) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    const int q = threadIdx.x / kMaxClasses, k = threadIdx.x % kMaxClasses;
+    if (threadIdx.x >= 3 * kMaxClasses)
+      atomicAdd(a.accum + 3 * c + (threadIdx.x - 3 * kMaxClasses), (double)s);
+    else if (k < c)
+      atomicAdd(a.accum + q * c + k, (double)s);
+  }
+}
+
+__global__ void dice_ce_finalize_kernel(unetk_dice_ce_args a) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int c = a.c;
+  double wsum = 0.0;
+  for (int k = 0; k < c; ++k) {
+    const bool valid = !(a.has_ignore && a.ignore_index >= 0 && a.ignore_index < c && k == a.ignore_index);
+    if (valid) wsum += a.class_weights ? (double)a.class_weights[k] : 1.0;
+  }
+  if (a.class_weights && wsum < 1e-8) wsum = 1e-8;
+  double dice = 0.0;
+  for (int k = 0; k < c; ++k) {
+    const bool valid = !(a.has_ignore && a.ignore_index >= 0 && a.ignore_index < c && k == a.ignore_index);
+    const double I = a.accum[k], P = a.accum[c + k], G = a.accum[2 * c + k];
+    const double den = P + G + (double)a.smooth;
+    const double den_c = den < 1e-8 ? 1e-8 : den;
+    const double dc = (2.0 * I + (double)a.smooth) / den_c;
+    const double ak = valid ? (a.class_weights ? (double)a.class_weights[k] : 1.0) / wsum : 0.0;
+    dice += ak * dc;
+    a.coef[k] = (float)((double)a.dice_weight * ak / den_c);
+    a.coef[c + k] = den < 1e-8 ? 0.f : (float)dc;
+  }
+  const double ce_num = a.accum[3 * c], ce_den = a.accum[3 * c + 1];
+  const double ce = ce_num / ce_den;  // NaN if every pixel is ignored, like torch
+  a.coef[2 * c] = (float)((double)a.ce_weight / ce_den);
+  a.loss[0] = (float)((double)a.dice_weight * (-dice) + (double)a.ce_weight * ce);
+}
+
+__global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) {
+  const int c = a.c;
+  const int64_t hw = (int64_t)a.h * a.w, npix = (int64_t)a.n * hw;
+  __shared__ float coef[2 * kMaxClasses + 1];
+  if (threadIdx.x < 2 * c + 1) coef[threadIdx.x] = a.coef[threadIdx.x];
+  __syncthreads();
+  const float go = a.grad_out ? a.grad_out[0] : 1.f;
+  const float ce_scale = coef[2 * c];
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t yl = a.target[p];
+    const int64_t img = p / hw, off = p % hw;
+    const int64_t base = img * c * hw + off;
+    if (yl < 0 || yl >= c) {
+      for (int k = 0; k < c; ++k) a.dlogits[base + k * hw] = 0.f;
+      continue;
+    }
+    const int y = (int)yl;
+    Softmax s;
+    pixel_softmax(a.logits, base, hw, c, y, s);
+    float g[kMaxClasses], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      const float oh = c == 1 ? (float)y : (k == y ? 1.f : 0.f);
+      g[k] = k < c ? -coef[k] * (2.f * oh - coef[c + k]) : 0.f;
+      dot = fmaf(s.p[k], g[k], dot);
+    }
+    const bool valid = !(a.has_ignore && yl == a.ignore_index);
+    const float wy = valid ? (a.class_weights ? a.class_weights[y] : 1.f) * ce_scale : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k) {
+      if (k < c) {
+        const float gx = s.p[k] * (g[k] - dot) + wy * (s.p[k] - (k == y ? 1.f : 0.f));
+        a.dlogits[base + k * hw] = gx * go;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// metrics
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    argmax_confusion_kernel(const float* __restrict__ pred, const int64_t* __restrict__ label, int n, int c, int64_t hw,
+                            unsigned long long* __restrict__ counts, uint8_t* __restrict__ argmax_out,
+                            int* __restrict__ status) {
+  __shared__ unsigned int cm[kMaxClasses * kMaxClasses];
+  for (int i = threadIdx.x; i < kMaxClasses * kMaxClasses; i += blockDim.x) cm[i] = 0;
+  __syncthreads();
+  const int64_t npix = (int64_t)n * hw;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t img = p / hw, off = p % hw;
+    const float* px = pred + img * c * hw + off;
+    float best = px[0];
+    int arg = 0;
+    for (int k = 1; k < c; ++k) {
+      const float v = px[k * hw];
+      // torch.argmax: first maximum wins, NaN counts as the largest value
+      if (v > best || (isnan(v) && !isnan(best))) {
+        best = v;
+        arg = k;
+      }
+    }
+    if (argmax_out) argmax_out[p] = (uint8_t)arg;
+    const int64_t yl = label[p];
+    if (yl < 0 || yl >= c) {
+      atomicOr(status, 1);
+      continue;
+    }
+    atomicAdd(&cm[(int)yl * kMaxClasses + arg], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < c) {
+    const int k = threadIdx.x;
+    unsigned long long tp = 0, fp = 0, fn = 0, total = 0;
+    for (int l = 0; l < c; ++l)
+      for (int q = 0; q < c; ++q) {
+        const unsigned long long v = cm[l * kMaxClasses + q];
+        total += v;
+        if (l == k && q == k) tp += v;
+        else if (q == k) fp += v;
+        else if (l == k) fn += v;
+      }
+    const unsigned long long tn = total - tp - fp - fn;
+    if (tp) atomicAdd(counts + 0 * c + k, tp);
+    if (fp) atomicAdd(counts + 1 * c + k, fp);
+    if (fn) atomicAdd(counts + 2 * c + k, fn);
+    if (tn) atomicAdd(counts + 3 * c + k, tn);
+  }
+}
+
+static int grid_pixels(int64_t npix, int per_thread) {
+  int64_t blocks = (npix + 256LL * per_thread - 1) / (256LL * per_thread);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks > 0 ? blocks : 1);
+}
+
+}  // namespace unetk
+
+using namespace unetk;
+
+extern "C" {
+
+int unetk_head_fprop(const unetk_tensor* a, const float* w, const float* b, int32_t dout, float* logits_nchw,
+                     void* stream) {
+  UNETK_REQUIRE(a && w && logits_nchw, "head_fprop: null argument");
+  UNETK_REQUIRE(tensor_ok(*a) && vec8_ok(*a), "head_fprop: a must be NHWC with c%%8==0");
+  UNETK_REQUIRE(dout >= 1 && dout <= kMaxClasses && a->c <= kMaxHeadCin, "head_fprop: dout<=8, cin<=256 supported");
+  const int64_t npix = pixels(*a), hw = (int64_t)a->h * a->w;
+  UNETK_DISPATCH_DTYPE(a->dtype, T, {
+    head_fprop_kernel<T><<<grid_pixels(npix, 1), 256, 0, (cudaStream_t)stream>>>((const T*)a->ptr, a->ld, a->c, npix, hw, w, b, dout, logits_nchw);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float* w, int32_t dout, const unetk_tensor* da,
+                   float* dw, float* db, void* stream) {
+  UNETK_REQUIRE(dlogits_nchw && a && w && da && dw, "head_bwd: null argument");
+  UNETK_REQUIRE(tensor_ok(*a) && vec8_ok(*a) && tensor_ok(*da) && vec8_ok(*da), "head_bwd: bad tensor");
+  UNETK_REQUIRE(da->dtype == a->dtype && da->n == a->n && da->h == a->h && da->w == a->w && da->c == a->c,
+                "head_bwd: da must match a");
+  UNETK_REQUIRE(dout >= 1 && dout <= kMaxClasses && a->c <= kMaxHeadCin && (256 % a->c) == 0,
+                "head_bwd: dout<=8 and cin dividing 256 supported");
+  const int64_t npix = pixels(*a), hw = (int64_t)a->h * a->w;
+  const int lanes = 256 / a->c;
+  const int ppb = lanes * 64;
+  const int64_t wblocks = (npix + ppb - 1) / ppb;
+  UNETK_REQUIRE(wblocks < (1LL << 31), "head_bwd: too many pixels");
+  UNETK_DISPATCH_DTYPE(a->dtype, T, {
+    head_bwd_data_kernel<T><<<grid_pixels(npix, 1), 256, 0, (cudaStream_t)stream>>>(dlogits_nchw, npix, hw, w, dout, a->c, (T*)da->ptr, da->ld, db);
+    head_bwd_weight_kernel<T><<<(unsigned)wblocks, 256, 0, (cudaStream_t)stream>>>(dlogits_nchw, (const T*)a->ptr, a->ld, a->c, npix, hw, dout, ppb, dw);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+static int check_loss(const unetk_dice_ce_args* a) {
+  UNETK_REQUIRE(a && a->logits && a->target && a->coef && a->status, "dice_ce: null argument");
+  UNETK_REQUIRE(a->n > 0 && a->h > 0 && a->w > 0 && a->c >= 1 && a->c <= kMaxClasses, "dice_ce: 1..8 classes supported");
+  return UNETK_OK;
+}
+
+int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream) {
+  int rc = check_loss(a);
+  if (rc) return rc;
+  UNETK_REQUIRE(a->accum && a->loss, "dice_ce_fwd: null accum/loss");
+  const int64_t npix = (int64_t)a->n * a->h * a->w;
+  dice_ce_reduce_kernel<<<grid_pixels(npix, 4), 256, 0, (cudaStream_t)stream>>>(*a);
+  dice_ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream) {
+  int rc = check_loss(a);
+  if (rc) return rc;
+  UNETK_REQUIRE(a->dlogits, "dice_ce_bwd: null dlogits");
+  const int64_t npix = (int64_t)a->n * a->h * a->w;
+  dice_ce_bwd_kernel<<<grid_pixels(npix, 2), 256, 0, (cudaStream_t)stream>>>(*a);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h, int32_t w,
+                           int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream) {
+  UNETK_REQUIRE(pred && label && counts && status, "argmax_confusion: null argument");
+  UNETK_REQUIRE(n > 0 && h > 0 && w > 0 && c >= 1 && c <= kMaxClasses, "argmax_confusion: 1..8 classes supported");
+  const int64_t hw = (int64_t)h * w;
+  argmax_confusion_kernel<<<grid_pixels((int64_t)n * hw, 4), 256, 0, (cudaStream_t)stream>>>(
+      pred, label, n, c, hw, reinterpret_cast<unsigned long long*>(counts), argmax_out, status);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+}

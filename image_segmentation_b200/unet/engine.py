@@ -1,0 +1,440 @@
+"""Whole-network forward/backward of the U-Net over libunetk.so (NHWC, bf16 or fp32 activations).
+
+The reference runs ``unet.forward`` (unet/unet.py:93-105) as ~90 ATen calls and lets autograd replay
+~150 more.  Here one ``torch.autograd.Function`` owns the complete pass: it packs the fp32
+``nn.Parameter`` tensors into K-major operand layouts, walks the 23 contraction layers through the
+C ABI (conv3x3 / ConvTranspose2d / 1x1 head), keeps BatchNorm + ReLU + MaxPool as fused bandwidth
+kernels around them, writes skip connections and up-sampled maps straight into one concat buffer
+(the ``torch.cat`` at unet/unet.py:63 becomes a channel-slice view), and returns parameter gradients
+in PyTorch's own layouts so that ``optimizer.step()`` / gradient accumulation (utils/training.py:49-56)
+work unchanged.
+
+Host code is plumbing: PyTorch allocates, this file sequences launches on the current stream.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from .. import _lib as L
+
+ENC_CH = (64, 128, 256, 512, 1024)
+BN_EPS_DEFAULT = 1e-5
+
+
+def _dtype_of(precision: str):
+    if precision == "bf16":
+        return torch.bfloat16
+    if precision == "fp32":
+        return torch.float32
+    raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+
+
+class _ConvBN:
+    """One conv3x3 -> BatchNorm -> ReLU layer: parameter holders, operand packs and activations."""
+
+    def __init__(self, name, conv, bn, cin, cout, h, w, first):
+        self.name, self.conv, self.bn = name, conv, bn
+        self.cin, self.cout, self.h, self.w, self.first = cin, cout, h, w, first
+        self.kin = cin  # channels of the gathered operand (im2col width for the first layer)
+        self.src = None      # input activation view [N,h,w,kin]
+        self.z = None        # raw conv output
+        self.a = None        # activated output view
+        self.pooled = None   # optional max-pooled output
+        self.wf = self.wd = None
+        self.dz = None       # gradient wrt z
+        self.g_in = None     # where the data gradient (wrt src) is written; None for the first layer
+
+
+class _ConvT:
+    def __init__(self, name, mod, cin, cout, h, w):
+        self.name, self.mod, self.cin, self.cout, self.h, self.w = name, mod, cin, cout, h, w
+        self.src = None   # [N,h,w,cin]
+        self.out = None   # view [N,2h,2w,cout] inside the concat buffer
+        self.wf = self.wd = None
+        self.g_out = None  # gradient wrt out (view of dcat)
+        self.g_in = None   # gradient wrt src
+
+
+class UNetPlan:
+    """Device buffers + launch sequence for one (N, H, W, din, dout, precision) problem."""
+
+    def __init__(self, model, n, h, w, precision, device):
+        if h % 16 or w % 16:
+            # the reference fails in torch.cat (unet/unet.py:63) for such sizes
+            raise ValueError(f"U-Net input height/width must be multiples of 16, got {h}x{w}")
+        self.model, self.n, self.h, self.w = model, n, h, w
+        self.precision, self.device = precision, device
+        self.dt = _dtype_of(precision)
+        self.din, self.dout = model.din, model.dout
+        self.busy = False
+        self.generation = 0
+        self.algo = L.ALGO_AUTO
+        self._pack_versions = None
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _act(self, n, h, w, c):
+        return torch.empty((n, h, w, c), dtype=self.dt, device=self.device)
+
+    def _build(self):
+        m, n, dev, dt = self.model, self.n, self.device, self.dt
+        H, W = self.h, self.w
+        self.kpad = ((9 * self.din + 63) // 64) * 64
+        self.xcol = self._act(n, H, W, self.kpad)
+        hs = [H >> i for i in range(5)]
+        ws = [W >> i for i in range(5)]
+        self.cat = [self._act(n, hs[l], ws[l], 2 * ENC_CH[l]) for l in range(4)]
+        self.dcat = [None] * 4
+        self.layers: List[_ConvBN] = []
+        self.convts: List[_ConvT] = []
+
+        def dc_modules(block):
+            seq = block.doubleConvReLU
+            return (seq[0], seq[1]), (seq[3], seq[4])
+
+        # ---- encoder ----
+        enc_blocks = [m.down1, m.down2.maxpool_doubleConv[1], m.down3.maxpool_doubleConv[1],
+                      m.down4.maxpool_doubleConv[1], m.down5.maxpool_doubleConv[1]]
+        enc_names = ["down1", "down2", "down3", "down4", "down5"]
+        prev = self.xcol
+        self.enc: List[List[_ConvBN]] = []
+        for l in range(5):
+            c = ENC_CH[l]
+            cin = self.din if l == 0 else ENC_CH[l - 1]
+            (c1, b1), (c2, b2) = dc_modules(enc_blocks[l])
+            l1 = _ConvBN(enc_names[l] + ".c1", c1, b1, cin, c, hs[l], ws[l], first=(l == 0))
+            if l == 0:
+                l1.kin = self.kpad
+            l1.src = prev
+            l1.z = self._act(n, hs[l], ws[l], c)
+            l1.a = self._act(n, hs[l], ws[l], c)
+            l2 = _ConvBN(enc_names[l] + ".c2", c2, b2, c, c, hs[l], ws[l], first=False)
+            l2.src = l1.a
+            l2.z = self._act(n, hs[l], ws[l], c)
+            if l < 4:
+                l2.a = self.cat[l][..., :c]
+                l2.pooled = self._act(n, hs[l + 1], ws[l + 1], c)
+                prev = l2.pooled
+            else:
+                l2.a = self._act(n, hs[l], ws[l], c)
+                prev = l2.a
+            self.enc.append([l1, l2])
+            self.layers += [l1, l2]
+        # ---- decoder (up1 works at level index 3, up4 at level index 0) ----
+        ups = [m.up1, m.up2, m.up3, m.up4]
+        self.dec: List[List[_ConvBN]] = []
+        for i, up in enumerate(ups):
+            l = 3 - i
+            c = ENC_CH[l]
+            ct = _ConvT(f"up{i + 1}.upsample", up.upsample, 2 * c, c, hs[l + 1], ws[l + 1])
+            ct.src = prev
+            ct.out = self.cat[l][..., c:]
+            self.convts.append(ct)
+            (c1, b1), (c2, b2) = dc_modules(up.doubleConv)
+            l1 = _ConvBN(f"up{i + 1}.c1", c1, b1, 2 * c, c, hs[l], ws[l], first=False)
+            l1.src = self.cat[l]
+            l1.z = self._act(n, hs[l], ws[l], c)
+            l1.a = self._act(n, hs[l], ws[l], c)
+            l2 = _ConvBN(f"up{i + 1}.c2", c2, b2, c, c, hs[l], ws[l], first=False)
+            l2.src = l1.a
+            l2.z = self._act(n, hs[l], ws[l], c)
+            l2.a = self._act(n, hs[l], ws[l], c)
+            prev = l2.a
+            self.dec.append([l1, l2])
+            self.layers += [l1, l2]
+        self.head_in = prev
+
+        # ---- per-channel scratch: fp64 accumulators (zeroed once per pass) and fp32 vectors ----
+        tot_c = sum(l.cout for l in self.layers)
+        self.acc64 = torch.zeros(4 * tot_c, dtype=torch.float64, device=dev)  # sum, sumsq, bwd s1, s2
+        self.vec32 = torch.empty(4 * tot_c, dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
+        off = 0
+        for l in self.layers:
+            c = l.cout
+            l.stat_sum = self.acc64[off:off + c]
+            l.stat_sumsq = self.acc64[tot_c + off:tot_c + off + c]
+            l.scale = self.vec32[off:off + c]
+            l.shift = self.vec32[tot_c + off:tot_c + off + c]
+            l.mean = self.vec32[2 * tot_c + off:2 * tot_c + off + c]
+            l.invstd = self.vec32[3 * tot_c + off:3 * tot_c + off + c]
+            off += c
+        self._tot_c = tot_c
+        # backward reduction sums [2][C] per layer, contiguous per layer
+        self.bwd64 = torch.zeros(2 * tot_c, dtype=torch.float64, device=dev)
+        off = 0
+        for l in self.layers:
+            l.bwd_sums = self.bwd64[off:off + 2 * l.cout]
+            off += 2 * l.cout
+
+        # ---- operand packs ----
+        for l in self.layers:
+            if l.first:
+                l.wf = torch.zeros((l.cout, self.kpad), dtype=dt, device=dev)
+            else:
+                l.wf = torch.empty((l.cout, 9, l.cin), dtype=dt, device=dev)
+                l.wd = torch.empty((l.cin, 9, l.cout), dtype=dt, device=dev)
+        for ct in self.convts:
+            ct.wf = torch.empty((4 * ct.cout, ct.cin), dtype=dt, device=dev)
+            ct.wd = torch.empty((ct.cin, 4, ct.cout), dtype=dt, device=dev)
+
+        self._bwd_ready = False
+
+    # ------------------------------------------------------------------------------------------
+    def _build_backward(self):
+        """Gradient buffers are only allocated when a backward pass is actually requested."""
+        n = self.n
+        for l in range(4):
+            c = ENC_CH[l]
+            self.dcat[l] = self._act(n, self.h >> l, self.w >> l, 2 * c)
+        for l in self.layers:
+            l.dz = torch.empty_like(l.z)
+        # data-gradient destinations
+        for lvl in range(5):
+            l1, l2 = self.enc[lvl]
+            l2.g_in = torch.empty_like(l1.a)          # grad wrt l1.a
+            l1.g_in = None if lvl == 0 else torch.empty_like(self.enc[lvl - 1][1].pooled)  # grad wrt pooled input
+        for i in range(4):
+            lvl = 3 - i
+            l1, l2 = self.dec[i]
+            l2.g_in = torch.empty_like(l1.a)
+            l1.g_in = self.dcat[lvl]
+            ct = self.convts[i]
+            ct.g_out = self.dcat[lvl][..., ENC_CH[lvl]:]
+            ct.g_in = torch.empty_like(ct.src)
+        self.g_head_in = torch.empty_like(self.head_in)
+        # flat layout of parameter gradients / weight-gradient workspaces in backward completion order
+        self.grad_order: List[torch.nn.Parameter] = []
+        m = self.model
+        self.grad_order += [m.output.weight, m.output.bias]
+        seq = []
+        for i in (3, 2, 1, 0):                       # up4 ... up1
+            l1, l2 = self.dec[i]
+            seq += [l2, l1, self.convts[i]]
+        for lvl in (4, 3, 2, 1, 0):
+            l1, l2 = self.enc[lvl]
+            seq += [l2, l1]
+        self.bwd_seq = seq
+        for item in seq:
+            if isinstance(item, _ConvBN):
+                self.grad_order += [item.conv.weight, item.conv.bias, item.bn.weight, item.bn.bias]
+            else:
+                self.grad_order += [item.mod.weight, item.mod.bias]
+        sizes = [p.numel() for p in self.grad_order]
+        self.grad_offsets = [0]
+        for s in sizes:
+            self.grad_offsets.append(self.grad_offsets[-1] + s)
+        self.grad_total = self.grad_offsets[-1]
+        # fp32 weight-gradient workspaces in operand layout ([Cu][taps][Cs])
+        ws_sizes = []
+        for item in seq:
+            if isinstance(item, _ConvBN):
+                ws_sizes.append(item.cout * (self.kpad if item.first else 9 * item.cin))
+            else:
+                ws_sizes.append(item.cin * 4 * item.cout)
+        self.ws_total = sum(ws_sizes)
+        self.ws = torch.empty(self.ws_total, dtype=torch.float32, device=self.device)
+        off = 0
+        for item, s in zip(seq, ws_sizes):
+            item.ws = self.ws[off:off + s]
+            off += s
+        self._bwd_ready = True
+
+    # ------------------------------------------------------------------------------------------
+    def pack_weights(self):
+        """fp32 OIHW / IOHW parameters -> K-major operand packs (only when a parameter changed)."""
+        versions = tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
+        if versions == self._pack_versions:
+            return
+        es = 2 if self.dt == torch.bfloat16 else 4
+        for l in self.layers:
+            w = l.conv.weight.detach()
+            co, ci = l.cout, l.cin
+            if l.first:
+                # [co][ci][t] -> [co][t*din + ci] (zero padded to kpad)
+                L.permute3(w, l.wf, (co, ci, 9), (ci * 9, 9, 1), (self.kpad, 1, ci))
+            else:
+                L.permute3(w, l.wf, (co, ci, 9), (ci * 9, 9, 1), (9 * ci, 1, ci))
+                # data-gradient pack: [ci][8 - t][co]  (flipped taps, transposed channels)
+                L.check(L.lib().unetk_permute3(w.data_ptr(), l.wd.data_ptr() + 8 * co * es, L._DTYPES[self.dt], co, ci, 9,
+                                               ci * 9, 9, 1, 1, 9 * co, -co, L.stream_ptr()))
+        for ct in self.convts:
+            w = ct.mod.weight.detach()   # [ci][co][2][2]
+            ci, co = ct.cin, ct.cout
+            L.permute3(w, ct.wf, (ci, co, 4), (co * 4, 4, 1), (1, ci, co * ci))      # [(ab)*co + co][ci]
+            L.permute3(w, ct.wd, (ci, co, 4), (co * 4, 4, 1), (4 * co, 1, co))       # [ci][(ab)][co]
+        self._pack_versions = versions
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        m = self.model
+        self.generation += 1
+        self.training_pass = training
+        self.pack_weights()
+        if training:
+            self.acc64.zero_()
+        L.im2col3x3_first(x, self.xcol)
+        n = self.n
+
+        def conv_bn(l: _ConvBN):
+            count = n * l.h * l.w
+            L.conv(l.src, l.wf, l.z, L.MODE_1X1 if l.first else L.MODE_3X3,
+                   stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
+                   algo=self.algo)
+            bn = l.bn
+            momentum = bn.momentum if bn.momentum is not None else 0.1
+            track = bn.track_running_stats and bn.running_mean is not None
+            L.bn_finalize(l.stat_sum, l.stat_sumsq, count, l.cout, training, bn.weight, bn.bias, l.conv.bias,
+                          bn.running_mean if track else None, bn.running_var if track else None,
+                          bn.num_batches_tracked if (track and training) else None,
+                          momentum, bn.eps, l.scale, l.shift, l.mean, l.invstd)
+            L.bn_relu_apply(l.z, l.scale, l.shift, l.a, l.pooled)
+
+        for lvl in range(5):
+            conv_bn(self.enc[lvl][0])
+            conv_bn(self.enc[lvl][1])
+        for i in range(4):
+            ct = self.convts[i]
+            L.conv(ct.src, ct.wf, ct.out, L.MODE_CONVT, bias=ct.mod.bias, algo=self.algo)
+            conv_bn(self.dec[i][0])
+            conv_bn(self.dec[i][1])
+        logits = torch.empty((n, self.dout, self.h, self.w), dtype=torch.float32, device=self.device)
+        L.head_fprop(self.head_in, m.output.weight, m.output.bias, self.dout, logits)
+        return logits
+
+    # ------------------------------------------------------------------------------------------
+    def backward(self, dlogits: torch.Tensor, bucket_hook: Optional[Callable] = None) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        """Returns {parameter: gradient} with gradients being views of one freshly allocated flat buffer."""
+        if not self.training_pass:
+            raise RuntimeError("backward through an eval-mode (running statistics) forward is not supported; "
+                               "call model.train() before the forward pass")
+        if not self._bwd_ready:
+            self._build_backward()
+        m = self.model
+        flat = torch.zeros(self.grad_total, dtype=torch.float32, device=self.device)
+        g = {}
+        for p, o0, o1 in zip(self.grad_order, self.grad_offsets[:-1], self.grad_offsets[1:]):
+            g[p] = flat[o0:o1].view(p.shape)
+        self.ws.zero_()
+        self.bwd64.zero_()
+        self.flat_grad = flat
+        dlogits = dlogits.contiguous()
+
+        L.head_bwd(dlogits, self.head_in, m.output.weight, self.dout, self.g_head_in, g[m.output.weight], g[m.output.bias])
+        if bucket_hook:
+            bucket_hook(self, self.grad_offsets[2])
+
+        def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
+            L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias])
+            if l.first:
+                L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo)
+                L.permute3(l.ws, g[l.conv.weight], (l.cout, l.cin, 9), (self.kpad, 1, l.cin), (l.cin * 9, 9, 1))
+            else:
+                L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo)
+                L.permute3(l.ws, g[l.conv.weight], (l.cout, l.cin, 9), (9 * l.cin, 1, l.cin), (l.cin * 9, 9, 1))
+                L.conv(l.dz, l.wd, l.g_in, L.MODE_3X3, algo=self.algo)
+            # conv bias in front of train-mode BN: its gradient is identically zero (flat buffer is zeroed)
+
+        grad_a2 = self.g_head_in
+        pos = 2
+        for i in (3, 2, 1, 0):
+            lvl = 3 - i
+            l1, l2 = self.dec[i]
+            conv_bn_bwd(l2, grad_a2)
+            conv_bn_bwd(l1, l2.g_in)
+            ct = self.convts[i]
+            L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
+            L.permute3(ct.ws, g[ct.mod.weight], (ct.cin, ct.cout, 4), (4 * ct.cout, 1, ct.cout), (ct.cout * 4, 4, 1))
+            L.channel_sum(ct.g_out, g[ct.mod.bias])
+            L.conv(ct.g_out, ct.wd, ct.g_in, L.MODE_CONVT_GATHER, algo=self.algo)
+            grad_a2 = ct.g_in
+            pos += 10
+            if bucket_hook:
+                bucket_hook(self, self.grad_offsets[pos])
+        for lvl in (4, 3, 2, 1, 0):
+            l1, l2 = self.enc[lvl]
+            if lvl == 4:
+                conv_bn_bwd(l2, grad_a2)
+            else:
+                conv_bn_bwd(l2, self.dcat[lvl][..., :ENC_CH[lvl]], dpool=self.enc[lvl + 1][0].g_in)
+            conv_bn_bwd(l1, l2.g_in)
+            pos += 8
+            if bucket_hook:
+                bucket_hook(self, self.grad_offsets[pos])
+        return g
+
+
+class _UNetFunction(torch.autograd.Function):
+    """The single autograd node standing for unet.forward (unet/unet.py:93-105)."""
+
+    @staticmethod
+    def forward(ctx, model, plan, x, *params):
+        ctx.plan = plan
+        ctx.model = model
+        ctx.params = params
+        ctx.generation = plan.generation + 1
+        logits = plan.forward(x, training=model.training)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        plan: UNetPlan = ctx.plan
+        if plan.generation != ctx.generation:
+            raise RuntimeError("the activations of this forward pass were overwritten by a later forward pass")
+        hook = getattr(ctx.model, "_bucket_hook", None)
+        scale = getattr(ctx.model, "_grad_scale", None)
+        if scale is not None and scale != 1.0:
+            dlogits = dlogits * scale
+        grads = plan.backward(dlogits, hook)
+        plan.busy = False
+        done = getattr(ctx.model, "_backward_done_hook", None)
+        if done:
+            done(plan)
+        out = [grads.get(p) if p.requires_grad else None for p in ctx.params]
+        return (None, None, None, *out)
+
+
+class UNetEngine:
+    """Plan cache + entry point used by ``unet.forward``."""
+
+    def __init__(self, model):
+        self.model = model
+        self.plans: Dict[tuple, List[UNetPlan]] = {}
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        params = list(m.parameters())
+        L.require_cuda(x, params[0])
+        if x.dim() != 4 or x.shape[1] != m.din:
+            raise RuntimeError(f"expected input [N,{m.din},H,W], got {tuple(x.shape)}")
+        if x.device != params[0].device:
+            raise RuntimeError(f"input is on {x.device} but the model is on {params[0].device}")
+        for p in params:
+            if p.dtype != torch.float32:
+                raise RuntimeError("parameters must stay fp32 (master weights); precision is selected with model.precision")
+        precision = os.environ.get("UNETK_PRECISION", m.precision)
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        n, _, h, w = x.shape
+        key = (n, h, w, precision, x.device.index)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        pool = self.plans.setdefault(key, [])
+        plan = next((p for p in pool if not p.busy), None)
+        if plan is None and len(pool) >= 2:
+            # forwards whose backward never ran (e.g. a validation loss computed with grad enabled) must not
+            # leak buffers: recycle the oldest plan; a late backward on it fails the generation check loudly
+            plan = min(pool, key=lambda p: p.generation)
+        if plan is None:
+            with torch.cuda.device(x.device):
+                plan = UNetPlan(m, n, h, w, precision, x.device)
+            pool.append(plan)
+        plan.algo = {"auto": L.ALGO_AUTO, "simt": L.ALGO_SIMT, "tc": L.ALGO_TC}[os.environ.get("UNETK_ALGO", m.conv_algo)]
+        with torch.cuda.device(x.device):
+            if needs_grad:
+                plan.busy = True
+                return _UNetFunction.apply(m, plan, x, *params)
+            with torch.no_grad():
+                return plan.forward(x, training=m.training)

@@ -1,0 +1,166 @@
+"""Drop-in for the reference's ``utils/MetricsHistory.py``: per-class TP/FP/FN/TN accumulation and
+Dice / IoU / accuracy epoch metrics, same public surface (``accumulate``, ``reset``,
+``compute_epoch_metrics``, ``to``, ``get_*``, picklable).
+
+Difference in *how*: ``accumulate`` (reference :55-86 = argmax + two one_hot + four masked sums + four
+``.cpu()`` syncs per image) is one CUDA kernel that adds exact int64 counts to device-resident
+accumulators; nothing is copied to the host until the totals are read (``total_tp`` ... properties,
+``compute_epoch_metrics`` or pickling).  Counts are integers, so results are bit-identical to the
+reference's float64 sums.
+"""
+import torch
+
+from .. import _lib as L
+
+_MAX_CLASSES = 8
+
+
+class MetricsHistory:
+    """
+    Accumulates TP, FP, FN, TN over an epoch for multi-class segmentation
+    and computes Dice, IoU, and Accuracy metrics.
+    """
+
+    def __init__(self, num_classes: int, ignore_index: int = None, device: str = 'cpu'):
+        self.num_classes = num_classes
+        self.ignore_index = ignore_index
+        self._host = torch.zeros(4, num_classes, dtype=torch.float64)      # synced totals (tp, fp, fn, tn)
+        self._pending = {}                                                  # device -> (int64 [4,C], status)
+
+        self.epoch_mean_dice_history = []
+        self.epoch_mean_iou_history = []
+        self.epoch_mean_acc_history = []
+        self.epoch_per_class_dice_history = []
+        self.epoch_per_class_iou_history = []
+        self.epoch_per_class_acc_history = []
+        self.last_per_class_iou = None
+        self.last_per_class_dice = None
+        self.last_per_class_acc = None
+
+        self.mask = torch.ones(num_classes, dtype=torch.bool)
+        if self.ignore_index is not None and 0 <= self.ignore_index < self.num_classes:
+            self.mask[self.ignore_index] = False
+
+    # ---- device-resident accumulation ----------------------------------------------------------
+    def _sync(self):
+        """Fold device counters into the float64 host totals (one D2H copy per device)."""
+        for dev, (counts, status) in list(self._pending.items()):
+            both = torch.cat([counts.flatten(), status.to(torch.int64)]).cpu()
+            if int(both[-1]) != 0:
+                counts.zero_()
+                status.zero_()
+                raise RuntimeError("Class values must be smaller than num_classes.")
+            self._host += both[:-1].view(4, self.num_classes).to(torch.float64)
+            counts.zero_()
+
+    def _totals(self, i):
+        self._sync()
+        return self._host[i]
+
+    total_tp = property(lambda self: self._totals(0))
+    total_fp = property(lambda self: self._totals(1))
+    total_fn = property(lambda self: self._totals(2))
+    total_tn = property(lambda self: self._totals(3))
+
+    def reset(self):
+        """Resets the accumulated TP, FP, FN, TN counts."""
+        for counts, status in self._pending.values():
+            counts.zero_()
+        self._host.zero_()
+
+    def accumulate(self, pred: torch.Tensor, label: torch.Tensor):
+        """pred: logits or probabilities (C,H,W) [or (N,C,H,W) for a whole batch]; label: (H,W), (1,H,W) [or (N,H,W)]."""
+        L.require_cuda(pred, label)
+        c = self.num_classes
+        if c > _MAX_CLASSES:
+            raise NotImplementedError(f"up to {_MAX_CLASSES} classes supported")
+        if pred.dim() == 3:
+            pred = pred.unsqueeze(0)
+        if pred.dim() != 4 or pred.shape[1] != c:
+            raise RuntimeError(f"pred must be [C,H,W] with C={c}, got {tuple(pred.shape)}")
+        n, _, h, w = pred.shape
+        if label.numel() != n * h * w:
+            raise RuntimeError(f"label shape {tuple(label.shape)} does not match pred {tuple(pred.shape)}")
+        pred = pred if (pred.dtype == torch.float32 and pred.is_contiguous()) else pred.float().contiguous()
+        label = label if (label.dtype == torch.int64 and label.is_contiguous()) else label.long().contiguous()
+        dev = pred.device
+        if dev not in self._pending:
+            self._pending[dev] = (torch.zeros(4, c, dtype=torch.int64, device=dev),
+                                  torch.zeros(1, dtype=torch.int32, device=dev))
+        counts, status = self._pending[dev]
+        with torch.cuda.device(dev):
+            L.argmax_confusion(pred, label, n, c, h, w, counts, None, status)
+
+    def compute_epoch_metrics(self, epsilon: float = 1e-6):
+        """Macro-averaged (mean_dice, mean_iou, mean_acc) of the accumulated epoch; appended to the histories."""
+        tp, fp, fn, tn = self.total_tp, self.total_fp, self.total_fn, self.total_tn
+        per_class_iou = tp / (tp + fp + fn)
+        per_class_dice = (2 * tp) / (2 * tp + fp + fn)
+        per_class_acc = (tp + tn) / (tp + tn + fp + fn)
+        mean_iou = per_class_iou[self.mask].mean().item()
+        mean_dice = per_class_dice[self.mask].mean().item()
+        mean_acc = per_class_acc[self.mask].mean().item()
+        self.epoch_mean_iou_history.append(mean_iou)
+        self.epoch_mean_dice_history.append(mean_dice)
+        self.epoch_mean_acc_history.append(mean_acc)
+        self.epoch_per_class_iou_history.append(per_class_iou.numpy())
+        self.epoch_per_class_dice_history.append(per_class_dice.numpy())
+        self.epoch_per_class_acc_history.append(per_class_acc.numpy())
+        self.last_per_class_iou = per_class_iou
+        self.last_per_class_dice = per_class_dice
+        self.last_per_class_acc = per_class_acc
+        return mean_dice, mean_iou, mean_acc
+
+    def to(self, device):
+        """Kept for API parity; totals live on the host, counters follow the predictions' device."""
+        self.mask = self.mask.to("cpu")
+
+    def all_reduce(self, group=None):
+        """Data-parallel evaluation: sum the exact counts over ranks (one small collective)."""
+        import torch.distributed as dist
+        self._sync()
+        if dist.is_available() and dist.is_initialized():
+            t = self._host.clone()
+            if dist.get_backend(group) == "nccl":
+                t = t.cuda()
+            dist.all_reduce(t, group=group)
+            self._host.copy_(t.cpu())
+
+    def __getstate__(self):
+        self._sync()
+        state = self.__dict__.copy()
+        state["_pending"] = {}
+        return state
+
+    def get_ignore_index(self):
+        return self.ignore_index
+
+    def get_num_classes(self):
+        return self.num_classes
+
+    def get_mean_dice_history(self):
+        return self.epoch_mean_dice_history
+
+    def get_mean_iou_history(self):
+        return self.epoch_mean_iou_history
+
+    def get_mean_acc_history(self):
+        return self.epoch_mean_acc_history
+
+    def get_class_dice_history(self):
+        return self.epoch_per_class_dice_history
+
+    def get_class_iou_history(self):
+        return self.epoch_per_class_iou_history
+
+    def get_class_acc_history(self):
+        return self.epoch_per_class_acc_history
+
+    def get_last_per_class_dice(self):
+        return self.last_per_class_dice
+
+    def get_last_per_class_iou(self):
+        return self.last_per_class_iou
+
+    def get_last_per_class_acc(self):
+        return self.last_per_class_acc

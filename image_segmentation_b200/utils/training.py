@@ -1,0 +1,157 @@
+"""Drop-in for the U-Net part of the reference's ``utils/training.py``: ``train_loop`` (:18-64),
+``eval_loop`` (:67-121) and ``start`` (:453-617) with the same signatures, printed lines and
+checkpoint dictionary keys.  Model, loss and metrics objects are passed in, exactly as in the
+reference; with this package's ``unet`` / ``WeightedDiceCELoss`` / ``MetricsHistory`` every step runs on
+the CUDA kernels, and the loops themselves only sequence work (host code stays Python).
+
+Changes that do not alter results:
+  * batches that already have the target resolution skip the per-image resize loop;
+  * the loss value is read back once per optimiser step (as the reference does) -- no other syncs.
+"""
+import os
+
+import torch
+
+from .MetricsHistory import MetricsHistory
+from .utils import process_batch_forward, process_batch_reverse
+
+try:  # progress bars are optional plumbing
+    from tqdm.auto import tqdm as _tqdm
+except Exception:  # pragma: no cover
+    _tqdm = None
+
+
+def _progress(iterable, **kw):
+    if _tqdm is None or os.environ.get("UNETK_NO_TQDM", "1") == "1":
+        class _P:
+            def __init__(self, it):
+                self._it = it
+
+            def __iter__(self):
+                return iter(self._it)
+
+            def set_postfix(self, *a, **k):
+                pass
+        return _P(iterable)
+    return _tqdm(iterable, **kw)
+
+
+def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device, scheduler=None, target_size=None):
+    """One epoch of training with gradient accumulation; returns the mean logged loss per optimiser step."""
+    model.train()
+    total_loss, processed_batches = 0.0, 0
+    num_batches = len(dataloader)
+    optimizer.zero_grad()
+    pbar = _progress(enumerate(dataloader), total=num_batches, desc="Training")
+    for batch_idx, (X, y) in pbar:
+        if target_size is not None:
+            X, _ = process_batch_forward(X, target_size=target_size)
+            y, _ = process_batch_forward(y, target_size=target_size, interpolation="nearest")
+        X = X.to(device, non_blocking=True)
+        y = y.to(device, non_blocking=True).long()
+        pred = model(X)
+        loss = loss_fn(pred, y.squeeze(1))
+        (loss / accumulation_steps).backward()
+        if (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches:
+            optimizer.step()
+            if scheduler:
+                scheduler.step()
+            optimizer.zero_grad()
+            value = loss.item()
+            total_loss += value
+            processed_batches += 1
+            pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
+    avg_loss = total_loss / processed_batches if processed_batches > 0 else 0
+    print(f"Training Avg loss (per effective batch): {avg_loss:>8f}")
+    return avg_loss
+
+
+def eval_loop(dataloader, model, loss_fn, device, target_size, agg):
+    """Evaluation at each image's original resolution: mean loss, macro Dice and mIoU."""
+    model.eval()
+    num_images_processed = 0
+    losses = []
+    agg.reset()
+    with torch.no_grad():
+        for X, y in _progress(dataloader, desc="Eval"):
+            X, meta_list = process_batch_forward(X, target_size=target_size)
+            preds = model(X.to(device, non_blocking=True))
+            preds = process_batch_reverse(preds, meta_list, interpolation='bilinear')
+            for pred, label in zip(preds, y):
+                label = label.to(device).long()
+                losses.append(loss_fn(pred.unsqueeze(0), label.unsqueeze(0).squeeze(1)))
+                agg.accumulate(pred, label)
+                num_images_processed += 1
+    avg_loss = torch.stack(losses).double().mean().item() if losses else float("nan")   # one sync for the epoch
+    mean_dice, mean_iou, mean_acc = agg.compute_epoch_metrics()
+    per_class_iou = agg.get_last_per_class_iou()
+    print(f"\n--- Evaluation Complete ---")
+    print(f"  Images Processed: {num_images_processed}")
+    print(f"  Average Loss (Original Size): {avg_loss:>8f}")
+    print(f"  Ignored Class : {agg.get_ignore_index()}")
+    print(f"  Macro Avg Acc score: {mean_acc:>8f}")
+    print(f"  Macro Avg Dice Score: {mean_dice:>8f}")
+    print(f"  Mean IoU (mIoU): {mean_iou:>8f}")
+    print(f"  --- Per-Class IoU ---")
+    for c in range(agg.get_num_classes()):
+        print(f"    Class {c}: {per_class_iou[c].item():>8f}")
+    print("-" * 25)
+    return avg_loss, mean_dice, mean_iou
+
+
+def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, val_dataloader, accumulation_steps,
+          device, train_loss_fn, val_loss_fn, target_size, scheduler=None, agg=None, load=True, save=True,
+          num_classes=4, ignore_index=3, epochs=100):
+    """Train/evaluate for ``epochs`` epochs with best-mIoU checkpointing and resume (reference :453-617)."""
+    model.to(device)
+    if agg is None:
+        agg = MetricsHistory(num_classes, ignore_index)
+    best = {"best_dev_dice": -1.0, "best_dev_miou": -1.0, "best_dev_loss": float("inf")}
+    start_epoch = 0
+    path = os.path.join(model_save_dir, model_save_name)
+    if save:
+        os.makedirs(os.path.join(model_save_dir, "metrics"), exist_ok=True)
+    if load and os.path.isfile(path):
+        print(f"Loading checkpoint from {path}")
+        ckpt = torch.load(path, map_location=device, weights_only=True)
+        model.load_state_dict(ckpt["model_state_dict"])
+        for key, obj in (("optimizer_state_dict", optimizer), ("scheduler_state_dict", scheduler)):
+            if obj is not None and key in ckpt:
+                try:
+                    obj.load_state_dict(ckpt[key])
+                except Exception as e:  # same tolerance as the reference
+                    print(f" -> could not restore {key}: {e}")
+        start_epoch = ckpt.get("epoch", 0)
+        for k in best:
+            best[k] = ckpt.get(k, best[k])
+        print(f" -> Resuming training from epoch {start_epoch + 1}")
+        print(f" -> Notes from checkpoint: {ckpt.get('notes', 'N/A')}")
+    else:
+        print(f"Checkpoint file not found at {path}. Starting training from scratch.")
+
+    print("\nStarting Training...")
+    for t in range(start_epoch, epochs):
+        print(f"Epoch {t + 1}\n-------------------------------")
+        train_loop(train_dataloader, model, train_loss_fn, optimizer, accumulation_steps, device, scheduler, target_size)
+        val_loss, val_dice, val_miou = eval_loop(val_dataloader, model, val_loss_fn, device, target_size, agg)
+        if save:
+            torch.save({"epoch": t + 1, "history": agg}, os.path.join(model_save_dir, "metrics", model_save_name))
+        if val_miou > best["best_dev_miou"]:
+            best.update(best_dev_dice=val_dice, best_dev_miou=val_miou, best_dev_loss=val_loss)
+            if save:
+                print(f"Validation IoU score improved ({val_miou:.6f}). Saving model...")
+                ckpt = {"epoch": t + 1, "model_state_dict": model.state_dict(),
+                        "optimizer_state_dict": optimizer.state_dict(), **best,
+                        "notes": f"Model saved based on best Micro Dice. Ignored index for metric: {ignore_index}"}
+                if scheduler:
+                    ckpt["scheduler_state_dict"] = scheduler.state_dict()
+                torch.save(ckpt, path)
+                torch.save({"epoch": t + 1, "model_state_dict": model.state_dict()},
+                           os.path.join(model_save_dir, f"MO_{model_save_name}"))
+        else:
+            print(f"Validation IoU score did not improve from {best['best_dev_miou']:.6f}")
+    print("\n--- Training Finished! ---")
+    print(f"Best validation IoU score achieved: {best['best_dev_miou']:.6f}")
+    print(f"Corresponding validation dice: {best['best_dev_dice']:.6f}")
+    print(f"Corresponding validation loss: {best['best_dev_loss']:.6f}")
+    return best

@@ -1,0 +1,197 @@
+/*
+ * unetk.h -- C ABI of the B200-native U-Net training-step kernels (libunetk.so).
+ *
+ * This is the drop-in boundary of the hot path.  The reference (in5omnia/Image_Segmentation)
+ * has no FFI of its own: its hot path is a chain of PyTorch ATen calls made from
+ *   unet/unet.py:16-21,40,59,63,91      (conv3x3, BatchNorm, ReLU, MaxPool, ConvTranspose, cat, 1x1 head)
+ *   utils/weighted_loss.py:36-98,163    (softmax, one-hot, Dice sums, cross entropy)
+ *   utils/MetricsHistory.py:65-86       (argmax, one-hot, TP/FP/FN/TN)
+ * Each entry point below names the reference call site(s) it replaces.  The host side
+ * (image_segmentation_b200/, Python, mirrors the reference's nn.Module / loss / metrics API)
+ * binds these with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs.  No torch / C++ types.
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); the library
+ *     never allocates, frees or keeps device memory beyond the call.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised.
+ *   - return 0 on success, negative on error; unetk_last_error() gives the thread-local message.
+ *   - activations are NHWC ("pixel-major"): element (n,h,w,c) lives at ptr[((n*H+h)*W+w)*ld + c];
+ *     `ld` >= c lets a tensor be a channel slice of a wider buffer (zero-copy skip concatenation).
+ *   - dtype: UNETK_F32 (parity tier, SIMT kernels) or UNETK_BF16 (throughput tier, tcgen05 kernels,
+ *     fp32 accumulation).  There is no CPU fallback anywhere.
+ */
+#ifndef UNETK_H
+#define UNETK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNETK_F32 0
+#define UNETK_BF16 1
+
+#define UNETK_OK 0
+#define UNETK_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define UNETK_ERR_CUDA (-2)      /* CUDA runtime / driver error */
+#define UNETK_ERR_UNSUPPORTED (-3)
+
+/* algo selector for the contraction kernels */
+#define UNETK_ALGO_AUTO 0   /* bf16 -> tcgen05, f32 -> SIMT */
+#define UNETK_ALGO_SIMT 1   /* CUDA-core FFMA kernels (any dtype; the fp32 parity tier) */
+#define UNETK_ALGO_TC 2     /* TMA + tcgen05.mma + TMEM (bf16 only) */
+
+typedef struct unetk_tensor {
+  void* ptr;
+  int32_t n, h, w, c;
+  int32_t ld;    /* elements between consecutive pixels (>= c) */
+  int32_t dtype; /* UNETK_F32 | UNETK_BF16 */
+} unetk_tensor;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int unetk_version(void);
+const char* unetk_last_error(void);
+/* sm_count / compute capability of the current device */
+int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* ---- layout --------------------------------------------------------------------------------
+ * unetk_im2col3x3_first: X.to(device) + first conv's implicit im2col (utils/training.py:45,
+ * unet/unet.py:16 for down1).  x is NCHW fp32 [N,Cin,H,W]; out is NHWC [N,H,W,out.c] with
+ * out[.., (r*3+s)*Cin + ci] = x[n, ci, h+r-1, w+s-1] (zero outside / for k >= 9*Cin).
+ * The first conv then runs as a 1x1 contraction over out.c channels.                          */
+int unetk_im2col3x3_first(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w,
+                          const unetk_tensor* out, void* stream);
+
+/* unetk_permute3: dst[i0*ds0+i1*ds1+i2*ds2] = (dst_dtype) src[i0*ss0+i1*ss1+i2*ss2], fp32 source.
+ * Packs nn.Conv2d / nn.ConvTranspose2d weights (OIHW / IOHW fp32, unet/unet.py:16,19,59) into the
+ * K-major operand layouts of the contraction kernels and unpacks weight gradients back.       */
+int unetk_permute3(const float* src, void* dst, int32_t dst_dtype, int32_t d0, int32_t d1, int32_t d2,
+                   int64_t ss0, int64_t ss1, int64_t ss2, int64_t ds0, int64_t ds1, int64_t ds2,
+                   void* stream);
+
+/* ---- contractions --------------------------------------------------------------------------
+ * One implicit-GEMM entry for every "activation x weight" product of the path:
+ *   mode 0  1x1           y[p, co]        = sum_ci          x[p, ci]            w[co][ci]
+ *   mode 1  3x3 pad 1     y[p, co]        = sum_{t,ci}      x[p + off(t), ci]   w[co][t][ci]
+ *           (nn.Conv2d k3 p1 forward, unet/unet.py:16,19; and its data gradient when w holds the
+ *            flipped/transposed pack)
+ *   mode 2  convT 2x2 s2  y[2p+(a,b), co] = sum_ci          x[p, ci]            w[(a,b,co)][ci]   (+bias)
+ *           (nn.ConvTranspose2d forward, unet/unet.py:59; y may be a channel slice of the concat buffer,
+ *            which replaces torch.cat at unet/unet.py:63)
+ *   mode 3  convT gather  y[p, ci]        = sum_{(a,b),co}  x[2p+(a,b), co]     w[ci][(a,b)][co]
+ *           (data gradient of ConvTranspose2d)
+ * Optional: bias[C_out]; stat_sum/stat_sumsq[C_out] (double, ACCUMULATED) = per-channel sum and
+ * sum of squares of y as stored (BatchNorm batch statistics, unet/unet.py:17,20).            */
+typedef struct unetk_conv_args {
+  unetk_tensor x;
+  const void* w; /* same dtype as x */
+  unetk_tensor y;
+  int32_t mode;
+  int32_t algo;
+  const float* bias;
+  double* stat_sum;
+  double* stat_sumsq;
+} unetk_conv_args;
+int unetk_conv(const unetk_conv_args* a, void* stream);
+
+/* Weight gradient: dw[cu][t][cs] += sum_p u[p, cu] * s[gather(p, t), cs]   (fp32, accumulated)
+ *   mode 0: 1 tap; mode 1: 3x3 pad 1 (u = dY, s = X); mode 2: 2x2 stride 2 (u = X low-res, s = dY hi-res)
+ * Replaces the filter-gradient half of convolution_backward for unet/unet.py:16,19,59.        */
+typedef struct unetk_wgrad_args {
+  unetk_tensor u;
+  unetk_tensor s;
+  float* dw;
+  int32_t mode;
+  int32_t algo;
+} unetk_wgrad_args;
+int unetk_wgrad(const unetk_wgrad_args* a, void* stream);
+
+/* per-channel sum over all pixels: out[c] += sum_p t[p, c]  (bias gradients of ConvTranspose2d) */
+int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream);
+
+/* ---- BatchNorm + ReLU + MaxPool (unet/unet.py:17-18,20-21,40) ------------------------------- */
+int unetk_bn_stats(const unetk_tensor* z, double* sum, double* sumsq, void* stream);
+
+typedef struct unetk_bn_finalize_args {
+  const double* sum;
+  const double* sumsq;
+  int64_t count; /* N*H*W */
+  int32_t c;
+  int32_t training; /* 1: batch statistics + running-stat update; 0: running statistics */
+  const float* gamma;
+  const float* beta;
+  const float* conv_bias; /* bias of the preceding conv: folded into mean / running_mean */
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum, eps;
+  float* scale;  /* gamma * invstd */
+  float* shift;  /* beta - mean*scale (training) */
+  float* mean;   /* batch mean of the bias-free conv output */
+  float* invstd;
+} unetk_bn_finalize_args;
+int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream);
+
+/* a = relu(z*scale+shift); optionally pooled = maxpool2x2(a) in the same pass (pooled->ptr may be NULL) */
+int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift,
+                        const unetk_tensor* a, const unetk_tensor* pooled, void* stream);
+
+/* Backward of (BN train -> ReLU [-> MaxPool]):
+ *   dy = dA * [a > 0],  dA = dy_full (optional) + route(dpool) (optional; first max in scan order)
+ *   reduce: sums[0][c] += sum dy, sums[1][c] += sum dy * xhat
+ *   apply : dz = scale * (dy - s1/M - xhat * s2/M);  dgamma = s2, dbeta = s1                   */
+typedef struct unetk_bn_bwd_args {
+  unetk_tensor z;
+  unetk_tensor dy;    /* ptr NULL if absent */
+  unetk_tensor dpool; /* ptr NULL if absent; [N,H/2,W/2,C] */
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  double* sums; /* [2][C] */
+  unetk_tensor dz;
+  float* dgamma;
+  float* dbeta;
+} unetk_bn_bwd_args;
+int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream);
+int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream);
+
+/* ---- 1x1 classifier head (unet/unet.py:91) -------------------------------------------------- */
+/* logits NCHW fp32 [N,dout,H,W] = a[N,H,W,64] . w[dout][cin] + b */
+int unetk_head_fprop(const unetk_tensor* a, const float* w, const float* b, int32_t dout,
+                     float* logits_nchw, void* stream);
+/* da = dlogits . w ; dw[dout][cin] += ; db[dout] += */
+int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float* w, int32_t dout,
+                   const unetk_tensor* da, float* dw, float* db, void* stream);
+
+/* ---- weighted Dice + CE loss (utils/weighted_loss.py:31-98,140-166) --------------------------- */
+typedef struct unetk_dice_ce_args {
+  const float* logits;   /* NCHW fp32 */
+  const int64_t* target; /* [N,H,W] */
+  int32_t n, c, h, w;
+  const float* class_weights; /* NULL or [C] */
+  int32_t has_ignore;
+  int64_t ignore_index;
+  float dice_weight, ce_weight, smooth;
+  double* accum; /* [3C+2] zeroed by caller: I_c, P_c, G_c, ce_num, ce_den */
+  float* coef;   /* [2C+1] written by fwd, read by bwd */
+  float* loss;   /* [1] */
+  int32_t* status; /* |= 1 if a label is outside [0,C) (the reference raises from scatter_) */
+  const float* grad_out; /* [1] device scalar (bwd) */
+  float* dlogits;        /* NCHW fp32 (bwd) */
+} unetk_dice_ce_args;
+int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream);
+int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
+
+/* ---- confusion-count metrics (utils/MetricsHistory.py:65-86) ---------------------------------- */
+/* pred NCHW fp32 [N,C,H,W] (N images at once), label [N,H,W] int64.
+ * counts[4][C] (tp, fp, fn, tn; int64) are ACCUMULATED; argmax_out (optional) receives the hard mask. */
+int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
+                           int32_t w, int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETK_H */

@@ -1,0 +1,367 @@
+"""Per-kernel parity tests of libunetk.so (through the C ABI) against CPU references:
+torch.nn.functional in float64 for the floating-point ops (same operator the reference calls),
+oracle/ for loss and metrics, golden vectors from the unmodified reference where they exist.
+
+Tolerances (stated per north_star): fp32 tier rel 1e-4, bf16 tier rel 2e-2 (here: max-abs error
+relative to the tensor's max-abs); integer outputs bit-exact.
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from image_segmentation_b200 import _lib as L  # noqa: E402
+from oracle import loss_oracle, metrics_oracle  # noqa: E402
+
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def relerr(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def rnd(shape, dt, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    t = (torch.randn(shape, generator=g) * scale).to(dt)   # values exactly representable in dt
+    return t
+
+
+def nhwc_to_nchw(t):
+    return t.permute(0, 3, 1, 2).contiguous()
+
+
+ALGOS = [(torch.float32, L.ALGO_SIMT), (torch.bfloat16, L.ALGO_SIMT), (torch.bfloat16, L.ALGO_TC)]
+IDS = ["f32-simt", "bf16-simt", "bf16-tc"]
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 8, 24, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 64, 128),
+                                              (5, 2, 2, 128, 128)])
+def test_conv3x3_fprop_with_stats(dt, algo, n, h, w, cin, cout):
+    x = rnd((n, h, w, cin), dt, 1)
+    wt = rnd((cout, cin, 3, 3), dt, 2, 0.05)
+    ref = F.conv2d(nhwc_to_nchw(x.double()), wt.double(), padding=1).permute(0, 2, 3, 1)
+    xd, y = x.to(DEV), torch.empty((n, h, w, cout), dtype=dt, device=DEV)
+    wp = wt.permute(0, 2, 3, 1).contiguous().to(DEV)          # [co][r][s][ci]
+    s1 = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    s2 = torch.zeros(cout, dtype=torch.float64, device=DEV)
+    L.conv(xd, wp, y, L.MODE_3X3, stat_sum=s1, stat_sumsq=s2, algo=algo)
+    torch.cuda.synchronize()
+    assert relerr(y, ref) < TOL[dt]
+    yd = y.double().cpu()
+    np.testing.assert_allclose(s1.cpu().numpy(), yd.sum(dim=(0, 1, 2)).numpy(), rtol=1e-5, atol=1e-4 * max(1.0, yd.abs().max().item()))
+    np.testing.assert_allclose(s2.cpu().numpy(), (yd * yd).sum(dim=(0, 1, 2)).numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+def test_conv1x1_and_bias(dt, algo):
+    n, h, w, cin, cout = 2, 8, 16, 64, 64
+    x = rnd((n, h, w, cin), dt, 3)
+    wt = rnd((cout, cin), dt, 4, 0.1)
+    b = rnd((cout,), torch.float32, 5)
+    ref = x.double() @ wt.double().t() + b.double()
+    y = torch.empty((n, h, w, cout), dtype=dt, device=DEV)
+    L.conv(x.to(DEV), wt.to(DEV), y, L.MODE_1X1, bias=b.to(DEV), algo=algo)
+    assert relerr(y, ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 4, 4, 128, 64), (1, 8, 8, 512, 256), (3, 2, 2, 64, 64)])
+def test_conv_transpose_fprop_into_concat_slice_and_dgrad(dt, algo, n, h, w, cin, cout):
+    x = rnd((n, h, w, cin), dt, 6)
+    wt = rnd((cin, cout, 2, 2), dt, 7, 0.1)
+    b = rnd((cout,), torch.float32, 8)
+    ref = F.conv_transpose2d(nhwc_to_nchw(x.double()), wt.double(), b.double(), stride=2).permute(0, 2, 3, 1)
+    cat = torch.full((n, 2 * h, 2 * w, 2 * cout), 7.0, dtype=dt, device=DEV)
+    out = cat[..., cout:]                                        # second half of the concat buffer
+    wf = wt.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous().to(DEV)   # [(a,b,co)][ci]
+    L.conv(x.to(DEV), wf, out, L.MODE_CONVT, bias=b.to(DEV), algo=algo)
+    assert relerr(out, ref) < TOL[dt]
+    assert torch.all(cat[..., :cout] == 7.0)                     # skip half untouched
+    # data gradient: dx[n,i,j,ci] = sum dy[n,2i+a,2j+b,co] w[ci,co,a,b]
+    dy = rnd((n, 2 * h, 2 * w, cout), dt, 9)
+    ref_dx = F.conv2d(nhwc_to_nchw(dy.double()), wt.double().permute(0, 1, 2, 3), stride=2).permute(0, 2, 3, 1)
+    dcat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), dtype=dt, device=DEV)
+    dcat[..., cout:] = dy.to(DEV)
+    wd = wt.permute(0, 2, 3, 1).reshape(cin, 4, cout).contiguous().to(DEV)    # [ci][(a,b)][co]
+    dx = torch.empty((n, h, w, cin), dtype=dt, device=DEV)
+    L.conv(dcat[..., cout:], wd, dx, L.MODE_CONVT_GATHER, algo=algo)
+    assert relerr(dx, ref_dx) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 8, 8, 128, 64), (1, 16, 32, 64, 128), (3, 4, 4, 256, 128)])
+def test_conv3x3_dgrad_and_wgrad(dt, algo, n, h, w, cin, cout):
+    x = rnd((n, h, w, cin), dt, 10)
+    wt = rnd((cout, cin, 3, 3), dt, 11, 0.05)
+    dy = rnd((n, h, w, cout), dt, 12)
+    xr = nhwc_to_nchw(x.double()).requires_grad_(True)
+    wr = wt.double().requires_grad_(True)
+    F.conv2d(xr, wr, padding=1).backward(nhwc_to_nchw(dy.double()))
+    # dgrad = 3x3 contraction with the flipped / transposed pack [ci][8-t][co]
+    wd = wt.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(DEV)
+    dx = torch.empty((n, h, w, cin), dtype=dt, device=DEV)
+    L.conv(dy.to(DEV), wd, dx, L.MODE_3X3, algo=algo)
+    assert relerr(dx, xr.grad.permute(0, 2, 3, 1)) < TOL[dt]
+    dw = torch.zeros((cout, 9, cin), dtype=torch.float32, device=DEV)
+    L.wgrad(dy.to(DEV), x.to(DEV), dw, 1, algo=algo)
+    ref_dw = wr.grad.permute(0, 2, 3, 1).reshape(cout, 9, cin)
+    assert relerr(dw, ref_dw) < 1e-4       # fp32 accumulation of exactly representable inputs
+    # accumulation semantics: a second call adds
+    L.wgrad(dy.to(DEV), x.to(DEV), dw, 1, algo=algo)
+    assert relerr(dw, 2 * ref_dw) < 1e-4
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+def test_wgrad_1x1_and_convT(dt, algo):
+    n, h, w, cin, cout = 2, 8, 8, 128, 64
+    x = rnd((n, h, w, cin), dt, 13)
+    dy = rnd((n, 2 * h, 2 * w, cout), dt, 14)
+    wr = torch.zeros(cin, cout, 2, 2, dtype=torch.float64, requires_grad=True)
+    F.conv_transpose2d(nhwc_to_nchw(x.double()), wr, stride=2).backward(nhwc_to_nchw(dy.double()))
+    dw = torch.zeros((cin, 4, cout), dtype=torch.float32, device=DEV)
+    dcat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), dtype=dt, device=DEV)
+    dcat[..., cout:] = dy.to(DEV)
+    L.wgrad(x.to(DEV), dcat[..., cout:], dw, 2, algo=algo)
+    assert relerr(dw, wr.grad.permute(0, 2, 3, 1).reshape(cin, 4, cout)) < 1e-4
+    # 1x1 (first layer on its im2col operand)
+    u = rnd((n, h, w, 64), dt, 15)
+    s = rnd((n, h, w, 64), dt, 16)
+    dw1 = torch.zeros((64, 1, 64), dtype=torch.float32, device=DEV)
+    L.wgrad(u.to(DEV), s.to(DEV), dw1, 0, algo=algo)
+    assert relerr(dw1.view(64, 64), u.double().reshape(-1, 64).t() @ s.double().reshape(-1, 64)) < 1e-4
+    # channel sum (ConvTranspose bias gradient)
+    out = torch.zeros(cout, dtype=torch.float32, device=DEV)
+    L.channel_sum(dcat[..., cout:], out)
+    assert relerr(out, dy.double().sum(dim=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("pool", [False, True], ids=["nopool", "pool"])
+@pytest.mark.parametrize("n,h,w,c", [(2, 8, 8, 64), (3, 4, 6, 128), (1, 2, 2, 1024)])
+def test_bn_relu_pool_forward_backward(dt, pool, n, h, w, c):
+    g = torch.Generator().manual_seed(20)
+    z = rnd((n, h, w, c), dt, 21, 2.0)
+    gamma = torch.rand(c, generator=g) + 0.5
+    beta = torch.randn(c, generator=g) * 0.3
+    cbias = torch.randn(c, generator=g)
+    rm0, rv0 = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5
+    count = n * h * w
+    # ---- reference (float64, NCHW, PyTorch ops the reference model uses) ----
+    zr = nhwc_to_nchw(z.double()).requires_grad_(True)
+    rm, rv = rm0.double().clone(), rv0.double().clone()
+    y = F.batch_norm(zr + cbias.double()[None, :, None, None], rm, rv, gamma.double(), beta.double(), True, 0.1, 1e-5)
+    a = torch.relu(y)
+    # the CUDA path stores a in `dt`; pooling and ties are defined on the stored values
+    a_q = a.detach().to(dt).double()
+    outp = F.max_pool2d(a, 2) if pool else None
+    # ---- CUDA ----
+    zd = z.to(DEV)
+    s1 = torch.zeros(c, dtype=torch.float64, device=DEV); s2 = torch.zeros_like(s1)
+    L.bn_stats(zd, s1, s2)
+    scale, shift, mean, invstd = (torch.empty(c, dtype=torch.float32, device=DEV) for _ in range(4))
+    rmd, rvd = rm0.to(DEV), rv0.to(DEV)
+    nbt = torch.zeros((), dtype=torch.int64, device=DEV)
+    L.bn_finalize(s1, s2, count, c, True, gamma.to(DEV), beta.to(DEV), cbias.to(DEV), rmd, rvd, nbt, 0.1, 1e-5,
+                  scale, shift, mean, invstd)
+    cat = torch.zeros((n, h, w, 2 * c), dtype=dt, device=DEV)
+    ad = cat[..., :c]
+    pooled = torch.empty((n, h // 2, w // 2, c), dtype=dt, device=DEV) if pool else None
+    L.bn_relu_apply(zd, scale, shift, ad, pooled)
+    assert relerr(ad, a.detach().permute(0, 2, 3, 1)) < TOL[dt]
+    assert int(nbt) == 1
+    assert relerr(rmd, rm) < 1e-5 and relerr(rvd, rv) < 1e-5
+    if pool:
+        assert torch.equal(pooled.cpu(), F.max_pool2d(nhwc_to_nchw(ad.cpu().float()), 2).permute(0, 2, 3, 1).to(dt))
+    # ---- backward ----
+    dy = rnd((n, h, w, c), dt, 22)
+    dp = rnd((n, h // 2, w // 2, c), dt, 23) if pool else None
+    if pool:
+        # route the pooled gradient exactly like torch's max_pool2d backward does on the stored activations
+        aq = nhwc_to_nchw(ad.cpu().double()).requires_grad_(True)
+        F.max_pool2d(aq, 2).backward(nhwc_to_nchw(dp.double()))
+        dA = nhwc_to_nchw(dy.double()) + aq.grad
+    else:
+        dA = nhwc_to_nchw(dy.double())
+    a.backward(dA)
+    sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    dz = torch.empty((n, h, w, c), dtype=dt, device=DEV)
+    dgamma, dbeta = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    L.bn_relu_bwd(zd, dy.to(DEV), dp.to(DEV) if pool else None, scale, shift, mean, invstd, sums, dz, dgamma, dbeta)
+    ref_dz = zr.grad.permute(0, 2, 3, 1)
+    # ReLU-mask decisions are taken on the stored (dt-rounded) activation: identical to the reference when a_q > 0 <=> a > 0
+    assert torch.equal(a_q > 0, a.detach() > 0)
+    assert relerr(dz, ref_dz) < TOL[dt]
+    g_ref = torch.autograd.grad  # noqa: F841
+    # dgamma/dbeta against closed form
+    xhat = (zr.detach() - zr.detach().mean(dim=(0, 2, 3), keepdim=True)) / torch.sqrt(zr.detach().var(dim=(0, 2, 3), unbiased=False, keepdim=True) + 1e-5)
+    dyy = dA * (a.detach() > 0)
+    assert relerr(dbeta, dyy.sum(dim=(0, 2, 3))) < 1e-4
+    assert relerr(dgamma, (dyy * xhat).sum(dim=(0, 2, 3))) < 2e-4
+
+
+def test_bn_eval_mode_uses_running_stats():
+    c = 64
+    g = torch.Generator().manual_seed(30)
+    gamma, beta, cbias = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g), torch.randn(c, generator=g)
+    rm, rv = torch.randn(c, generator=g), torch.rand(c, generator=g) + 0.5
+    scale, shift = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    L.bn_finalize(None, None, 0, c, False, gamma.to(DEV), beta.to(DEV), cbias.to(DEV), rm.to(DEV), rv.to(DEV), None, 0.1, 1e-5,
+                  scale, shift, None, None)
+    z = torch.randn(4, c, generator=g)
+    ref = (z + cbias - rm) / torch.sqrt(rv + 1e-5) * gamma + beta
+    assert relerr(z.to(DEV) * scale + shift, ref) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dout", [1, 3, 4])
+def test_head_forward_backward(dt, dout):
+    n, h, w, cin = 2, 16, 8, 64
+    a = rnd((n, h, w, cin), dt, 40)
+    wt = rnd((dout, cin, 1, 1), torch.float32, 41, 0.2)
+    b = rnd((dout,), torch.float32, 42)
+    ar = nhwc_to_nchw(a.double()).requires_grad_(True)
+    wr, br = wt.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = F.conv2d(ar, wr, br)
+    logits = torch.empty((n, dout, h, w), dtype=torch.float32, device=DEV)
+    L.head_fprop(a.to(DEV), wt.to(DEV), b.to(DEV), dout, logits)
+    assert relerr(logits, ref) < 1e-5
+    dl = rnd((n, dout, h, w), torch.float32, 43)
+    ref.backward(dl.double())
+    da = torch.empty((n, h, w, cin), dtype=dt, device=DEV)
+    dw = torch.zeros((dout, cin), dtype=torch.float32, device=DEV)
+    db = torch.zeros(dout, dtype=torch.float32, device=DEV)
+    L.head_bwd(dl.to(DEV), a.to(DEV), wt.to(DEV), dout, da, dw, db)
+    assert relerr(da, ar.grad.permute(0, 2, 3, 1)) < TOL[dt]
+    assert relerr(dw, wr.grad.view(dout, cin)) < 1e-5
+    assert relerr(db, br.grad) < 1e-5
+
+
+def test_im2col_first_and_permute3():
+    n, cin, h, w = 2, 3, 8, 8
+    x = rnd((n, cin, h, w), torch.float32, 50)
+    for dt in (torch.float32, torch.bfloat16):
+        out = torch.empty((n, h, w, 64), dtype=dt, device=DEV)
+        L.im2col3x3_first(x.to(DEV), out)
+        cols = F.unfold(x, 3, padding=1).view(n, cin, 9, h, w)          # [n][ci][t][h][w]
+        ref = torch.zeros(n, h, w, 64)
+        ref[..., :27] = cols.permute(0, 3, 4, 2, 1).reshape(n, h, w, 27)  # k = t*cin + ci
+        assert torch.equal(out.cpu().float(), ref.to(dt).float())
+    wt = rnd((8, 5, 9), torch.float32, 51)
+    dst = torch.empty((5, 9, 8), dtype=torch.float32, device=DEV)
+    # [co][ci][t] -> [ci][8-t][co]
+    L.check(L.lib().unetk_permute3(wt.to(DEV).data_ptr(), dst.data_ptr() + 8 * 8 * 4, L.F32, 8, 5, 9, 45, 9, 1, 1, 72, -8,
+                                   L.stream_ptr()))
+    assert torch.equal(dst.cpu(), wt.flip(2).permute(1, 2, 0).contiguous())
+
+
+def test_loss_against_golden_and_oracle(golden):
+    from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss, WeightedMemoryEfficientDiceLoss
+    g = golden["loss"]
+    cases = json.loads(str(g["cases"]))
+    for ci, case in enumerate(cases):
+        kw = {k: v for k, v in case.items() if k != "c"}
+        if "class_weights" in kw:
+            kw["class_weights"] = torch.tensor(kw["class_weights"], dtype=torch.float32)
+        logits = torch.from_numpy(g[f"logits_{ci}"]).to(DEV).requires_grad_(True)
+        target = torch.from_numpy(g[f"target_{ci}"]).to(DEV)
+        fn = WeightedDiceCELoss(**kw)
+        loss = fn(logits, target)
+        loss.backward()
+        assert abs(loss.item() - float(g[f"loss_{ci}"])) < 2e-6, ci                 # vs the unmodified reference
+        np.testing.assert_allclose(logits.grad.cpu().numpy(), g[f"grad_{ci}"], rtol=2e-4, atol=2e-8)
+        ref = loss_oracle.dice_ce_loss(logits.detach().cpu(), target.cpu(), **kw)     # vs the float64 oracle
+        assert abs(loss.item() - ref.item()) < 1e-6
+        assert fn(logits.detach(), target.unsqueeze(1)).item() == loss.item()        # [N,1,H,W] form
+        # scaled upstream gradient (gradient accumulation divides the loss, utils/training.py:49)
+        lg2 = logits.detach().clone().requires_grad_(True)
+        (fn(lg2, target) / 4).backward()
+        np.testing.assert_allclose(lg2.grad.cpu().numpy(), logits.grad.cpu().numpy() / 4, rtol=1e-6, atol=1e-12)
+        with pytest.raises(ValueError):
+            fn(logits.detach(), target.unsqueeze(1).repeat(1, 2, 1, 1))
+    # standalone Dice
+    logits = torch.from_numpy(g["logits_0"]).to(DEV)
+    target = torch.from_numpy(g["target_0"]).to(DEV)
+    d = WeightedMemoryEfficientDiceLoss(smooth=1.0)(logits, target.unsqueeze(1))
+    ref = loss_oracle.dice_ce_loss(logits.cpu(), target.cpu(), smooth_dice=1.0, ce_weight=0.0)
+    assert abs(d.item() - ref.item()) < 1e-6
+
+
+def test_loss_large_random_vs_oracle():
+    from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss
+    g = torch.Generator().manual_seed(60)
+    logits = torch.randn(4, 4, 64, 96, generator=g) * 3
+    target = torch.randint(0, 4, (4, 64, 96), generator=g)
+    w = torch.tensor([0.2, 1.0, 1.2, 1.5])
+    fn = WeightedDiceCELoss(smooth_dice=1e-5, class_weights=w, ignore_index=3)
+    lg = logits.to(DEV).requires_grad_(True)
+    loss = fn(lg, target.to(DEV))
+    loss.backward()
+    ref = loss_oracle.dice_ce_loss(logits, target, smooth_dice=1e-5, class_weights=w, ignore_index=3)
+    gref = loss_oracle.dice_ce_grad(logits, target, smooth_dice=1e-5, class_weights=w, ignore_index=3)
+    assert abs(loss.item() - ref.item()) < 1e-6 * max(1, abs(ref.item()))
+    assert relerr(lg.grad, gref) < 1e-5
+
+
+def test_loss_out_of_range_label_raises():
+    from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss
+    import os
+    os.environ["UNETK_STRICT_LABELS"] = "1"
+    try:
+        fn = WeightedDiceCELoss()
+        with pytest.raises(RuntimeError):
+            fn(torch.zeros(1, 3, 4, 4, device=DEV), torch.full((1, 4, 4), 3, device=DEV))
+    finally:
+        os.environ.pop("UNETK_STRICT_LABELS")
+
+
+def test_metrics_bit_exact_against_golden_and_oracle(golden):
+    from image_segmentation_b200.utils.MetricsHistory import MetricsHistory
+    g = golden["metrics"]
+    cases = json.loads(str(g["cases"]))
+    for ci, case in enumerate(cases):
+        c, ign = case["c"], case["ignore_index"]
+        agg = MetricsHistory(c, ign)
+        for pred, label in zip(g[f"pred_{ci}"], g[f"label_{ci}"]):
+            agg.accumulate(torch.from_numpy(pred).to(DEV), torch.from_numpy(label).to(DEV))
+        counts = np.stack([agg.total_tp.numpy(), agg.total_fp.numpy(), agg.total_fn.numpy(), agg.total_tn.numpy()])
+        np.testing.assert_array_equal(counts, g[f"counts_{ci}"])                   # bit-exact vs the reference
+        md, mi, ma = agg.compute_epoch_metrics()
+        np.testing.assert_allclose([md, mi, ma], g[f"means_{ci}"], rtol=1e-12)
+        agg.reset()
+        assert float(agg.total_tp.sum()) == 0.0
+    # batch form + NaN/tie semantics vs the numpy oracle
+    gen = torch.Generator().manual_seed(70)
+    pred = torch.randn(5, 4, 33, 17, generator=gen)
+    pred[:, :, ::2, ::3] = pred[:, :1, ::2, ::3]
+    pred[0, 2, 0, 0] = float("nan")
+    label = torch.randint(0, 4, (5, 33, 17), generator=gen)
+    agg = MetricsHistory(4)
+    agg.accumulate(pred.to(DEV), label.to(DEV))
+    tot = np.zeros((4, 4), dtype=np.int64)
+    for p, l in zip(pred.numpy(), label.numpy()):
+        tot += np.stack(metrics_oracle.confusion_counts(p, l, 4))
+    got = np.stack([agg.total_tp.numpy(), agg.total_fp.numpy(), agg.total_fn.numpy(), agg.total_tn.numpy()]).astype(np.int64)
+    np.testing.assert_array_equal(got, tot)
+    import pickle
+    agg2 = pickle.loads(pickle.dumps(agg))
+    assert torch.equal(agg2.total_tp, agg.total_tp)
+    bad = MetricsHistory(3)
+    bad.accumulate(torch.zeros(3, 2, 2, device=DEV), torch.full((2, 2), 3, device=DEV))
+    with pytest.raises(RuntimeError):
+        bad.total_tp
+
+
+def test_cpu_tensors_are_rejected():
+    from image_segmentation_b200.unet.unet import unet
+    from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss
+    with pytest.raises(RuntimeError):
+        unet(3, 3)(torch.zeros(1, 3, 16, 16))
+    with pytest.raises(RuntimeError):
+        WeightedDiceCELoss()(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
