@@ -87,8 +87,9 @@ def test_fp32_tier_matches_reference_golden(golden, din, dout, hw):
     for key in g.files:
         if key.startswith(f"buf_{tag}_f64:"):
             k = key.split(":", 1)[1]
-            # running_mean = 0.1 * mean(z): with 8 samples per channel the mean cancels to ~1e-3 of |z|, so allow fp32 noise of |z|
-                np.testing.assert_allclose(sd[k].double().cpu().numpy(), g[key], rtol=2e-4, atol=5e-6)
+            # running_mean = 0.1 * mean(z): with 8 samples per channel the mean cancels to ~1e-3 of |z|:
+            # allow fp32 noise of |z|
+            np.testing.assert_allclose(sd[k].double().cpu().numpy(), g[key], rtol=2e-4, atol=5e-6)
     m.eval()
     with torch.no_grad():
         ev = m(x.to(DEV))
