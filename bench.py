@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- U-Net 256x256 training throughput (images/s) on N B200s; one JSON line on stdout.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (bf16 tcgen05 tier)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): unet(3,3) bf16 training step, batch 64 per GPU at 256x256,
+WeightedDiceCELoss(smooth_dice=1, class weights), AdamW(lr 1e-3, wd 0.01), MetricsHistory.accumulate,
+synthetic U[0,1) images and i.i.d. 3-class labels, random-init weights.
+
+A step = forward + loss + backward (+ gradient all-reduce for N > 1) + optimizer.step + zero_grad + metrics.
+`value`  : images/s of the whole job with the batch already resident in HBM (CUDA events, max over ranks).
+`e2e`    : the same through the public API with the batch in pinned HOST memory: H2D of X (fp32) and y (uint8)
+           and a D2H read of the loss inside the timed region every step.
+`roofline`: tensor-pipe roofline of the tcgen05 contraction kernels (algorithmic FLOPs / CUDA-event time of those
+           launches, measured in extra instrumented steps right after the timed region).
+`cpu_baseline`: the oracle port (kind "port": the reference is Python and does not travel to the GPU box) timed on
+           the host cores for a bounded sample (batch 4 steps).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "unet256_train_images_per_sec"
+UNIT = "images/s"
+CLASS_W3 = [0.2046795970925636, 1.0271954434416883, 1.2293222812780409]
+FLOP_PER_IMAGE_TRAIN = 288.8282e9   # BASELINE.md section 2 (conv/convT/head, 2 FLOP per MAC, fwd + dgrad + wgrad)
+H = W = 256
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(burst=float(d["bf16_tflops"]), sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port (the only place besides tests/ and smoke() that executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, batch=4):
+    import torch
+    from image_segmentation_b200.utils.synthetic import make_batch
+    from oracle import loss_oracle, metrics_oracle, unet_oracle
+    torch.manual_seed(0)
+    m = unet_oracle.OracleUNet(3, 3).train()
+    opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
+    w = torch.tensor(CLASS_W3)
+    x, y = make_batch(batch, H, W, 3, 3, seed=1234)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        pred = m(x)
+        loss = loss_oracle.dice_ce_loss(pred, y, smooth_dice=1.0, class_weights=w, dtype=torch.float32)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        for j in range(batch):
+            metrics_oracle.confusion_counts(pred[j].detach().numpy(), y[j].numpy(), 3)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch, times, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch, times, threads = cpu_reference_steps(args.steps, args.warmup)
+    total = sum(times)
+    value = batch * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "unet(3,3) 256x256 training step (fwd+loss+bwd+AdamW+metrics), CPU fp32, "
+                               f"bounded sample: batch {batch} per step instead of 64"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(times)} steps of batch {batch} at 256x256 on {threads} threads "
+                                   f"(os.cpu_count()={os.cpu_count()})"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from image_segmentation_b200 import _lib as L
+    from image_segmentation_b200.parallel import DataParallelUNet
+    from image_segmentation_b200.unet.unet import unet
+    from image_segmentation_b200.utils.MetricsHistory import MetricsHistory
+    from image_segmentation_b200.utils.synthetic import make_batch
+    from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()  # fail loudly now if the extension is missing
+    peaks = load_peaks()
+    B = args.batch
+
+    torch.manual_seed(0)
+    model = unet(3, 3)
+    model.precision = "bf16"
+    model = model.to(dev).train()
+    dp = DataParallelUNet(model) if world > 1 else None
+    opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01)
+    loss_fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor(CLASS_W3))
+    agg = MetricsHistory(3)
+    x_cpu, y_cpu = make_batch(B, H, W, 3, 3, seed=1234 + rank)
+    x_pin = x_cpu.pin_memory()
+    y_pin = y_cpu.to(torch.uint8).pin_memory()          # the reference's dataset yields uint8 label maps
+    x_dev, y_dev = x_cpu.to(dev), y_cpu.squeeze(1).to(dev)
+
+    def step_resident():
+        pred = model(x_dev)
+        loss = loss_fn(pred, y_dev)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        agg.accumulate(pred.detach(), y_dev)
+        return loss
+
+    def step_e2e():
+        # exactly the body of train_loop (utils/training.py:45-60) + metrics
+        X = x_pin.to(dev, non_blocking=True)
+        y = y_pin.to(dev, non_blocking=True).long()
+        pred = model(X)
+        loss = loss_fn(pred, y.squeeze(1))
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        agg.accumulate(pred.detach(), y.squeeze(1))
+        return loss.item()                               # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.COUNTERS["launches"] = 0
+    ms = timed(step_resident, args.steps)
+    launches = L.COUNTERS["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-launch instrumentation of the contraction kernels (extra steps, not part of `value`) ----
+    roof = None
+    if rank == 0:
+        records = []
+        L.PROFILE_HOOK = records
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        prof_steps = 2
+        for _ in range(prof_steps):
+            step_resident()
+        e1.record()
+        torch.cuda.synchronize()
+        L.PROFILE_HOOK = None
+        step_ms = e0.elapsed_time(e1) / prof_steps
+        flops = sum(r[1] for r in records if r[0] in ("conv", "wgrad"))
+        kms = sum(r[2].elapsed_time(r[3]) for r in records if r[0] in ("conv", "wgrad"))
+        by_kind = {}
+        for r in records:
+            by_kind.setdefault(r[0], [0.0, 0.0])
+            by_kind[r[0]][0] += r[2].elapsed_time(r[3]) / prof_steps
+            by_kind[r[0]][1] += r[1] / prof_steps
+        achieved = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["sustained"], "frac_of_burst": achieved / peaks["burst"], "traffic": None,
+                "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a long step)",
+                "kernel": "tc_conv_kernel / tc_wgrad_kernel (tcgen05 implicit GEMM)",
+                "how": f"CUDA events around every unetk_conv/unetk_wgrad launch over {prof_steps} instrumented steps",
+                "share_of_step": kms / prof_steps / step_ms,
+                "ms_per_step_by_kernel": {k: round(v[0], 3) for k, v in sorted(by_kind.items())},
+                "step_tflops": (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12,
+                "step_frac_of_sustained_peak": (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12 / peaks["sustained"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b, times, threads = cpu_reference_steps(steps=3, warmup=1)
+        v = b * len(times) / sum(times)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"3 steps of batch {b} at 256x256 (fp32, {threads} threads, os.cpu_count()={os.cpu_count()})"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"unet(3,3) 256x256 training step, batch {B}/GPU, bf16 activations + fp32 master weights, "
+                                   "WeightedDiceCELoss + AdamW + MetricsHistory",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "per-step working set ~20 GB >> 126 MB L2 (no flush needed)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel(),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU")
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -142,34 +142,63 @@ def nhwc(t: Optional[torch.Tensor]) -> Tensor:
     return Tensor(t.data_ptr(), n, h, w, c, ld, _DTYPES[t.dtype])
 
 
+# ---- instrumentation (bench.py): launch counter and optional per-call CUDA-event records ----------
+COUNTERS = {"launches": 0}
+PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start_event, end_event)
+
+
+def _run(kind, nlaunch, flops, fn, *args):
+    COUNTERS["launches"] += nlaunch
+    hook = PROFILE_HOOK
+    if hook is None:
+        check(fn(*args))
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    check(fn(*args))
+    e1.record()
+    hook.append((kind, flops, e0, e1))
+
+
 # ---- thin wrappers ------------------------------------------------------------------------------
 def im2col3x3_first(x_nchw: torch.Tensor, out: torch.Tensor):
     n, cin, h, w = x_nchw.shape
-    check(lib().unetk_im2col3x3_first(x_nchw.data_ptr(), n, cin, h, w, C.byref(nhwc(out)), stream_ptr()))
+    _run("layout", 1, 0, lib().unetk_im2col3x3_first, x_nchw.data_ptr(), n, cin, h, w, C.byref(nhwc(out)), stream_ptr())
 
 
-def permute3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_strides):
-    check(lib().unetk_permute3(src.data_ptr(), dst.data_ptr(), _DTYPES[dst.dtype], dims[0], dims[1], dims[2],
-                               src_strides[0], src_strides[1], src_strides[2],
-                               dst_strides[0], dst_strides[1], dst_strides[2], stream_ptr()))
+def permute3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_strides, dst_offset_elems: int = 0):
+    _run("layout", 1, 0, lib().unetk_permute3, src.data_ptr(), dst.data_ptr() + dst_offset_elems * dst.element_size(),
+         _DTYPES[dst.dtype], dims[0], dims[1], dims[2], src_strides[0], src_strides[1], src_strides[2],
+         dst_strides[0], dst_strides[1], dst_strides[2], stream_ptr())
 
 
-def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO):
+def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None):
     a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo, ptr(bias), ptr(stat_sum), ptr(stat_sumsq))
-    check(lib().unetk_conv(C.byref(a), stream_ptr()))
+    if algo_flops is None:
+        if mode in (MODE_1X1, MODE_3X3):
+            algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * (9 if mode == MODE_3X3 else 1) * x.shape[3] * y.shape[3]
+        elif mode == MODE_CONVT:
+            algo_flops = 2 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * 4 * y.shape[3]
+        else:
+            algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * 4 * x.shape[3] * y.shape[3]
+    simt = algo == ALGO_SIMT or (algo == ALGO_AUTO and x.dtype != torch.bfloat16)
+    _run("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, C.byref(a), stream_ptr())
 
 
-def wgrad(u, s, dw, mode, algo=ALGO_AUTO):
+def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
     a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo)
-    check(lib().unetk_wgrad(C.byref(a), stream_ptr()))
+    if algo_flops is None:
+        taps = (1, 9, 4)[mode]
+        algo_flops = 2 * u.shape[0] * u.shape[1] * u.shape[2] * taps * u.shape[3] * s.shape[3]
+    _run("wgrad", 1, algo_flops, lib().unetk_wgrad, C.byref(a), stream_ptr())
 
 
 def channel_sum(t, out):
-    check(lib().unetk_channel_sum(C.byref(nhwc(t)), out.data_ptr(), stream_ptr()))
+    _run("reduce", 1, 0, lib().unetk_channel_sum, C.byref(nhwc(t)), out.data_ptr(), stream_ptr())
 
 
 def bn_stats(z, s, ss):
-    check(lib().unetk_bn_stats(C.byref(nhwc(z)), s.data_ptr(), ss.data_ptr(), stream_ptr()))
+    _run("bn_stats", 1, 0, lib().unetk_bn_stats, C.byref(nhwc(z)), s.data_ptr(), ss.data_ptr(), stream_ptr())
 
 
 def bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
@@ -177,31 +206,39 @@ def bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean,
     a = BnFinalizeArgs(ptr(s), ptr(ss), count, c, 1 if training else 0, ptr(gamma), ptr(beta), ptr(conv_bias),
                        ptr(running_mean), ptr(running_var), ptr(nbt), momentum, eps, ptr(scale), ptr(shift),
                        ptr(mean), ptr(invstd))
-    check(lib().unetk_bn_finalize(C.byref(a), stream_ptr()))
+    _run("bn_finalize", 1, 0, lib().unetk_bn_finalize, C.byref(a), stream_ptr())
 
 
 def bn_relu_apply(z, scale, shift, a, pooled=None):
-    check(lib().unetk_bn_relu_apply(C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(), C.byref(nhwc(a)),
-                                    C.byref(nhwc(pooled)), stream_ptr()))
+    _run("bn_apply", 1, 0, lib().unetk_bn_relu_apply, C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(),
+         C.byref(nhwc(a)), C.byref(nhwc(pooled)), stream_ptr())
 
 
 def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta):
     a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
                   ptr(dgamma), ptr(dbeta))
     s = stream_ptr()
-    check(lib().unetk_bn_relu_bwd_reduce(C.byref(a), s))
-    check(lib().unetk_bn_relu_bwd_apply(C.byref(a), s))
+    _run("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, C.byref(a), s)
+    _run("bn_bwd_apply", 1, 0, lib().unetk_bn_relu_bwd_apply, C.byref(a), s)
 
 
 def head_fprop(a, w, b, dout, logits):
-    check(lib().unetk_head_fprop(C.byref(nhwc(a)), w.data_ptr(), ptr(b), dout, logits.data_ptr(), stream_ptr()))
+    _run("head", 1, 0, lib().unetk_head_fprop, C.byref(nhwc(a)), w.data_ptr(), ptr(b), dout, logits.data_ptr(), stream_ptr())
 
 
 def head_bwd(dlogits, a, w, dout, da, dw, db):
-    check(lib().unetk_head_bwd(dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
-                               dw.data_ptr(), ptr(db), stream_ptr()))
+    _run("head", 2, 0, lib().unetk_head_bwd, dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
+         dw.data_ptr(), ptr(db), stream_ptr())
+
+
+def dice_ce_fwd(args):
+    _run("loss", 2, 0, lib().unetk_dice_ce_fwd, C.byref(args), stream_ptr())
+
+
+def dice_ce_bwd(args):
+    _run("loss", 1, 0, lib().unetk_dice_ce_bwd, C.byref(args), stream_ptr())
 
 
 def argmax_confusion(pred, label, n, c, h, w, counts, argmax_out, status):
-    check(lib().unetk_argmax_confusion(pred.data_ptr(), label.data_ptr(), n, c, h, w, counts.data_ptr(),
-                                       ptr(argmax_out), status.data_ptr(), stream_ptr()))
+    _run("metrics", 1, 0, lib().unetk_argmax_confusion, pred.data_ptr(), label.data_ptr(), n, c, h, w, counts.data_ptr(),
+         ptr(argmax_out), status.data_ptr(), stream_ptr())

@@ -248,7 +248,6 @@ class UNetPlan:
         versions = tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
         if versions == self._pack_versions:
             return
-        es = 2 if self.dt == torch.bfloat16 else 4
         for l in self.layers:
             w = l.conv.weight.detach()
             co, ci = l.cout, l.cin
@@ -258,8 +257,7 @@ class UNetPlan:
             else:
                 L.permute3(w, l.wf, (co, ci, 9), (ci * 9, 9, 1), (9 * ci, 1, ci))
                 # data-gradient pack: [ci][8 - t][co]  (flipped taps, transposed channels)
-                L.check(L.lib().unetk_permute3(w.data_ptr(), l.wd.data_ptr() + 8 * co * es, L._DTYPES[self.dt], co, ci, 9,
-                                               ci * 9, 9, 1, 1, 9 * co, -co, L.stream_ptr()))
+                L.permute3(w, l.wd, (co, ci, 9), (ci * 9, 9, 1), (1, 9 * co, -co), dst_offset_elems=8 * co)
         for ct in self.convts:
             w = ct.mod.weight.detach()   # [ci][co][2][2]
             ci, co = ct.cin, ct.cout
@@ -282,7 +280,7 @@ class UNetPlan:
             count = n * l.h * l.w
             L.conv(l.src, l.wf, l.z, L.MODE_1X1 if l.first else L.MODE_3X3,
                    stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
-                   algo=self.algo)
+                   algo=self.algo, algo_flops=(2 * count * 9 * l.cin * l.cout) if l.first else None)
             bn = l.bn
             momentum = bn.momentum if bn.momentum is not None else 0.1
             track = bn.track_running_stats and bn.running_mean is not None
@@ -329,7 +327,7 @@ class UNetPlan:
         def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
             L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias])
             if l.first:
-                L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo)
+                L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo, algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout)
                 L.permute3(l.ws, g[l.conv.weight], (l.cout, l.cin, 9), (self.kpad, 1, l.cin), (l.cin * 9, 9, 1))
             else:
                 L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo)

@@ -11,7 +11,6 @@ Out-of-range labels: the reference raises from ``scatter_`` synchronously.  Here
 device flag; it is checked without stalling the stream on the *next* call (or immediately when
 ``UNETK_STRICT_LABELS=1``), and raises the same ``RuntimeError``.
 """
-import ctypes as C
 import os
 from typing import Optional
 
@@ -63,7 +62,7 @@ class _DiceCEFunction(torch.autograd.Function):
                             cfg["ignore_index"] if cfg["ignore_index"] is not None else 0,
                             cfg["dice_weight"], cfg["ce_weight"], cfg["smooth"], accum.data_ptr(), coef.data_ptr(),
                             loss.data_ptr(), cfg["status"].dev.data_ptr(), None, None)
-        L.check(L.lib().unetk_dice_ce_fwd(C.byref(args), L.stream_ptr()))
+        L.dice_ce_fwd(args)
         ctx.save_for_backward(logits, target, coef)
         ctx.cfg = cfg
         ctx.keep = (cw,)
@@ -82,7 +81,7 @@ class _DiceCEFunction(torch.autograd.Function):
                             cfg["ignore_index"] if cfg["ignore_index"] is not None else 0,
                             cfg["dice_weight"], cfg["ce_weight"], cfg["smooth"], None, coef.data_ptr(), None,
                             cfg["status"].dev.data_ptr(), go.data_ptr(), dlogits.data_ptr())
-        L.check(L.lib().unetk_dice_ce_bwd(C.byref(args), L.stream_ptr()))
+        L.dice_ce_bwd(args)
         return dlogits, None, None
 
 
