@@ -144,7 +144,8 @@ def nhwc(t: Optional[torch.Tensor]) -> Tensor:
 
 # ---- instrumentation (bench.py): launch counter and optional per-call CUDA-event records ----------
 COUNTERS = {"launches": 0}
-PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start_event, end_event)
+PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start_event, end_event, label)
+LABEL = ""            # free-form tag of the layer being launched (set by the engine, read by the hook)
 
 
 def _run(kind, nlaunch, flops, fn, *args):
@@ -157,7 +158,7 @@ def _run(kind, nlaunch, flops, fn, *args):
     e0.record()
     check(fn(*args))
     e1.record()
-    hook.append((kind, flops, e0, e1))
+    hook.append((kind, flops, e0, e1, LABEL))
 
 
 # ---- thin wrappers ------------------------------------------------------------------------------
@@ -227,7 +228,7 @@ def head_fprop(a, w, b, dout, logits):
 
 
 def head_bwd(dlogits, a, w, dout, da, dw, db):
-    _run("head", 2, 0, lib().unetk_head_bwd, dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
+    _run("head", 1, 0, lib().unetk_head_bwd, dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
          dw.data_ptr(), ptr(db), stream_ptr())
 
 

