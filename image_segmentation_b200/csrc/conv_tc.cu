@@ -11,6 +11,9 @@
 // filter-gradient half of convolution_backward for both (tc_wgrad).
 //
 // Roofline: tensor pipe.  Algorithmic FLOPs per launch = 2 * rows * K * N_total.
+#include <stdlib.h>
+#include <string.h>
+
 #include <mutex>
 
 #include "conv_internal.cuh"
@@ -92,100 +95,214 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 }
 
 // =================================================================================================
-// forward-family kernel: y[rows, N] = A[rows, K] * B[N, K]^T, both operands K-major in shared memory
+// forward-family kernels: y[rows, N] = A[rows, K] * B[N, K]^T, both operands K-major in shared memory
+//   tc_conv_kernel       : one TMA box per (tap, 64-channel chunk) -- every mode
+//   tc_conv_halo_kernel  : 3x3 only; ONE (18 x 10 pixel) halo box per 64-channel chunk feeds all 9 taps through
+//                          row-shifted UMMA descriptors (start + (r*10+s)*128 B, SBO = 10*128 B).  tools/umma_probe.cu
+//                          established on B200 that 128B swizzling is a function of the absolute shared-memory address,
+//                          so shifted starts and a 1280-byte group stride address the TMA-written tile consistently.
+//                          Cuts L2->SMEM operand traffic of the A side 6.4x (23 KB instead of 9 x 16 KB per chunk).
 // =================================================================================================
 constexpr int kTileM = 128;
-constexpr int kBlockK = 64;                  // bf16 elements per K step = one 128-byte swizzle row
+constexpr int kBlockK = 64;                    // bf16 elements per K step = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
 constexpr int kNumThreads = 256;
-constexpr int kMaxStatChannels = 1024;
+constexpr int kStagingBytes = kTileM * 128;    // one 128-row x 64-channel bf16 output block
+constexpr int kHaloRows = 18 * 10;             // (16+2) x (8+2) pixels
+constexpr int kHaloBytes = kHaloRows * 128;    // 23040
+constexpr int kHaloStride = 23 * 1024;         // halo buffers on 1 KiB boundaries
+constexpr int kMaxBSlots = 24;
+constexpr int kMaxAStages = 8;
 
 struct ConvParams {
   CUtensorMap map_a[4];
   CUtensorMap map_b;
+  CUtensorMap map_y[4];
   int mode, taps, chunks_per_tap;
   int pw, ph, nb, tiles_w, tiles_h;
   int num_m_tiles, num_n_tiles;
   int n, h, w;          // grid of the GEMM rows
-  __nv_bfloat16* y;
-  int yld, cout;        // cout = channels of y (mode 2: N_total = 4*cout)
+  int cout;             // channels of y (mode 2: N_total = 4*cout)
   const float* bias;
   double* stat_sum;
   double* stat_sumsq;
+  // shared-memory plan (bytes from the 1 KiB aligned base)
+  int stages;           // per-tap kernel: ring depth; halo kernel: halo ring depth
+  int b_slots;          // halo kernel: B ring depth (== K steps when resident)
+  int resident_b;       // halo kernel: B loaded once and kept for every tile
+  int num_staging;      // 1 or 2 epilogue staging blocks
+  uint32_t off_b, off_staging, off_stats, off_bars;
+  int stat_channels;    // size of each statistics array in shared memory (0 = none)
 };
 
+// barrier block: [fullA 8][emptyA 8][fullB 24][emptyB 24][tmem_full 2][tmem_empty 2] + tmem pointer
+constexpr int kBarBytes = (2 * kMaxAStages + 2 * kMaxBSlots + 4) * 8 + 16;
+
+struct Bars {
+  uint64_t* full_a;
+  uint64_t* empty_a;
+  uint64_t* full_b;
+  uint64_t* empty_b;
+  uint64_t* tmem_full;
+  uint64_t* tmem_empty;
+  uint32_t* tmem_ptr;
+  __device__ explicit Bars(uint8_t* base) {
+    full_a = reinterpret_cast<uint64_t*>(base);
+    empty_a = full_a + kMaxAStages;
+    full_b = empty_a + kMaxAStages;
+    empty_b = full_b + kMaxBSlots;
+    tmem_full = empty_b + kMaxBSlots;
+    tmem_empty = tmem_full + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  }
+};
+
+// Epilogue of one accumulator tile (128 rows x BLOCK_N fp32 in TMEM), executed by the 4 epilogue warps:
+//   TMEM -> registers (+bias) -> bf16 -> 128B-swizzled staging block in shared memory -> TMA store (clipped at the
+//   tensor edge) ; BatchNorm batch statistics are column sums over the staged (bf16-rounded) block.
 template <int BLOCK_N>
-struct ConvCfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  // ring | stats (2 x 1024 floats) | barriers | tmem ptr
-  static constexpr int kStatsOff = kStages * kStageBytes;
-  static constexpr int kBarOff = kStatsOff + 2 * kMaxStatChannels * 4;
-  static constexpr int kSmemBytes = kBarOff + (2 * kStages + 4) * 8 + 16 + 1024;  // + slack for 1024B alignment
-};
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* smem, uint32_t tmem_acc, int q, int lane,
+                                              bool valid_row, int col0, int w0, int h0, int n0, uint32_t& store_count,
+                                              uint64_t* tmem_empty_bar) {
+  const int row = q * 32 + lane;
+  const bool storer = (q == 0 && lane == 0);
+  const bool do_stats = p.stat_channels > 0;
+  float* stat_s1 = reinterpret_cast<float*>(smem + p.off_stats);
+  float* stat_s2 = stat_s1 + p.stat_channels;
+  int map_idx = 0, ch0 = col0;
+  if (p.mode == 2) {
+    map_idx = col0 / p.cout;
+    ch0 = col0 % p.cout;
+  }
+#pragma unroll 1
+  for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
+    const uint32_t buf = p.num_staging == 2 ? (store_count & 1u) : 0u;
+    uint8_t* staging = smem + p.off_staging + buf * kStagingBytes;
+    const uint32_t srow = smem_u32(staging) + row * 128;
+    if (storer) {
+      if (p.num_staging == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    }
+    named_bar_sync(1, 128);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + blk * 64 + half * 32, r);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float lo = __uint_as_float(r[2 * j]), hi = __uint_as_float(r[2 * j + 1]);
+        if (p.bias) {
+          lo += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j);
+          hi += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j + 1);
+        }
+        packed[j] = valid_row ? pack_bf16x2(lo, hi) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t chunk = (uint32_t)(half * 4 + j) ^ (uint32_t)(row & 7);
+        st_shared_v4(srow + chunk * 16, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+    }
+    if (blk == BLOCK_N / 64 - 1) {
+      // accumulator fully drained: hand the TMEM stage back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (storer) {
+      tma_store_4d(&p.map_y[map_idx], staging, ch0 + blk * 64, w0, h0, n0);
+      tma_store_commit();
+    }
+    if (do_stats) {
+      // thread (q, lane): channel pair `lane` of this 64-channel block, rows q*32 .. q*32+31
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      const uint32_t base = smem_u32(staging) + (uint32_t)(lane & 3) * 4;
+#pragma unroll 8
+      for (int i = 0; i < 32; ++i) {
+        const int rr = q * 32 + i;
+        const uint32_t word = ld_shared_u32(base + rr * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(rr & 7)) << 4));
+        const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
+        s1a += lo;
+        s1b += hi;
+        s2a = fmaf(lo, lo, s2a);
+        s2b = fmaf(hi, hi, s2b);
+      }
+      const int ch = ch0 + blk * 64 + 2 * lane;
+      atomicAdd(&stat_s1[ch], s1a);
+      atomicAdd(&stat_s1[ch + 1], s1b);
+      atomicAdd(&stat_s2[ch], s2a);
+      atomicAdd(&stat_s2[ch + 1], s2b);
+    }
+    ++store_count;
+  }
+}
 
-// warp-level "transpose reduce": on return lane L holds sum over the 32 lanes of v[L]
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+__device__ __forceinline__ void init_common(const ConvParams& p, uint8_t* smem, Bars& bars, int warp, int lane, int a_stages,
+                                            int b_slots) {
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_a[0]);
+    prefetch_tensormap(&p.map_b);
+    prefetch_tensormap(&p.map_y[0]);
+    if (p.mode >= 2)
+      for (int i = 1; i < 4; ++i) prefetch_tensormap(p.mode == 3 ? &p.map_a[i] : &p.map_y[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a_stages; ++i) {
+      mbar_init(&bars.full_a[i], 1);
+      mbar_init(&bars.empty_a[i], 1);
+    }
+    for (int i = 0; i < b_slots; ++i) {
+      mbar_init(&bars.full_b[i], 1);
+      mbar_init(&bars.empty_b[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.tmem_full[i], 1);
+      mbar_init(&bars.tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (p.stat_channels > 0) {
+    float* st = reinterpret_cast<float*>(smem + p.off_stats);
+    for (int i = threadIdx.x; i < 2 * p.stat_channels; i += kNumThreads) st[i] = 0.f;
+  }
+}
+
+__device__ __forceinline__ void flush_stats(const ConvParams& p, uint8_t* smem) {
+  if (p.stat_channels > 0) {
+    const float* s1 = reinterpret_cast<const float*>(smem + p.off_stats);
+    const float* s2 = s1 + p.stat_channels;
+    for (int i = threadIdx.x; i < p.stat_channels; i += kNumThreads) {
+      const float a = s1[i], b = s2[i];
+      if (a != 0.f || b != 0.f) {
+        atomicAdd(p.stat_sum + i, (double)a);
+        atomicAdd(p.stat_sumsq + i, (double)b);
+      }
     }
   }
-  return v[0];
 }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ ConvParams p) {
-  using Cfg = ConvCfg<BLOCK_N>;
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* stat_s1 = reinterpret_cast<float*>(smem + Cfg::kStatsOff);
-  float* stat_s2 = stat_s1 + kMaxStatChannels;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-
+  Bars bars(smem + p.off_bars);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int ksteps = p.taps * p.chunks_per_tap;
-  const bool do_stats = p.stat_sum != nullptr;
+  const int stages = p.stages;
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&p.map_a[0]);
-    prefetch_tensormap(&p.map_b);
-    if (p.mode == 3) {
-      prefetch_tensormap(&p.map_a[1]);
-      prefetch_tensormap(&p.map_a[2]);
-      prefetch_tensormap(&p.map_a[3]);
-    }
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
-  if (do_stats)
-    for (int i = threadIdx.x; i < 2 * kMaxStatChannels; i += kNumThreads) stat_s1[i] = 0.f;
+  init_common(p, smem, bars, warp, lane, stages, 0);
+  if (warp == 2) tmem_alloc<kTmemCols>(bars.tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = *bars.tmem_ptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -205,19 +322,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
           } else if (p.mode == 3) {
             mi = t;
           }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(sa, &p.map_a[mi], &full_bar[stage], chunk * kBlockK, w0 + dw, h0 + dh, n0);
-          tma_load_2d(sb, &p.map_b, &full_bar[stage], s * kBlockK, n_tile * BLOCK_N);
-          if (++stage == Cfg::kStages) {
+          mbar_wait(&bars.empty_a[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&bars.full_a[stage], kStageBytes);
+          tma_load_4d(sa, &p.map_a[mi], &bars.full_a[stage], chunk * kBlockK, w0 + dw, h0 + dh, n0);
+          tma_load_2d(sa + kABytes, &p.map_b, &bars.full_a[stage], s * kBlockK, n_tile * BLOCK_N);
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
     if (lane == 0) {
@@ -228,13 +345,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int s = 0; s < ksteps; ++s) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&bars.full_a[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
           const uint64_t da = make_smem_desc(sa, 0, 1024);
           const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
 #pragma unroll
@@ -242,101 +359,191 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
             // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
             umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
+          umma_commit(&bars.empty_a[stage]);
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        umma_commit(&bars.tmem_full[acc]);
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp - 4;  // TMEM lane quadrant
     const int row = q * 32 + lane;
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
+    uint32_t store_count = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
-      const int x = tw * p.pw + pw_i, y = th * p.ph + ph_i, img = tn * p.nb + nb_i;
-      const bool valid = x < p.w && y < p.h && img < p.n;
+      const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
+      const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      mbar_wait(&bars.tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int col0 = n_tile * BLOCK_N;
-      // destination pixel
-      int64_t opix;
-      int ch0;
-      if (p.mode == 2) {
-        const int quad = col0 / p.cout;
-        ch0 = col0 % p.cout;
-        opix = ((int64_t)img * (2 * p.h) + 2 * y + (quad >> 1)) * (2 * p.w) + 2 * x + (quad & 1);
-      } else {
-        ch0 = col0;
-        opix = ((int64_t)img * p.h + y) * p.w + x;
-      }
-      __nv_bfloat16* dst = p.y + opix * p.yld + ch0;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float f = __uint_as_float(r[j]);
-          if (p.bias) f += __ldg(p.bias + ch0 + c * 32 + j);
-          v[j] = f;
-        }
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        if (valid) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) d4[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        }
-        if (do_stats) {
-          // statistics of the values as stored (bf16-rounded), invalid rows contribute zero
-          float s1[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float lo = valid ? __uint_as_float(packed[j] << 16) : 0.f;
-            const float hi = valid ? __uint_as_float(packed[j] & 0xffff0000u) : 0.f;
-            s1[2 * j] = lo;
-            s1[2 * j + 1] = hi;
-            s2[2 * j] = lo * lo;
-            s2[2 * j + 1] = hi * hi;
-          }
-          const float t1 = warp_transpose_reduce(s1, lane);
-          const float t2 = warp_transpose_reduce(s2, lane);
-          atomicAdd(&stat_s1[ch0 + c * 32 + lane], t1);
-          atomicAdd(&stat_s2[ch0 + c * 32 + lane], t2);
-        }
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      epilogue_tile<BLOCK_N>(p, smem, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N, q, lane, valid,
+                             n_tile * BLOCK_N, w0, h0, n0, store_count, &bars.tmem_empty[acc]);
     }
+    if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (do_stats) {
-    for (int i = threadIdx.x; i < p.cout; i += kNumThreads) {
-      const float a = stat_s1[i], b = stat_s2[i];
-      if (a != 0.f || b != 0.f) {
-        atomicAdd(p.stat_sum + i, (double)a);
-        atomicAdd(p.stat_sumsq + i, (double)b);
-      }
-    }
-  }
+  flush_stats(p, smem);
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars bars(smem + p.off_bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int cpt = p.chunks_per_tap;
+  const int a_stages = p.stages, b_slots = p.b_slots;
+  const bool resident = p.resident_b != 0;
+
+  init_common(p, smem, bars, warp, lane, a_stages, b_slots);
+  if (warp == 2) tmem_alloc<kTmemCols>(bars.tmem_ptr);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *bars.tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * 8, h0 = th * 16;
+        for (int chunk = 0; chunk < cpt; ++chunk) {
+          mbar_wait(&bars.empty_a[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&bars.full_a[sa], kHaloBytes);
+          tma_load_4d(smem + sa * kHaloStride, &p.map_a[0], &bars.full_a[sa], chunk * kBlockK, w0 - 1, h0 - 1, tn);
+          if (++sa == a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            if (resident) {
+              if (first) {
+                const int slot = chunk * 9 + tap;
+                mbar_arrive_expect_tx(&bars.full_b[slot], kBBytes);
+                tma_load_2d(smem + p.off_b + slot * kBBytes, &p.map_b, &bars.full_b[slot], (tap * cpt + chunk) * kBlockK,
+                            n_tile * BLOCK_N);
+              }
+            } else {
+              mbar_wait(&bars.empty_b[sb], pb ^ 1);
+              mbar_arrive_expect_tx(&bars.full_b[sb], kBBytes);
+              tma_load_2d(smem + p.off_b + sb * kBBytes, &p.map_b, &bars.full_b[sb], (tap * cpt + chunk) * kBlockK,
+                          n_tile * BLOCK_N);
+              if (++sb == b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first = true;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int chunk = 0; chunk < cpt; ++chunk) {
+          mbar_wait(&bars.full_a[sa], pa);
+          tcgen05_fence_after();
+          const uint32_t halo = smem_u32(smem + sa * kHaloStride);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t bslot;
+            if (resident) {
+              bslot = chunk * 9 + tap;
+              if (first) {
+                mbar_wait(&bars.full_b[bslot], 0);
+                tcgen05_fence_after();
+              }
+            } else {
+              bslot = sb;
+              mbar_wait(&bars.full_b[sb], pb);
+              tcgen05_fence_after();
+            }
+            // tap (r,s): output pixel (ph,pw) reads halo pixel (ph+r, pw+s) = halo row (ph+r)*10 + pw+s
+            const uint32_t a0 = halo + ((tap / 3) * 10 + (tap % 3)) * 128;
+            const uint64_t da = make_smem_desc(a0, 0, 10 * 128);
+            const uint64_t db = make_smem_desc(smem_u32(smem + p.off_b + bslot * kBBytes), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if (!resident) {
+              umma_commit(&bars.empty_b[sb]);
+              if (++sb == b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+          umma_commit(&bars.empty_a[sa]);
+          if (++sa == a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit(&bars.tmem_full[acc]);
+        first = false;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    const int pw_i = row & 7, ph_i = row >> 3;
+    uint32_t store_count = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+      const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 8, h0 = th * 16;
+      const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&bars.tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BLOCK_N>(p, smem, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N, q, lane, valid,
+                             n_tile * BLOCK_N, w0, h0, tn, store_count, &bars.tmem_empty[acc]);
+    }
+    if (q == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  flush_stats(p, smem);
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -535,14 +742,20 @@ static int set_smem_attr(K kernel, int bytes) {
   return UNETK_OK;
 }
 
+constexpr int kMaxSmem = 227 * 1024;
+
 template <int BLOCK_N>
-static int launch_conv(const ConvParams& p, cudaStream_t stream) {
-  using Cfg = ConvCfg<BLOCK_N>;
-  static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N>, Cfg::kSmemBytes);
+static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, cudaStream_t stream) {
+  static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N>, kMaxSmem);
+  static int attr_rc2 = set_smem_attr(tc_conv_halo_kernel<BLOCK_N>, kMaxSmem);
   if (attr_rc) return attr_rc;
+  if (attr_rc2) return attr_rc2;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  tc_conv_kernel<BLOCK_N><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  if (halo)
+    tc_conv_halo_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  else
+    tc_conv_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
@@ -574,44 +787,110 @@ bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char**
     *why = "pointers must be 16B aligned and pixel strides multiples of 8";
     return false;
   }
-  if (a->stat_sum && g.cout > tc::kMaxStatChannels) { *why = "statistics support at most 1024 channels"; return false; }
+  if (a->stat_sum && g.cout > 4096) { *why = "statistics support at most 4096 channels"; return false; }
   return true;
+}
+
+static bool halo_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UNETK_NO_HALO");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   using namespace tc;
   ConvParams p;
   memset(&p, 0, sizeof(p));
-  const PixelTile pt = choose_pixel_tile(g.rows_n, g.rows_h, g.rows_w);
   int rc;
-  if (a->mode == 3) {
-    for (int t = 0; t < 4; ++t)
-      if ((rc = make_act_map(&p.map_a[t], a->x, pt.pw, pt.ph, pt.nb, 2, t >> 1, t & 1))) return rc;
-  } else {
-    if ((rc = make_act_map(&p.map_a[0], a->x, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
-  }
   // N tile: the widest of 256/128/64 that divides the channel count of one output slice
   const int nslice = g.cout;  // mode 2: a tile must stay inside one (a,b) quadrant
   const int block_n = nslice % 256 == 0 ? 256 : (nslice % 128 == 0 ? 128 : 64);
+  const int b_bytes = block_n * kBlockK * 2;
   const int64_t ktotal = (int64_t)g.taps * g.cin;
+  const int cpt = g.cin / 64;
+  // halo variant: 3x3, N tile <= 128 (the layers whose operand traffic is L2-bound), image at least one tile big
+  const bool halo = a->mode == 1 && block_n <= 128 && g.rows_h >= 16 && g.rows_w >= 8 && !halo_disabled();
+  PixelTile pt;
+  if (halo) {
+    pt.pw = 8; pt.ph = 16; pt.nb = 1;
+    pt.tiles_w = (g.rows_w + 7) / 8;
+    pt.tiles_h = (g.rows_h + 15) / 16;
+    pt.tiles_n = g.rows_n;
+    if ((rc = make_act_map(&p.map_a[0], a->x, 10, 18, 1, 1, 0, 0))) return rc;
+  } else {
+    pt = choose_pixel_tile(g.rows_n, g.rows_h, g.rows_w);
+    if (a->mode == 3) {
+      for (int t = 0; t < 4; ++t)
+        if ((rc = make_act_map(&p.map_a[t], a->x, pt.pw, pt.ph, pt.nb, 2, t >> 1, t & 1))) return rc;
+    } else {
+      if ((rc = make_act_map(&p.map_a[0], a->x, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+    }
+  }
+  if (a->mode == 2) {
+    for (int t = 0; t < 4; ++t)
+      if ((rc = make_act_map(&p.map_y[t], a->y, pt.pw, pt.ph, pt.nb, 2, t >> 1, t & 1))) return rc;
+  } else {
+    if ((rc = make_act_map(&p.map_y[0], a->y, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+  }
   if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, block_n))) return rc;
   p.mode = a->mode;
   p.taps = g.taps;
-  p.chunks_per_tap = g.cin / 64;
+  p.chunks_per_tap = cpt;
   p.pw = pt.pw; p.ph = pt.ph; p.nb = pt.nb; p.tiles_w = pt.tiles_w; p.tiles_h = pt.tiles_h;
   UNETK_REQUIRE(pt.num_tiles() * (g.cout_total / block_n) < (1LL << 31), "conv(tc): too many tiles");
   p.num_m_tiles = (int)pt.num_tiles();
   p.num_n_tiles = g.cout_total / block_n;
   p.n = g.rows_n; p.h = g.rows_h; p.w = g.rows_w;
-  p.y = static_cast<__nv_bfloat16*>(a->y.ptr);
-  p.yld = a->y.ld;
   p.cout = g.cout;
   p.bias = a->bias;
   p.stat_sum = a->stat_sum;
   p.stat_sumsq = a->stat_sumsq;
-  if (block_n == 256) return launch_conv<256>(p, stream);
-  if (block_n == 128) return launch_conv<128>(p, stream);
-  return launch_conv<64>(p, stream);
+  p.stat_channels = a->stat_sum ? g.cout : 0;
+  // ---- shared-memory plan ----
+  const int stats_bytes = ((2 * p.stat_channels * 4 + 127) / 128) * 128;
+  const int budget = kMaxSmem - 1024 /*alignment slack*/ - kBarBytes - stats_bytes;
+  int ring_bytes;
+  if (!halo) {
+    const int stage_bytes = kABytes + b_bytes;
+    p.num_staging = 2;
+    p.stages = (budget - 2 * kStagingBytes) / stage_bytes;
+    if (p.stages < 4) {
+      p.num_staging = 1;
+      p.stages = (budget - kStagingBytes) / stage_bytes;
+    }
+    if (p.stages > kMaxAStages) p.stages = kMaxAStages;
+    ring_bytes = p.stages * stage_bytes;
+    p.off_b = 0;
+  } else {
+    const int ksteps = 9 * cpt;
+    p.resident_b = (p.num_n_tiles == 1 && ksteps <= kMaxBSlots && ksteps * b_bytes + 2 * kHaloStride + kStagingBytes <= budget) ? 1 : 0;
+    if (p.resident_b) {
+      p.b_slots = ksteps;
+      const int rest = budget - ksteps * b_bytes;
+      p.num_staging = (rest - 2 * kStagingBytes) >= 2 * kHaloStride ? 2 : 1;
+      p.stages = (rest - p.num_staging * kStagingBytes) / kHaloStride;
+      if (p.stages > 4) p.stages = 4;
+    } else {
+      p.num_staging = 2;
+      p.stages = 3;
+      p.b_slots = (budget - 2 * kStagingBytes - p.stages * kHaloStride) / b_bytes;
+      if (p.b_slots > 9) p.b_slots = 9;
+      UNETK_REQUIRE(p.b_slots >= 2, "conv(tc halo): shared-memory plan failed");
+    }
+    p.off_b = p.stages * kHaloStride;
+    ring_bytes = p.off_b + p.b_slots * b_bytes;
+  }
+  p.off_staging = ring_bytes;
+  p.off_stats = p.off_staging + p.num_staging * kStagingBytes;
+  p.off_bars = p.off_stats + stats_bytes;
+  const int smem_bytes = p.off_bars + kBarBytes + 1024;
+  UNETK_REQUIRE(smem_bytes <= kMaxSmem && p.stages >= 2, "conv(tc): shared-memory plan failed (%d bytes, %d stages)", smem_bytes, p.stages);
+  if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, stream);
+  if (block_n == 128) return launch_conv<128>(p, smem_bytes, halo, stream);
+  return launch_conv<64>(p, smem_bytes, halo, stream);
 }
 
 bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {

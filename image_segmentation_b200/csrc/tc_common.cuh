@@ -57,6 +57,33 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* map, uin
       : "memory");
 }
 
+// TMA store (shared -> global, bulk-group completion); out-of-range parts of the box are clipped by hardware
+__device__ __forceinline__ void tma_store_4d(const void* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (TMA) before a bulk store
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // whole warp
@@ -129,7 +156,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_fn();
 
 // bf16 NHWC activation view as a 4-D map (C, W, H, N) with a (64, pw, ph, nb) box, 128B swizzle, zero OOB fill.
-// `step` = 1 for the tensor itself; 2 selects every other pixel starting at (oh, ow) (stride-2 gather views).
+// `step` = 1 for the tensor itself; 2 selects every other pixel starting at (oh, ow) (stride-2 gather/scatter views).
+// The same maps serve TMA loads (operands) and TMA stores (epilogue; out-of-range rows are clipped).
 int make_act_map(CUtensorMap* map, const unetk_tensor& t, int pw, int ph, int nb, int step, int oh, int ow);
 // bf16 row-major matrix [rows][k] (k contiguous) as a 2-D map with a (64, box_rows) box, 128B swizzle
 int make_mat_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t k, int box_rows);

@@ -42,7 +42,11 @@ IDS = ["f32-simt", "bf16-simt", "bf16-tc"]
 
 @pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (1, 8, 24, 128, 64), (3, 4, 4, 64, 256), (2, 32, 32, 64, 128),
-                                              (5, 2, 2, 128, 128)])
+                                              (5, 2, 2, 128, 128),
+                                              # halo kernel: resident 18-slot B, streamed B (K steps > 24), partial tiles,
+                                              # several N tiles, many tiles per CTA
+                                              (1, 24, 20, 128, 64), (2, 16, 8, 256, 128), (1, 32, 16, 64, 192), (3, 48, 40, 64, 64),
+                                              (2, 128, 128, 64, 64), (1, 16, 16, 512, 256)])
 def test_conv3x3_fprop_with_stats(dt, algo, n, h, w, cin, cout):
     x = rnd((n, h, w, cin), dt, 1)
     wt = rnd((cout, cin, 3, 3), dt, 2, 0.05)
