@@ -736,6 +736,176 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   }
 }
 
+// =================================================================================================
+// 3x3 weight gradient, halo form.  Work item = (cu tile, 64-channel cs slab, kernel row r, pixel split).
+// Per 128-pixel block (16 x 8 patch) ONE band of the shifted operand (16 x 10 pixels, rows h0-1+r ..) is loaded; the
+// three taps s = 0,1,2 of kernel row r are the same band shifted by one pixel, i.e. by one 128-byte shared-memory row.
+// A single MMA of N = 192 therefore covers all three taps: its B descriptor uses LBO = 128 B (atom j = tap s=j) and
+// SBO = 10*128 B (next image row inside the band).  Versus the per-tap kernel this is 3x fewer, 3x wider MMAs and
+// 3x less operand traffic.   dw[cu, 3r+s, cs] += sum_p U[p, cu] * S[p + (r-1, s-1), cs]
+// =================================================================================================
+constexpr int kBandBytes = 16 * 10 * 128;  // 20480
+
+template <int BM_SLABS>
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kUBytes = BM_SLABS * kABytes;
+  constexpr int kStageBytes = kUBytes + kBandBytes;
+  constexpr int kStages = (220 * 1024) / kStageBytes > 8 ? 8 : (220 * 1024) / kStageBytes;
+  constexpr int BLOCK_N = 192;
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.cu_tiles * p.cs_tiles * 3 * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_u);
+    prefetch_tensormap(&p.map_s[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](int item, int& cu_t, int& cs_t, int& r, int& split) {
+    split = item % p.splits;
+    int q = item / p.splits;
+    r = q % 3;
+    q /= 3;
+    cs_t = q % p.cs_tiles;
+    cu_t = q / p.cs_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int cu_t, cs_t, r, split;
+        decode(item, cu_t, cs_t, r, split);
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tw = pt % p.tiles_w, th = (pt / p.tiles_w) % p.tiles_h, tn = pt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * 8, h0 = th * 16;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* su = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+#pragma unroll
+          for (int i = 0; i < BM_SLABS; ++i)
+            tma_load_4d(su + i * kABytes, &p.map_u, &full_bar[stage], (cu_t * BM_SLABS + i) * 64, w0, h0, tn);
+          tma_load_4d(su + kUBytes, &p.map_s[0], &full_bar[stage], cs_t * 64, w0 - 1, h0 - 1 + r, tn);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      constexpr uint32_t lbo_a = BM_SLABS == 2 ? kABytes : 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        int cu_t, cs_t, r, split;
+        decode(item, cu_t, cs_t, r, split);
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t su = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sband = su + kUBytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // K block k = image rows 2k, 2k+1 of the patch: U rows 16k..16k+15; band rows (2k)*10 .. , next row +1280 B
+            const uint64_t da = make_smem_desc(su + k * 2048, lbo_a, 1024);
+            const uint64_t db = make_smem_desc(sband + k * 2560, 128, 1280);
+            umma_bf16(d_tmem, da, db, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int cu_t, cs_t, r, split;
+      decode(item, cu_t, cs_t, r, split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int cu_idx = cu_t * (BM_SLABS * 64) + row;
+      const bool valid = row < BM_SLABS * 64 && cu_idx < p.cu;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t rg[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + c * 32, rg);
+        tmem_ld_wait();
+        if (valid) {
+          const int s_tap = c >> 1;
+          float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + s_tap)) * p.cs + cs_t * 64 + (c & 1) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+template <int BM_SLABS>
+constexpr int wgrad3x3_smem_bytes() {
+  constexpr int stage = BM_SLABS * kABytes + kBandBytes;
+  constexpr int stages = (220 * 1024) / stage > 8 ? 8 : (220 * 1024) / stage;
+  return stages * stage + (2 * stages + 4) * 8 + 16 + 1024;
+}
+
 template <typename K>
 static int set_smem_attr(K kernel, int bytes) {
   UNETK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
@@ -768,6 +938,18 @@ static int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
   const int items = p.cu_tiles * p.cs_tiles * p.taps * p.splits;
   const int grid = items < sm_count() ? items : sm_count();
   tc_wgrad_kernel<BM_SLABS, BN_SLABS><<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(p);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+template <int BM_SLABS>
+static int launch_wgrad3x3(const WgradParams& p, cudaStream_t stream) {
+  constexpr int smem_bytes = wgrad3x3_smem_bytes<BM_SLABS>();
+  static int attr_rc = set_smem_attr(tc_wgrad3x3_kernel<BM_SLABS>, smem_bytes);
+  if (attr_rc) return attr_rc;
+  const int items = p.cu_tiles * p.cs_tiles * 3 * p.splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  tc_wgrad3x3_kernel<BM_SLABS><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
@@ -904,8 +1086,40 @@ bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
   return true;
 }
 
+static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
+  using namespace tc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = make_act_map(&p.map_u, a->u, 8, 16, 1, 1, 0, 0))) return rc;
+  if ((rc = make_act_map(&p.map_s[0], a->s, 10, 16, 1, 1, 0, 0))) return rc;
+  const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1;
+  p.mode = 1;
+  p.taps = 9;
+  p.pw = 8; p.ph = 16; p.nb = 1;
+  p.tiles_w = (a->u.w + 7) / 8;
+  p.tiles_h = (a->u.h + 15) / 16;
+  const int64_t ptiles = (int64_t)p.tiles_w * p.tiles_h * a->u.n;
+  UNETK_REQUIRE(ptiles < (1LL << 30), "wgrad(tc): too many pixel tiles");
+  p.num_ptiles = (int)ptiles;
+  p.cu = a->u.c; p.cs = a->s.c;
+  p.cu_tiles = a->u.c / (64 * bm_slabs);
+  p.cs_tiles = a->s.c / 64;
+  const int64_t out_tiles = (int64_t)p.cu_tiles * p.cs_tiles * 3;
+  int64_t splits = (2LL * sm_count() + out_tiles - 1) / out_tiles;
+  const int64_t max_splits = (p.num_ptiles + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.ptiles_per_split = (int)((p.num_ptiles + splits - 1) / splits);
+  p.splits = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
+  p.dw = a->dw;
+  return bm_slabs == 2 ? launch_wgrad3x3<2>(p, stream) : launch_wgrad3x3<1>(p, stream);
+}
+
 int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
   using namespace tc;
+  if (a->mode == 1 && a->u.h >= 16 && a->u.w >= 8 && !halo_disabled()) return tc_wgrad3x3_halo(a, stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   const PixelTile pt = choose_pixel_tile(a->u.n, a->u.h, a->u.w);

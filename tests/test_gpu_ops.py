@@ -100,7 +100,8 @@ def test_conv_transpose_fprop_into_concat_slice_and_dgrad(dt, algo, n, h, w, cin
 
 
 @pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
-@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 8, 8, 128, 64), (1, 16, 32, 64, 128), (3, 4, 4, 256, 128)])
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 8, 8, 128, 64), (1, 16, 32, 64, 128), (3, 4, 4, 256, 128),
+                                              (2, 32, 24, 128, 256), (1, 48, 40, 64, 64), (4, 64, 64, 64, 64), (1, 16, 16, 512, 128)])
 def test_conv3x3_dgrad_and_wgrad(dt, algo, n, h, w, cin, cout):
     x = rnd((n, h, w, cin), dt, 10)
     wt = rnd((cout, cin, 3, 3), dt, 11, 0.05)
