@@ -106,7 +106,8 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                    // bf16 elements per K step = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 256;       // wgrad kernels: 4 control warps + 4 epilogue warps
+constexpr int kConvThreads = 384;      // conv kernels: 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kStagingBytes = kTileM * 128;    // one 128-row x 64-channel bf16 output block
 constexpr int kHaloRows = 18 * 10;             // (16+2) x (8+2) pixels
 constexpr int kHaloBytes = kHaloRows * 128;    // 23040
@@ -157,42 +158,74 @@ struct Bars {
   }
 };
 
-// Epilogue of one accumulator tile (128 rows x BLOCK_N fp32 in TMEM), executed by the 4 epilogue warps:
-//   TMEM -> registers (+bias) -> bf16 -> 128B-swizzled staging block in shared memory -> TMA store (clipped at the
-//   tensor edge) ; BatchNorm batch statistics are column sums over the staged (bf16-rounded) block.
+// Epilogue of one accumulator tile (128 rows x BLOCK_N fp32 in TMEM), executed by ONE of the two epilogue groups
+// (4 warps each; group g serves accumulator stage g, staging block g, named barrier 1+g, so two tiles drain
+// concurrently):  TMEM -> registers (+bias) -> bf16 -> 128B-swizzled staging block in shared memory -> TMA store
+// (clipped at the tensor edge).  BatchNorm batch statistics are column sums over the staged (bf16-rounded) block,
+// kept in registers across tiles (a thread always owns the same channel pair) and flushed with fp64 atomics.
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* smem, uint32_t tmem_acc, int q, int lane,
-                                              bool valid_row, int col0, int w0, int h0, int n0, uint32_t& store_count,
-                                              uint64_t* tmem_empty_bar) {
+struct StatRegs {
+  float v[BLOCK_N / 64][4];
+  int n_tile;
+  __device__ void clear() {
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 64; ++i) v[i][0] = v[i][1] = v[i][2] = v[i][3] = 0.f;
+  }
+  __device__ void flush(const ConvParams& p, int lane) {
+    if (n_tile < 0) return;
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 64; ++i) {
+      const int ch = n_tile * BLOCK_N + i * 64 + 2 * lane;
+      atomicAdd(p.stat_sum + ch, (double)v[i][0]);
+      atomicAdd(p.stat_sum + ch + 1, (double)v[i][1]);
+      atomicAdd(p.stat_sumsq + ch, (double)v[i][2]);
+      atomicAdd(p.stat_sumsq + ch + 1, (double)v[i][3]);
+    }
+    clear();
+  }
+};
+
+template <int BLOCK_N, bool HAS_BIAS>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* staging, int bar_id, uint32_t tmem_acc, int q,
+                                              int lane, bool valid_row, int n_tile, int w0, int h0, int n0,
+                                              StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar) {
   const int row = q * 32 + lane;
   const bool storer = (q == 0 && lane == 0);
-  const bool do_stats = p.stat_channels > 0;
-  float* stat_s1 = reinterpret_cast<float*>(smem + p.off_stats);
-  float* stat_s2 = stat_s1 + p.stat_channels;
+  const bool do_stats = p.stat_sum != nullptr;
+  const int col0 = n_tile * BLOCK_N;
   int map_idx = 0, ch0 = col0;
   if (p.mode == 2) {
     map_idx = col0 / p.cout;
     ch0 = col0 % p.cout;
   }
-#pragma unroll 1
+  if (do_stats && st.n_tile != n_tile) {
+    st.flush(p, lane);
+    st.n_tile = n_tile;
+  }
+  const uint32_t sbase = smem_u32(staging);
+  const uint32_t srow = sbase + row * 128;
+#pragma unroll
   for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
-    const uint32_t buf = p.num_staging == 2 ? (store_count & 1u) : 0u;
-    uint8_t* staging = smem + p.off_staging + buf * kStagingBytes;
-    const uint32_t srow = smem_u32(staging) + row * 128;
-    if (storer) {
-      if (p.num_staging == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+    if (storer) tma_store_wait_read<0>();   // the previous store out of this staging block has been read
+    named_bar_sync(bar_id, 128);
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(tmem_acc + blk * 64, r0);
+    tmem_ld_32x32(tmem_acc + blk * 64 + 32, r1);
+    tmem_ld_wait();
+    if (blk == BLOCK_N / 64 - 1) {
+      // accumulator fully drained: hand the TMEM stage back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
     }
-    named_bar_sync(1, 128);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_acc + blk * 64 + half * 32, r);
-      tmem_ld_wait();
       uint32_t packed[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float lo = __uint_as_float(r[2 * j]), hi = __uint_as_float(r[2 * j + 1]);
-        if (p.bias) {
+        float lo = __uint_as_float(half ? r1[2 * j] : r0[2 * j]);
+        float hi = __uint_as_float(half ? r1[2 * j + 1] : r0[2 * j + 1]);
+        if (HAS_BIAS) {
           lo += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j);
           hi += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j + 1);
         }
@@ -204,14 +237,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* smem
         st_shared_v4(srow + chunk * 16, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
       }
     }
-    if (blk == BLOCK_N / 64 - 1) {
-      // accumulator fully drained: hand the TMEM stage back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar);
-    }
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(bar_id, 128);
     if (storer) {
       tma_store_4d(&p.map_y[map_idx], staging, ch0 + blk * 64, w0, h0, n0);
       tma_store_commit();
@@ -219,24 +246,22 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* smem
     if (do_stats) {
       // thread (q, lane): channel pair `lane` of this 64-channel block, rows q*32 .. q*32+31
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-      const uint32_t base = smem_u32(staging) + (uint32_t)(lane & 3) * 4;
-#pragma unroll 8
+      const uint32_t base = sbase + (uint32_t)(lane & 3) * 4 + (uint32_t)(q * 32) * 128;
+      const uint32_t cgrp = (uint32_t)lane >> 2;
+#pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int rr = q * 32 + i;
-        const uint32_t word = ld_shared_u32(base + rr * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(rr & 7)) << 4));
+        const uint32_t word = ld_shared_u32(base + i * 128 + ((cgrp ^ (uint32_t)(i & 7)) << 4));
         const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
         s1a += lo;
         s1b += hi;
         s2a = fmaf(lo, lo, s2a);
         s2b = fmaf(hi, hi, s2b);
       }
-      const int ch = ch0 + blk * 64 + 2 * lane;
-      atomicAdd(&stat_s1[ch], s1a);
-      atomicAdd(&stat_s1[ch + 1], s1b);
-      atomicAdd(&stat_s2[ch], s2a);
-      atomicAdd(&stat_s2[ch + 1], s2b);
+      st.v[blk][0] += s1a;
+      st.v[blk][1] += s1b;
+      st.v[blk][2] += s2a;
+      st.v[blk][3] += s2b;
     }
-    ++store_count;
   }
 }
 
@@ -264,28 +289,10 @@ __device__ __forceinline__ void init_common(const ConvParams& p, uint8_t* smem, 
     }
     fence_barrier_init();
   }
-  if (p.stat_channels > 0) {
-    float* st = reinterpret_cast<float*>(smem + p.off_stats);
-    for (int i = threadIdx.x; i < 2 * p.stat_channels; i += kNumThreads) st[i] = 0.f;
-  }
 }
 
-__device__ __forceinline__ void flush_stats(const ConvParams& p, uint8_t* smem) {
-  if (p.stat_channels > 0) {
-    const float* s1 = reinterpret_cast<const float*>(smem + p.off_stats);
-    const float* s2 = s1 + p.stat_channels;
-    for (int i = threadIdx.x; i < p.stat_channels; i += kNumThreads) {
-      const float a = s1[i], b = s2[i];
-      if (a != 0.f || b != 0.f) {
-        atomicAdd(p.stat_sum + i, (double)a);
-        atomicAdd(p.stat_sumsq + i, (double)b);
-      }
-    }
-  }
-}
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_constant__ ConvParams p) {
+template <int BLOCK_N, bool HAS_BIAS>
+__global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -310,7 +317,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        // m fastest: a CTA keeps its N tile (weights, statistics channels) for long runs of tiles
+        const int n_tile = tile / p.num_m_tiles, m_tile = tile % p.num_m_tiles;
         const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
         for (int s = 0; s < ksteps; ++s) {
@@ -370,30 +378,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp - 4;  // TMEM lane quadrant
+    // ===================== epilogue: group g = (warp-4)/4 drains the tiles with (it & 1) == g =====================
+    const int g = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;  // TMEM lane quadrant
     const int row = q * 32 + lane;
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
-    uint32_t store_count = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+    uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    StatRegs<BLOCK_N> st;
+    st.clear();
+    st.n_tile = -1;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int n_tile = tile / p.num_m_tiles, m_tile = tile % p.num_m_tiles;
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
-      const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&bars.tmem_full[acc], acc_phase);
+      mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BLOCK_N>(p, smem, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N, q, lane, valid,
-                             n_tile * BLOCK_N, w0, h0, n0, store_count, &bars.tmem_empty[acc]);
+      epilogue_tile<BLOCK_N, HAS_BIAS>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
+                                       n_tile, w0, h0, n0, st, &bars.tmem_empty[g]);
     }
+    if (p.stat_sum) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  flush_stats(p, smem);
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_kernel(const __grid_co
 }
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kNumThreads, 1) tc_conv_halo_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_halo_kernel(const __gr
       uint32_t pa = 0, pb = 0;
       bool first = true;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+        const int n_tile = tile / p.num_m_tiles, m_tile = tile % p.num_m_tiles;
         const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * 8, h0 = th * 16;
         for (int chunk = 0; chunk < cpt; ++chunk) {
@@ -518,29 +529,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_conv_halo_kernel(const __gr
     }
     __syncwarp();
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int g = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;
     const int row = q * 32 + lane;
     const int pw_i = row & 7, ph_i = row >> 3;
-    uint32_t store_count = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile % p.num_n_tiles;
+    uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    StatRegs<BLOCK_N> st;
+    st.clear();
+    st.n_tile = -1;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int n_tile = tile / p.num_m_tiles, m_tile = tile % p.num_m_tiles;
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * 8, h0 = th * 16;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h;
-      const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&bars.tmem_full[acc], acc_phase);
+      mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
-      epilogue_tile<BLOCK_N>(p, smem, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N, q, lane, valid,
-                             n_tile * BLOCK_N, w0, h0, tn, store_count, &bars.tmem_empty[acc]);
+      epilogue_tile<BLOCK_N, false>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
+                                    n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
     }
+    if (p.stat_sum) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  flush_stats(p, smem);
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
@@ -916,16 +930,20 @@ constexpr int kMaxSmem = 227 * 1024;
 
 template <int BLOCK_N>
 static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, cudaStream_t stream) {
-  static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N>, kMaxSmem);
+  static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N, false>, kMaxSmem);
+  static int attr_rc1 = set_smem_attr(tc_conv_kernel<BLOCK_N, true>, kMaxSmem);
   static int attr_rc2 = set_smem_attr(tc_conv_halo_kernel<BLOCK_N>, kMaxSmem);
   if (attr_rc) return attr_rc;
+  if (attr_rc1) return attr_rc1;
   if (attr_rc2) return attr_rc2;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (halo)
-    tc_conv_halo_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+    tc_conv_halo_kernel<BLOCK_N><<<grid, kConvThreads, smem_bytes, stream>>>(p);
+  else if (p.bias)
+    tc_conv_kernel<BLOCK_N, true><<<grid, kConvThreads, smem_bytes, stream>>>(p);
   else
-    tc_conv_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+    tc_conv_kernel<BLOCK_N, false><<<grid, kConvThreads, smem_bytes, stream>>>(p);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
@@ -1030,35 +1048,27 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   p.bias = a->bias;
   p.stat_sum = a->stat_sum;
   p.stat_sumsq = a->stat_sumsq;
-  p.stat_channels = a->stat_sum ? g.cout : 0;
-  // ---- shared-memory plan ----
-  const int stats_bytes = ((2 * p.stat_channels * 4 + 127) / 128) * 128;
-  const int budget = kMaxSmem - 1024 /*alignment slack*/ - kBarBytes - stats_bytes;
+  p.stat_channels = 0;
+  // ---- shared-memory plan: operand ring(s) | 2 staging blocks (one per epilogue group) | barriers ----
+  const int budget = kMaxSmem - 1024 /*alignment slack*/ - kBarBytes - 2 * kStagingBytes;
+  p.num_staging = 2;
   int ring_bytes;
   if (!halo) {
     const int stage_bytes = kABytes + b_bytes;
-    p.num_staging = 2;
-    p.stages = (budget - 2 * kStagingBytes) / stage_bytes;
-    if (p.stages < 4) {
-      p.num_staging = 1;
-      p.stages = (budget - kStagingBytes) / stage_bytes;
-    }
+    p.stages = budget / stage_bytes;
     if (p.stages > kMaxAStages) p.stages = kMaxAStages;
     ring_bytes = p.stages * stage_bytes;
     p.off_b = 0;
   } else {
     const int ksteps = 9 * cpt;
-    p.resident_b = (p.num_n_tiles == 1 && ksteps <= kMaxBSlots && ksteps * b_bytes + 2 * kHaloStride + kStagingBytes <= budget) ? 1 : 0;
+    p.resident_b = (p.num_n_tiles == 1 && ksteps <= kMaxBSlots && ksteps * b_bytes + 2 * kHaloStride <= budget) ? 1 : 0;
     if (p.resident_b) {
       p.b_slots = ksteps;
-      const int rest = budget - ksteps * b_bytes;
-      p.num_staging = (rest - 2 * kStagingBytes) >= 2 * kHaloStride ? 2 : 1;
-      p.stages = (rest - p.num_staging * kStagingBytes) / kHaloStride;
+      p.stages = (budget - ksteps * b_bytes) / kHaloStride;
       if (p.stages > 4) p.stages = 4;
     } else {
-      p.num_staging = 2;
       p.stages = 3;
-      p.b_slots = (budget - 2 * kStagingBytes - p.stages * kHaloStride) / b_bytes;
+      p.b_slots = (budget - p.stages * kHaloStride) / b_bytes;
       if (p.b_slots > 9) p.b_slots = 9;
       UNETK_REQUIRE(p.b_slots >= 2, "conv(tc halo): shared-memory plan failed");
     }
@@ -1066,8 +1076,8 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
     ring_bytes = p.off_b + p.b_slots * b_bytes;
   }
   p.off_staging = ring_bytes;
-  p.off_stats = p.off_staging + p.num_staging * kStagingBytes;
-  p.off_bars = p.off_stats + stats_bytes;
+  p.off_stats = 0;
+  p.off_bars = p.off_staging + 2 * kStagingBytes;
   const int smem_bytes = p.off_bars + kBarBytes + 1024;
   UNETK_REQUIRE(smem_bytes <= kMaxSmem && p.stages >= 2, "conv(tc): shared-memory plan failed (%d bytes, %d stages)", smem_bytes, p.stages);
   if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, stream);

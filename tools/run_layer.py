@@ -1,0 +1,64 @@
+"""Run one contraction of the path in isolation (for ncu / quick timing):
+    python tools/run_layer.py --op conv --cin 64 --cout 64 --hw 256 --batch 16 [--iters 5]
+ops: conv (3x3 fprop with BN statistics), dgrad (3x3 without statistics), wgrad (3x3), convt, convt_dgrad"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from image_segmentation_b200 import _lib as L  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--op", default="conv")
+ap.add_argument("--cin", type=int, default=64)
+ap.add_argument("--cout", type=int, default=64)
+ap.add_argument("--hw", type=int, default=256)
+ap.add_argument("--batch", type=int, default=16)
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
+dev = "cuda"
+n, h, w = a.batch, a.hw, a.hw
+bf = torch.bfloat16
+x = torch.randn(n, h, w, a.cin, device=dev).to(bf)
+if a.op in ("conv", "dgrad"):
+    wt = (torch.randn(a.cout, 9, a.cin, device=dev) * 0.05).to(bf)
+    y = torch.empty(n, h, w, a.cout, device=dev, dtype=bf)
+    s1 = torch.zeros(a.cout, dtype=torch.float64, device=dev)
+    s2 = torch.zeros_like(s1)
+    flops = 2 * n * h * w * 9 * a.cin * a.cout
+
+    def run():
+        if a.op == "conv":
+            L.conv(x, wt, y, L.MODE_3X3, stat_sum=s1, stat_sumsq=s2)
+        else:
+            L.conv(x, wt, y, L.MODE_3X3)
+elif a.op == "wgrad":
+    dy = torch.randn(n, h, w, a.cout, device=dev).to(bf)
+    dw = torch.zeros(a.cout, 9, a.cin, device=dev)
+    flops = 2 * n * h * w * 9 * a.cin * a.cout
+
+    def run():
+        L.wgrad(dy, x, dw, 1)
+elif a.op == "convt":
+    wt = (torch.randn(4 * a.cout, a.cin, device=dev) * 0.05).to(bf)
+    y = torch.empty(n, 2 * h, 2 * w, a.cout, device=dev, dtype=bf)
+    b = torch.zeros(a.cout, device=dev)
+    flops = 2 * n * h * w * a.cin * 4 * a.cout
+
+    def run():
+        L.conv(x, wt, y, L.MODE_CONVT, bias=b)
+else:
+    raise SystemExit("unknown op")
+for _ in range(2):
+    run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    run()
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+print(f"{a.op} cin={a.cin} cout={a.cout} hw={a.hw} batch={a.batch}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
