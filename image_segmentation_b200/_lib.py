@@ -50,6 +50,11 @@ class BnBwdArgs(C.Structure):
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
 
 
+class WJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst0", C.c_void_p), ("dst1", C.c_void_p), ("kind", C.c_int32),
+                ("cout", C.c_int32), ("cin", C.c_int32), ("kpad", C.c_int32)]
+
+
 class DiceCeArgs(C.Structure):
     _fields_ = [("logits", C.c_void_p), ("target", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32),
                 ("w", C.c_int32), ("class_weights", C.c_void_p), ("has_ignore", C.c_int32), ("ignore_index", C.c_int64),
@@ -78,6 +83,8 @@ def lib():
             "unetk_device_query": [P(C.c_int32), P(C.c_int32), P(C.c_int32)],
             "unetk_im2col3x3_first": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(Tensor), vp],
             "unetk_permute3": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_int64] * 6 + [vp],
+            "unetk_weights_pack": [vp, vp, C.c_int32, C.c_int32, vp],
+            "unetk_weights_unpack": [vp, vp, C.c_int32, vp, vp],
             "unetk_conv": [P(ConvArgs), vp],
             "unetk_wgrad": [P(WgradArgs), vp],
             "unetk_channel_sum": [P(Tensor), vp, vp],
@@ -102,6 +109,7 @@ def lib():
 
 EXPORTED_SYMBOLS = (
     "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_im2col3x3_first", "unetk_permute3",
+    "unetk_weights_pack", "unetk_weights_unpack",
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion",
@@ -171,6 +179,35 @@ def permute3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_stride
     _run("layout", 1, 0, lib().unetk_permute3, src.data_ptr(), dst.data_ptr() + dst_offset_elems * dst.element_size(),
          _DTYPES[dst.dtype], dims[0], dims[1], dims[2], src_strides[0], src_strides[1], src_strides[2],
          dst_strides[0], dst_strides[1], dst_strides[2], stream_ptr())
+
+
+class WeightJobs:
+    """Device-resident job + tile tables for unetk_weights_pack / unetk_weights_unpack."""
+
+    def __init__(self, jobs, device):
+        # jobs: list of (src_ptr_or_offset, dst0, dst1, kind, cout, cin, kpad)
+        arr = (WJob * len(jobs))(*[WJob(*j) for j in jobs])
+        tiles = []
+        for ji, (_, _, _, kind, cout, cin, _) in enumerate(jobs):
+            if kind == 2:
+                tiles.append((ji, 0, 0, 0))
+                continue
+            na, nb = (cout, cin) if kind == 0 else (cin, cout)
+            if na % 32 or nb % 32:
+                raise ValueError("channel counts must be multiples of 32 for the batched weight kernels")
+            tiles += [(ji, a0, b0, 0) for a0 in range(0, na, 32) for b0 in range(0, nb, 32)]
+        self.ntiles = len(tiles)
+        self.jobs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+        self.tiles = torch.tensor(tiles, dtype=torch.int32).to(device)
+
+
+def weights_pack(wj: "WeightJobs", dtype):
+    _run("layout", 1, 0, lib().unetk_weights_pack, wj.jobs.data_ptr(), wj.tiles.data_ptr(), wj.ntiles, _DTYPES[dtype], stream_ptr())
+
+
+def weights_unpack(wj: "WeightJobs", dst_base: torch.Tensor):
+    _run("layout", 1, 0, lib().unetk_weights_unpack, wj.jobs.data_ptr(), wj.tiles.data_ptr(), wj.ntiles, dst_base.data_ptr(),
+         stream_ptr())
 
 
 def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None):

@@ -46,6 +46,123 @@ __global__ void __launch_bounds__(256) permute3_kernel(const float* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// batched weight pack / unpack: one block per 32x32 channel tile, transposition through shared memory so that both
+// the parameter side and the operand-pack side are accessed in contiguous runs
+// ------------------------------------------------------------------------------------------------
+constexpr int kWT = 32;
+
+template <typename T, bool PACK>
+__global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restrict__ jobs, const int32_t* __restrict__ tiles,
+                                                      uint8_t* dst_base) {
+  __shared__ float sm[kWT][kWT * 9 + 1];
+  const int4 tl = reinterpret_cast<const int4*>(tiles)[blockIdx.x];
+  unetk_wjob j = jobs[tl.x];
+  if (dst_base) j.dst0 = dst_base + reinterpret_cast<uintptr_t>(j.dst0);
+  const int a0 = tl.y, b0 = tl.z;
+  const int tid = threadIdx.x;
+  if (j.kind == 2) {
+    // tiny first layer: [co][ci][9] <-> [co][kpad], k = t*cin + ci
+    const int total = j.cout * j.cin * 9;
+    for (int i = tid; i < total; i += 256) {
+      const int co = i / (j.cin * 9), r = i % (j.cin * 9), ci = r / 9, t = r % 9;
+      if (PACK)
+        reinterpret_cast<T*>(j.dst0)[(size_t)co * j.kpad + t * j.cin + ci] = from_f<T>(reinterpret_cast<const float*>(j.src)[i]);
+      else
+        reinterpret_cast<float*>(j.dst0)[i] = reinterpret_cast<const float*>(j.src)[(size_t)co * j.kpad + t * j.cin + ci];
+    }
+    return;
+  }
+  const int taps = j.kind == 0 ? 9 : 4;
+  const int run = kWT * taps;                       // contiguous floats per `a` row of the parameter tile
+  // parameter layout: [a][b][taps] with a = co (conv) / ci (convT);  A = rows, B = columns
+  const int B = j.kind == 0 ? j.cin : j.cout;
+  const float* param = PACK ? reinterpret_cast<const float*>(j.src) : nullptr;
+  if (PACK) {
+    for (int i = tid; i < kWT * run; i += 256) {
+      const int al = i / run, e = i % run;
+      sm[al][e] = param[((size_t)(a0 + al) * B + b0) * taps + e];
+    }
+    __syncthreads();
+    T* wf = reinterpret_cast<T*>(j.dst0);
+    T* wd = reinterpret_cast<T*>(j.dst1);
+    for (int i = tid; i < kWT * run; i += 256) {
+      const int t = (i / kWT) % taps;
+      if (j.kind == 0) {
+        // wf[co][t][ci]: consecutive threads -> consecutive ci
+        { const int co = i / run, ci = i % kWT;
+          wf[((size_t)(a0 + co) * 9 + t) * j.cin + b0 + ci] = from_f<T>(sm[co][ci * 9 + t]); }
+        // wd[ci][8-t][co]: consecutive threads -> consecutive co
+        { const int ci = i / run, co = i % kWT;
+          wd[((size_t)(b0 + ci) * 9 + (8 - t)) * j.cout + a0 + co] = from_f<T>(sm[co][ci * 9 + t]); }
+      } else {
+        // convT: sm[ci][co*4 + ab];  wf[(ab*cout + co)][ci]: consecutive threads -> consecutive ci
+        { const int co = i / run, ci = i % kWT;
+          wf[((size_t)t * j.cout + b0 + co) * j.cin + a0 + ci] = from_f<T>(sm[ci][co * 4 + t]); }
+        // wd[ci][ab][co]: consecutive threads -> consecutive co
+        { const int ci = i / run, co = i % kWT;
+          wd[((size_t)(a0 + ci) * 4 + t) * j.cout + b0 + co] = from_f<T>(sm[ci][co * 4 + t]); }
+      }
+    }
+  } else {
+    const float* ws = reinterpret_cast<const float*>(j.src);
+    for (int i = tid; i < kWT * run; i += 256) {
+      const int t = (i / kWT) % taps;
+      if (j.kind == 0) {
+        const int co = i / run, ci = i % kWT;          // ws[co][t][ci]
+        sm[co][ci * 9 + t] = ws[((size_t)(a0 + co) * 9 + t) * j.cin + b0 + ci];
+      } else {
+        const int ci = i / run, co = i % kWT;          // ws[ci][ab][co]
+        sm[ci][co * 4 + t] = ws[((size_t)(a0 + ci) * 4 + t) * j.cout + b0 + co];
+      }
+    }
+    __syncthreads();
+    float* grad = reinterpret_cast<float*>(j.dst0);
+    for (int i = tid; i < kWT * run; i += 256) {
+      const int al = i / run, e = i % run;
+      grad[((size_t)(a0 + al) * B + b0) * taps + e] = sm[al][e];
+    }
+  }
+}
+
+// NCHW fp32 image -> NHWC im2col operand, 8 consecutive K values per thread with the (tap, channel) decoding hoisted
+// out of the pixel loop (thread's K group is fixed: the grid stride is a multiple of kg)
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_first_kernel_v2(const float* __restrict__ x, int n, int cin, int h, int w,
+                                                              T* __restrict__ out, int kpad, int ld) {
+  const int kg = kpad / 8;                       // K groups per pixel
+  const int g = threadIdx.x % kg;
+  const int pix_lane = threadIdx.x / kg, lanes = blockDim.x / kg;
+  int dy[8], dx[8], ci[8];
+  bool kv[8];
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int k = g * 8 + jj;
+    kv[jj] = k < 9 * cin;
+    const int t = kv[jj] ? k / cin : 0;
+    ci[jj] = kv[jj] ? k % cin : 0;
+    dy[jj] = t / 3 - 1;
+    dx[jj] = t % 3 - 1;
+  }
+  const int64_t npix = (int64_t)n * h * w;
+  const int64_t hw = (int64_t)h * w;
+  for (int64_t p = (int64_t)blockIdx.x * lanes + pix_lane; p < npix; p += (int64_t)gridDim.x * lanes) {
+    const int px = (int)(p % w);
+    const int py = (int)((p / w) % h);
+    const int64_t img = p / hw;
+    const float* xi = x + img * cin * hw;
+    float v[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int yy = py + dy[jj], xx = px + dx[jj];
+      const bool ok = kv[jj] && yy >= 0 && yy < h && xx >= 0 && xx < w;
+      v[jj] = ok ? __ldg(xi + ci[jj] * hw + (int64_t)yy * w + xx) : 0.f;
+    }
+    store8(out + p * ld + g * 8, v);
+  }
+}
+
 }  // namespace unetk
 
 using namespace unetk;
@@ -62,9 +179,19 @@ int unetk_im2col3x3_first(const float* x_nchw, int32_t n, int32_t cin, int32_t h
   int64_t blocks = (items + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  UNETK_DISPATCH_DTYPE(out->dtype, T, {
-    im2col_first_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (T*)out->ptr, out->c, out->ld);
-  });
+  const int kg = out->c / 8;
+  if (256 % kg == 0) {
+    const int lanes = 256 / kg;
+    int64_t b2 = ((int64_t)n * h * w + lanes - 1) / lanes;
+    if (b2 > cap) b2 = cap;
+    UNETK_DISPATCH_DTYPE(out->dtype, T, {
+      im2col_first_kernel_v2<T><<<(int)b2, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (T*)out->ptr, out->c, out->ld);
+    });
+  } else {
+    UNETK_DISPATCH_DTYPE(out->dtype, T, {
+      im2col_first_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (T*)out->ptr, out->c, out->ld);
+    });
+  }
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
@@ -80,6 +207,21 @@ int unetk_permute3(const float* src, void* dst, int32_t dst_dtype, int32_t d0, i
   UNETK_DISPATCH_DTYPE(dst_dtype, T, {
     permute3_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (T*)dst, d0, d1, d2, ss0, ss1, ss2, ds0, ds1, ds2);
   });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_weights_pack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, int32_t dtype, void* stream) {
+  UNETK_REQUIRE(jobs && tiles && ntiles > 0, "weights_pack: bad argument");
+  UNETK_REQUIRE(dtype == UNETK_F32 || dtype == UNETK_BF16, "weights_pack: bad dtype");
+  UNETK_DISPATCH_DTYPE(dtype, T, { weights_kernel<T, true><<<ntiles, 256, 0, (cudaStream_t)stream>>>(jobs, tiles, nullptr); });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_weights_unpack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, void* dst_base, void* stream) {
+  UNETK_REQUIRE(jobs && tiles && ntiles > 0, "weights_unpack: bad argument");
+  weights_kernel<float, false><<<ntiles, 256, 0, (cudaStream_t)stream>>>(jobs, tiles, static_cast<uint8_t*>(dst_base));
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }

@@ -73,6 +73,9 @@ class UNetPlan:
         self.generation = 0
         self.algo = L.ALGO_AUTO
         self._pack_versions = None
+        self._pack_jobs = None
+        self._pack_ptrs = None
+        self._unpack_jobs = None
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -240,30 +243,51 @@ class UNetPlan:
         for item, s in zip(seq, ws_sizes):
             item.ws = self.ws[off:off + s]
             off += s
+        # batched weight-gradient unpack tables, one per all-reduce segment (decoder level / encoder level);
+        # destinations are byte offsets into the flat gradient buffer, which is a fresh allocation every backward pass
+        off_of = {id(p): o for p, o in zip(self.grad_order, self.grad_offsets[:-1])}
+        segments = []
+        for i in (3, 2, 1, 0):
+            segments.append([self.dec[i][1], self.dec[i][0], self.convts[i]])
+        for lvl in (4, 3, 2, 1, 0):
+            segments.append([self.enc[lvl][1], self.enc[lvl][0]])
+        self._unpack_jobs = []
+        for items in segments:
+            jobs = []
+            for item in items:
+                if isinstance(item, _ConvBN):
+                    dst = 4 * off_of[id(item.conv.weight)]
+                    if item.first:
+                        jobs.append((item.ws.data_ptr(), dst, None, 2, item.cout, item.cin, self.kpad))
+                    else:
+                        jobs.append((item.ws.data_ptr(), dst, None, 0, item.cout, item.cin, 0))
+                else:
+                    jobs.append((item.ws.data_ptr(), 4 * off_of[id(item.mod.weight)], None, 1, item.cout, item.cin, 0))
+            self._unpack_jobs.append(L.WeightJobs(jobs, self.device))
         self._bwd_ready = True
 
     # ------------------------------------------------------------------------------------------
     def pack_weights(self):
-        """fp32 OIHW / IOHW parameters -> K-major operand packs (only when a parameter changed)."""
-        versions = tuple(p._version for p in self.model.parameters()) + tuple(p.data_ptr() for p in self.model.parameters())
-        if versions == self._pack_versions:
+        """fp32 OIHW / IOHW parameters -> K-major operand packs: one batched launch, only when a parameter changed."""
+        params = list(self.model.parameters())
+        versions = tuple(p._version for p in params)
+        ptrs = tuple(p.data_ptr() for p in params)
+        if (versions, ptrs) == self._pack_versions:
             return
-        for l in self.layers:
-            w = l.conv.weight.detach()
-            co, ci = l.cout, l.cin
-            if l.first:
-                # [co][ci][t] -> [co][t*din + ci] (zero padded to kpad)
-                L.permute3(w, l.wf, (co, ci, 9), (ci * 9, 9, 1), (self.kpad, 1, ci))
-            else:
-                L.permute3(w, l.wf, (co, ci, 9), (ci * 9, 9, 1), (9 * ci, 1, ci))
-                # data-gradient pack: [ci][8 - t][co]  (flipped taps, transposed channels)
-                L.permute3(w, l.wd, (co, ci, 9), (ci * 9, 9, 1), (1, 9 * co, -co), dst_offset_elems=8 * co)
-        for ct in self.convts:
-            w = ct.mod.weight.detach()   # [ci][co][2][2]
-            ci, co = ct.cin, ct.cout
-            L.permute3(w, ct.wf, (ci, co, 4), (co * 4, 4, 1), (1, ci, co * ci))      # [(ab)*co + co][ci]
-            L.permute3(w, ct.wd, (ci, co, 4), (co * 4, 4, 1), (4 * co, 1, co))       # [ci][(ab)][co]
-        self._pack_versions = versions
+        if self._pack_jobs is None or self._pack_ptrs != ptrs:
+            jobs = []
+            for l in self.layers:
+                w = l.conv.weight
+                if l.first:
+                    jobs.append((w.data_ptr(), l.wf.data_ptr(), None, 2, l.cout, l.cin, self.kpad))
+                else:
+                    jobs.append((w.data_ptr(), l.wf.data_ptr(), l.wd.data_ptr(), 0, l.cout, l.cin, 0))
+            for ct in self.convts:
+                jobs.append((ct.mod.weight.data_ptr(), ct.wf.data_ptr(), ct.wd.data_ptr(), 1, ct.cout, ct.cin, 0))
+            self._pack_jobs = L.WeightJobs(jobs, self.device)
+            self._pack_ptrs = ptrs
+        L.weights_pack(self._pack_jobs, self.dt)
+        self._pack_versions = (versions, ptrs)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
@@ -331,15 +355,14 @@ class UNetPlan:
             L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias])
             if l.first:
                 L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo, algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout)
-                L.permute3(l.ws, g[l.conv.weight], (l.cout, l.cin, 9), (self.kpad, 1, l.cin), (l.cin * 9, 9, 1))
             else:
                 L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo)
-                L.permute3(l.ws, g[l.conv.weight], (l.cout, l.cin, 9), (9 * l.cin, 1, l.cin), (l.cin * 9, 9, 1))
                 L.conv(l.dz, l.wd, l.g_in, L.MODE_3X3, algo=self.algo)
             # conv bias in front of train-mode BN: its gradient is identically zero (flat buffer is zeroed)
 
         grad_a2 = self.g_head_in
         pos = 2
+        seg = 0
         for i in (3, 2, 1, 0):
             lvl = 3 - i
             l1, l2 = self.dec[i]
@@ -348,11 +371,12 @@ class UNetPlan:
             ct = self.convts[i]
             L.LABEL = ct.name
             L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
-            L.permute3(ct.ws, g[ct.mod.weight], (ct.cin, ct.cout, 4), (4 * ct.cout, 1, ct.cout), (ct.cout * 4, 4, 1))
             L.channel_sum(ct.g_out, g[ct.mod.bias])
             L.conv(ct.g_out, ct.wd, ct.g_in, L.MODE_CONVT_GATHER, algo=self.algo)
             grad_a2 = ct.g_in
             pos += 10
+            L.weights_unpack(self._unpack_jobs[seg], flat)
+            seg += 1
             if bucket_hook:
                 bucket_hook(self, self.grad_offsets[pos])
         for lvl in (4, 3, 2, 1, 0):
@@ -363,6 +387,8 @@ class UNetPlan:
                 conv_bn_bwd(l2, self.dcat[lvl][..., :ENC_CH[lvl]], dpool=self.enc[lvl + 1][0].g_in)
             conv_bn_bwd(l1, l2.g_in)
             pos += 8
+            L.weights_unpack(self._unpack_jobs[seg], flat)
+            seg += 1
             if bucket_hook:
                 bucket_hook(self, self.grad_offsets[pos])
         return g

@@ -71,6 +71,26 @@ int unetk_permute3(const float* src, void* dst, int32_t dst_dtype, int32_t d0, i
                    int64_t ss0, int64_t ss1, int64_t ss2, int64_t ds0, int64_t ds1, int64_t ds2,
                    void* stream);
 
+/* Batched weight (un)packing: ONE launch for all layers instead of one unetk_permute3 per tensor.
+ *   kind 0  conv3x3    param [co][ci][3][3]   <->  fwd pack [co][t][ci]        and  dgrad pack [ci][8-t][co]
+ *   kind 1  convT2x2   param [ci][co][2][2]   <->  fwd pack [(a,b,co)][ci]     and  dgrad pack [ci][(a,b)][co]
+ *   kind 2  first conv param [co][ci][3][3]   <->  fwd pack [co][kpad] with k = t*ci_count + ci (zero padded)
+ * pack  : src = fp32 parameter, dst0 = fwd pack, dst1 = dgrad pack (NULL for kind 2), packs have dtype `dtype`.
+ * unpack: src = fp32 weight-gradient workspace in the layout unetk_wgrad produces
+ *         (kind 0: [co][t][ci]; kind 1: [ci][(a,b)][co]; kind 2: [co][kpad]), dst0 = fp32 gradient in parameter layout.
+ * `jobs` and `tiles` are DEVICE arrays built once by the host; tiles[i] = {job, a0, b0, 0} enumerates the 32x32
+ * (a,b) channel tiles of every job (kind 0: a = co, b = ci; kind 1: a = ci, b = co; kind 2: one tile {job,0,0,0}).
+ * unpack: when `dst_base` is not NULL each job's dst0 is a BYTE OFFSET into dst_base (the gradient buffer is a fresh
+ * allocation every backward pass, the job table is not). */
+typedef struct unetk_wjob {
+  const void* src;
+  void* dst0;
+  void* dst1;
+  int32_t kind, cout, cin, kpad;
+} unetk_wjob;
+int unetk_weights_pack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, int32_t dtype, void* stream);
+int unetk_weights_unpack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, void* dst_base, void* stream);
+
 /* ---- contractions --------------------------------------------------------------------------
  * One implicit-GEMM entry for every "activation x weight" product of the path:
  *   mode 0  1x1           y[p, co]        = sum_ci          x[p, ci]            w[co][ci]

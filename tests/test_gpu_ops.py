@@ -370,3 +370,39 @@ def test_cpu_tensors_are_rejected():
         unet(3, 3)(torch.zeros(1, 3, 16, 16))
     with pytest.raises(RuntimeError):
         WeightedDiceCELoss()(torch.zeros(1, 3, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long))
+
+
+def test_batched_weight_pack_and_unpack():
+    g = torch.Generator().manual_seed(80)
+    w3 = torch.randn(64, 96, 3, 3, generator=g)        # conv3x3  [co][ci][3][3]
+    wT = torch.randn(128, 64, 2, 2, generator=g)       # convT    [ci][co][2][2]
+    w1 = torch.randn(64, 3, 3, 3, generator=g)         # first conv
+    for dt in (torch.float32, torch.bfloat16):
+        d3, dT, d1 = w3.to(DEV), wT.to(DEV), w1.to(DEV)
+        wf3 = torch.empty((64, 9, 96), dtype=dt, device=DEV); wd3 = torch.empty((96, 9, 64), dtype=dt, device=DEV)
+        wfT = torch.empty((4 * 64, 128), dtype=dt, device=DEV); wdT = torch.empty((128, 4, 64), dtype=dt, device=DEV)
+        wf1 = torch.zeros((64, 64), dtype=dt, device=DEV)
+        jobs = L.WeightJobs([(d3.data_ptr(), wf3.data_ptr(), wd3.data_ptr(), 0, 64, 96, 0),
+                             (dT.data_ptr(), wfT.data_ptr(), wdT.data_ptr(), 1, 64, 128, 0),
+                             (d1.data_ptr(), wf1.data_ptr(), None, 2, 64, 3, 64)], DEV)
+        L.weights_pack(jobs, dt)
+        assert torch.equal(wf3.cpu(), w3.permute(0, 2, 3, 1).reshape(64, 9, 96).to(dt))
+        assert torch.equal(wd3.cpu(), w3.flip(2, 3).permute(1, 2, 3, 0).reshape(96, 9, 64).to(dt))
+        assert torch.equal(wfT.cpu(), wT.permute(2, 3, 1, 0).reshape(256, 128).to(dt))
+        assert torch.equal(wdT.cpu(), wT.permute(0, 2, 3, 1).reshape(128, 4, 64).to(dt))
+        ref1 = torch.zeros(64, 64)
+        ref1[:, :27] = w1.permute(0, 2, 3, 1).reshape(64, 27)
+        assert torch.equal(wf1.cpu(), ref1.to(dt))
+    # unpack: gradient workspaces (operand layout) -> parameter layout, destinations as offsets into one flat buffer
+    ws3 = torch.randn(64, 9, 96, generator=g).to(DEV)
+    wsT = torch.randn(128, 4, 64, generator=g).to(DEV)
+    ws1 = torch.randn(64, 64, generator=g).to(DEV)
+    flat = torch.zeros(7 + w3.numel() + wT.numel() + w1.numel(), device=DEV)
+    o3, oT, o1 = 7, 7 + w3.numel(), 7 + w3.numel() + wT.numel()
+    jobs = L.WeightJobs([(ws3.data_ptr(), 4 * o3, None, 0, 64, 96, 0), (wsT.data_ptr(), 4 * oT, None, 1, 64, 128, 0),
+                         (ws1.data_ptr(), 4 * o1, None, 2, 64, 3, 64)], DEV)
+    L.weights_unpack(jobs, flat)
+    assert torch.equal(flat[o3:oT].view(64, 96, 3, 3).cpu(), ws3.cpu().view(64, 3, 3, 96).permute(0, 3, 1, 2))
+    assert torch.equal(flat[oT:o1].view(128, 64, 2, 2).cpu(), wsT.cpu().view(128, 2, 2, 64).permute(0, 3, 1, 2))
+    assert torch.equal(flat[o1:].view(64, 3, 3, 3).cpu(), ws1.cpu()[:, :27].view(64, 3, 3, 3).permute(0, 3, 1, 2))
+    assert float(flat[:7].abs().sum()) == 0.0
