@@ -159,6 +159,32 @@ struct BwdSrc {
   int n, h, w, cg;
 };
 
+// One 2x2 pooling window, 8 channels: which position holds the (first) maximum of the stored activation, and which
+// positions pass the ReLU.  Packed: bits [2k,2k+2) of `arg` = window position for channel k, bit (4k+q) of `pos` = a>0.
+template <typename T>
+__device__ __forceinline__ void window_scan(const T* __restrict__ z, int zld, const int64_t (&pix)[4], int g,
+                                            const float (&sc)[8], const float (&sh)[8], uint32_t& arg, uint32_t& pos) {
+  float best[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
+  arg = 0;
+  pos = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float zv[8];
+    load8(z + pix[q] * zld + g * 8, zv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+      if (act > best[k]) {
+        best[k] = act;
+        arg = (arg & ~(3u << (2 * k))) | ((uint32_t)q << (2 * k));
+      }
+      if (act > 0.f) pos |= 1u << (4 * k + q);
+    }
+  }
+}
+
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
     bn_bwd_reduce_kernel(BwdSrc<T> s, int cgb, int items_per_block, double* __restrict__ s1, double* __restrict__ s2) {
@@ -178,8 +204,25 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
   float acc[2][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
-  for (int64_t it = i0 + row; it < i1; it += rows) {
-    if (!POOL) {
+  if (!POOL) {
+    // two pixels per iteration: four independent 16-byte loads in flight per thread
+    int64_t it = i0 + row;
+    for (; it + rows < i1; it += 2 * rows) {
+      float za[8], da[8], zb[8], db[8];
+      load8(s.z + it * s.zld + g * 8, za);
+      load8(s.dy + it * s.dyld + g * 8, da);
+      load8(s.z + (it + rows) * s.zld + g * 8, zb);
+      load8(s.dy + (it + rows) * s.dyld + g * 8, db);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
+        const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
+        const float ya = aa > 0.f ? da[k] : 0.f, yb = ab > 0.f ? db[k] : 0.f;
+        acc[0][k] += ya + yb;
+        acc[1][k] = fmaf(ya, za[k], fmaf(yb, zb[k], acc[1][k]));
+      }
+    }
+    for (; it < i1; it += rows) {
       float zv[8], d[8];
       load8(s.z + it * s.zld + g * 8, zv);
       load8(s.dy + it * s.dyld + g * 8, d);
@@ -190,35 +233,23 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
         acc[0][k] += dyk;
         acc[1][k] = fmaf(dyk, zv[k], acc[1][k]);
       }
-    } else {
+    }
+  } else {
+    for (int64_t it = i0 + row; it < i1; it += rows) {
       const int x = (int)(it % ww);
       const int y = (int)((it / ww) % hh);
       const int img = (int)(it / ((int64_t)ww * hh));
-      float zv[4][8], act[4][8], dp[8];
       int64_t pix[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-        load8(s.z + pix[q] * s.zld + g * 8, zv[q]);
-      }
+      for (int q = 0; q < 4; ++q) pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+      uint32_t arg, pos;
+      window_scan<T>(s.z, s.zld, pix, g, sc, sh, arg, pos);
+      float dp[8];
       load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
-      int arg[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float best = -INFINITY;
-        arg[k] = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          act[q][k] = round_to<T>(fmaxf(fmaf(zv[q][k], sc[k], sh[k]), 0.f));
-          if (act[q][k] > best) {
-            best = act[q][k];
-            arg[k] = q;
-          }
-        }
-      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float d[8];
+        float zv[8], d[8];
+        load8(s.z + pix[q] * s.zld + g * 8, zv);   // second touch: L1 hit
         if (s.dy) {
           load8(s.dy + pix[q] * s.dyld + g * 8, d);
         } else {
@@ -227,10 +258,10 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float gsum = d[k] + (arg[k] == q ? dp[k] : 0.f);
-          const float dyk = act[q][k] > 0.f ? gsum : 0.f;
+          const float gsum = d[k] + ((((arg >> (2 * k)) & 3u) == (uint32_t)q) ? dp[k] : 0.f);
+          const float dyk = ((pos >> (4 * k + q)) & 1u) ? gsum : 0.f;
           acc[0][k] += dyk;
-          acc[1][k] = fmaf(dyk, zv[q][k], acc[1][k]);
+          acc[1][k] = fmaf(dyk, zv[k], acc[1][k]);
         }
       }
     }
@@ -283,47 +314,51 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
       if (dbeta) dbeta[g * 8 + k] = (float)s1[g * 8 + k];
     }
   }
-  for (int64_t it = i0 + row; it < i1; it += rows) {
-    if (!POOL) {
+  if (!POOL) {
+    int64_t it = i0 + row;
+    for (; it + rows < i1; it += 2 * rows) {
+      float za[8], da[8], zb[8], db[8], oa[8], ob[8];
+      load8(s.z + it * s.zld + g * 8, za);
+      load8(s.dy + it * s.dyld + g * 8, da);
+      load8(s.z + (it + rows) * s.zld + g * 8, zb);
+      load8(s.dy + (it + rows) * s.dyld + g * 8, db);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
+        const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
+        oa[k] = fmaf(sc[k], aa > 0.f ? da[k] : 0.f, fmaf(cb[k], za[k], cc[k]));
+        ob[k] = fmaf(sc[k], ab > 0.f ? db[k] : 0.f, fmaf(cb[k], zb[k], cc[k]));
+      }
+      store8(dz + it * dzld + g * 8, oa);
+      store8(dz + (it + rows) * dzld + g * 8, ob);
+    }
+    for (; it < i1; it += rows) {
       float zv[8], d[8], o[8];
       load8(s.z + it * s.zld + g * 8, zv);
       load8(s.dy + it * s.dyld + g * 8, d);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-        const float dyk = act > 0.f ? d[k] : 0.f;
-        o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[k], cc[k]));
+        o[k] = fmaf(sc[k], act > 0.f ? d[k] : 0.f, fmaf(cb[k], zv[k], cc[k]));
       }
       store8(dz + it * dzld + g * 8, o);
-    } else {
+    }
+  } else {
+    for (int64_t it = i0 + row; it < i1; it += rows) {
       const int x = (int)(it % ww);
       const int y = (int)((it / ww) % hh);
       const int img = (int)(it / ((int64_t)ww * hh));
-      float zv[4][8], act[4][8], dp[8];
       int64_t pix[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-        load8(s.z + pix[q] * s.zld + g * 8, zv[q]);
-      }
+      for (int q = 0; q < 4; ++q) pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
+      uint32_t arg, pos;
+      window_scan<T>(s.z, s.zld, pix, g, sc, sh, arg, pos);
+      float dp[8];
       load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
-      int arg[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float best = -INFINITY;
-        arg[k] = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          act[q][k] = round_to<T>(fmaxf(fmaf(zv[q][k], sc[k], sh[k]), 0.f));
-          if (act[q][k] > best) {
-            best = act[q][k];
-            arg[k] = q;
-          }
-        }
-      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float d[8], o[8];
+        float zv[8], d[8], o[8];
+        load8(s.z + pix[q] * s.zld + g * 8, zv);   // second touch: L1 hit
         if (s.dy) {
           load8(s.dy + pix[q] * s.dyld + g * 8, d);
         } else {
@@ -332,9 +367,9 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float gsum = d[k] + (arg[k] == q ? dp[k] : 0.f);
-          const float dyk = act[q][k] > 0.f ? gsum : 0.f;
-          o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[q][k], cc[k]));
+          const float gsum = d[k] + ((((arg >> (2 * k)) & 3u) == (uint32_t)q) ? dp[k] : 0.f);
+          const float dyk = ((pos >> (4 * k + q)) & 1u) ? gsum : 0.f;
+          o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[k], cc[k]));
         }
         store8(dz + pix[q] * dzld + g * 8, o);
       }

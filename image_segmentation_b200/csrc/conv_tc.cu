@@ -1096,6 +1096,21 @@ bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
   return true;
 }
 
+// Split the pixel reduction of the weight gradient so that (output tiles x splits) fills the persistent grid in whole
+// waves: the largest split count with at most 2 work items per SM (never rounding UP past a wave boundary, which would
+// leave most SMs idle for a third round), at least 4 pixel tiles per item.
+static void choose_splits(int64_t out_tiles, int num_ptiles, int* ptiles_per_split, int* splits_out) {
+  const int64_t slots = 2LL * sm_count();
+  int64_t splits = slots / out_tiles;
+  if (splits < 1) splits = 1;
+  const int64_t max_splits = (num_ptiles + 3) / 4;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int per = (int)((num_ptiles + splits - 1) / splits);
+  *ptiles_per_split = per;
+  *splits_out = (num_ptiles + per - 1) / per;
+}
+
 static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   using namespace tc;
   WgradParams p;
@@ -1116,12 +1131,7 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   p.cu_tiles = a->u.c / (64 * bm_slabs);
   p.cs_tiles = a->s.c / 64;
   const int64_t out_tiles = (int64_t)p.cu_tiles * p.cs_tiles * 3;
-  int64_t splits = (2LL * sm_count() + out_tiles - 1) / out_tiles;
-  const int64_t max_splits = (p.num_ptiles + 3) / 4;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.ptiles_per_split = (int)((p.num_ptiles + splits - 1) / splits);
-  p.splits = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  choose_splits(out_tiles, p.num_ptiles, &p.ptiles_per_split, &p.splits);
   UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
   p.dw = a->dw;
   return bm_slabs == 2 ? launch_wgrad3x3<2>(p, stream) : launch_wgrad3x3<1>(p, stream);
@@ -1152,13 +1162,7 @@ int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
   p.cu_tiles = a->u.c / (64 * bm_slabs);
   p.cs_tiles = a->s.c / (64 * bn_slabs);
   const int64_t out_tiles = (int64_t)p.cu_tiles * p.cs_tiles * taps;
-  // split the pixel reduction until there are ~2 waves of work items, but keep >= 4 pixel tiles per item
-  int64_t splits = (2LL * sm_count() + out_tiles - 1) / out_tiles;
-  const int64_t max_splits = (p.num_ptiles + 3) / 4;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  p.ptiles_per_split = (int)((p.num_ptiles + splits - 1) / splits);
-  p.splits = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+  choose_splits(out_tiles, p.num_ptiles, &p.ptiles_per_split, &p.splits);
   UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
   p.dw = a->dw;
   if (bm_slabs == 2 && bn_slabs == 2) return launch_wgrad<2, 2>(p, stream);
