@@ -103,6 +103,13 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 //                          so shifted starts and a 1280-byte group stride address the TMA-written tile consistently.
 //                          Cuts L2->SMEM operand traffic of the A side 6.4x (23 KB instead of 9 x 16 KB per chunk).
 // =================================================================================================
+// per-CTA cycle counters of the halo kernel (role idle times), read back with unetk_debug_counters(); 8 slots per CTA:
+// [0] producer wait(empty A) [1] mma wait(full A) [2] mma wait(full B) [3] mma wait(tmem empty) [4] mma total
+// [5] epilogue g0 wait(tmem full) [6] epilogue g0 inside epilogue_tile [7] epilogue g0 total
+__device__ long long g_dbg[160 * 8];
+#define DBG_T0() const long long _t0 = clock64()
+#define DBG_ADD(var) var += clock64() - _t0
+
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                    // bf16 elements per K step = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;  // 16 KiB
@@ -436,12 +443,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first = true;
+      long long dbg_a = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile / p.num_m_tiles, m_tile = tile % p.num_m_tiles;
         const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * 8, h0 = th * 16;
         for (int chunk = 0; chunk < cpt; ++chunk) {
-          mbar_wait(&bars.empty_a[sa], pa ^ 1);
+          {
+            DBG_T0();
+            mbar_wait(&bars.empty_a[sa], pa ^ 1);
+            DBG_ADD(dbg_a);
+          }
           mbar_arrive_expect_tx(&bars.full_a[sa], kHaloBytes);
           tma_load_4d(smem + sa * kHaloStride, &p.map_a[0], &bars.full_a[sa], chunk * kBlockK, w0 - 1, h0 - 1, tn);
           if (++sa == a_stages) {
@@ -470,6 +482,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
         }
         first = false;
       }
+      if (blockIdx.x < 160) g_dbg[blockIdx.x * 8 + 0] = dbg_a;
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -479,14 +492,24 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
+      long long dbg_fa = 0, dbg_fb = 0, dbg_te = 0;
+      const long long dbg_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        {
+          DBG_T0();
+          mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+          DBG_ADD(dbg_te);
+        }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int chunk = 0; chunk < cpt; ++chunk) {
-          mbar_wait(&bars.full_a[sa], pa);
+          {
+            DBG_T0();
+            mbar_wait(&bars.full_a[sa], pa);
+            DBG_ADD(dbg_fa);
+          }
           tcgen05_fence_after();
           const uint32_t halo = smem_u32(smem + sa * kHaloStride);
           for (int tap = 0; tap < 9; ++tap) {
@@ -499,7 +522,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
               }
             } else {
               bslot = sb;
-              mbar_wait(&bars.full_b[sb], pb);
+              {
+                DBG_T0();
+                mbar_wait(&bars.full_b[sb], pb);
+                DBG_ADD(dbg_fb);
+              }
               tcgen05_fence_after();
             }
             // tap (r,s): output pixel (ph,pw) reads halo pixel (ph+r, pw+s) = halo row (ph+r)*10 + pw+s
@@ -526,6 +553,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
         umma_commit(&bars.tmem_full[acc]);
         first = false;
       }
+      if (blockIdx.x < 160) {
+        g_dbg[blockIdx.x * 8 + 1] = dbg_fa;
+        g_dbg[blockIdx.x * 8 + 2] = dbg_fb;
+        g_dbg[blockIdx.x * 8 + 3] = dbg_te;
+        g_dbg[blockIdx.x * 8 + 4] = clock64() - dbg_start;
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -533,6 +566,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
     const int q = (warp - 4) & 3;
     const int row = q * 32 + lane;
     const int pw_i = row & 7, ph_i = row >> 3;
+    long long dbg_tf = 0, dbg_epi = 0;
+    const long long dbg_start = clock64();
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     StatRegs<BLOCK_N> st;
     st.clear();
@@ -544,10 +579,23 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
       const int w0 = tw * 8, h0 = th * 16;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&bars.tmem_full[g], acc_phase);
+      {
+        DBG_T0();
+        mbar_wait(&bars.tmem_full[g], acc_phase);
+        DBG_ADD(dbg_tf);
+      }
       tcgen05_fence_after();
-      epilogue_tile<BLOCK_N, false>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
-                                    n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
+      {
+        DBG_T0();
+        epilogue_tile<BLOCK_N, false>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
+                                      n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
+        DBG_ADD(dbg_epi);
+      }
+    }
+    if (g == 0 && q == 0 && lane == 0 && blockIdx.x < 160) {
+      g_dbg[blockIdx.x * 8 + 5] = dbg_tf;
+      g_dbg[blockIdx.x * 8 + 6] = dbg_epi;
+      g_dbg[blockIdx.x * 8 + 7] = clock64() - dbg_start;
     }
     if (p.stat_sum) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
@@ -973,6 +1021,16 @@ static int launch_wgrad3x3(const WgradParams& p, cudaStream_t stream) {
 }
 
 }  // namespace tc
+
+}  // namespace unetk
+
+// internal debugging aid (not part of include/unetk.h): per-CTA idle-cycle counters of the last halo conv launch
+extern "C" int unetk_debug_counters(long long* host_out, int n) {
+  if (n > 160 * 8) n = 160 * 8;
+  return cudaMemcpyFromSymbol(host_out, unetk::tc::g_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
+}
+
+namespace unetk {
 
 // =================================================================================================
 // dispatcher-facing entry points

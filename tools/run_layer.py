@@ -62,3 +62,13 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 print(f"{a.op} cin={a.cin} cout={a.cout} hw={a.hw} batch={a.batch}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
+if os.environ.get("UNETK_DBG") == "1":
+    import ctypes
+    buf = (ctypes.c_longlong * (148 * 8))()
+    L.lib().unetk_debug_counters(buf, 148 * 8)
+    import numpy as np
+    d = np.array(buf[:]).reshape(148, 8)
+    names = ["prod wait emptyA", "mma wait fullA", "mma wait fullB", "mma wait tmem_empty", "mma total",
+             "epi0 wait tmem_full", "epi0 in epilogue", "epi0 total"]
+    for i, nm in enumerate(names):
+        print(f"{nm:22s} mean {d[:, i].mean():12.0f}  min {d[:, i].min():12d}  max {d[:, i].max():12d} cycles")
