@@ -167,7 +167,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     L.lib()  # fail loudly now if the extension is missing
     peaks = load_peaks()
     B = args.batch
@@ -177,7 +178,7 @@ def run_gpu_arm(args):
     model.precision = "bf16"
     model = model.to(dev).train()
     dp = DataParallelUNet(model) if world > 1 else None
-    opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01)
+    opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01, fused=True)   # same update rule, one fused kernel
     loss_fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor(CLASS_W3))
     agg = MetricsHistory(3)
     x_cpu, y_cpu = make_batch(B, H, W, 3, 3, seed=1234 + rank)
@@ -243,20 +244,22 @@ def run_gpu_arm(args):
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
-    # ---- per-launch instrumentation of the contraction kernels (extra steps, not part of `value`) ----
+    # ---- per-launch instrumentation of the contraction kernels (extra steps, not part of `value`; every rank runs
+    #      them -- they contain collectives -- but only rank 0 records events) ----
     roof = None
+    records = []
+    prof_steps = 2
     if rank == 0:
-        records = []
         L.PROFILE_HOOK = records
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        prof_steps = 2
-        for _ in range(prof_steps):
-            step_resident()
-        e1.record()
-        torch.cuda.synchronize()
-        L.PROFILE_HOOK = None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(prof_steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    L.PROFILE_HOOK = None
+    if rank == 0:
         step_ms = e0.elapsed_time(e1) / prof_steps
         flops = sum(r[1] for r in records if r[0] in ("conv", "wgrad"))
         kms = sum(r[2].elapsed_time(r[3]) for r in records if r[0] in ("conv", "wgrad"))
@@ -266,11 +269,19 @@ def run_gpu_arm(args):
             by_kind[r[0]][0] += r[2].elapsed_time(r[3]) / prof_steps
             by_kind[r[0]][1] += r[1] / prof_steps
         achieved = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        dominant = None
+        dpath = os.path.join(ROOT, "profiles", "dominant_launch.json")
+        if os.path.isfile(dpath):
+            dominant = json.load(open(dpath))
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["sustained"], "frac_of_burst": achieved / peaks["burst"], "traffic": None,
+                "frac": achieved / peaks["sustained"], "frac_of_burst": achieved / peaks["burst"],
+                "traffic": dominant["traffic_bytes"] if dominant else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a long step)",
-                "kernel": "tc_conv_kernel / tc_wgrad_kernel (tcgen05 implicit GEMM)",
-                "how": f"CUDA events around every unetk_conv/unetk_wgrad launch over {prof_steps} instrumented steps",
+                "kernel": "tc::tc_conv_kernel / tc_conv_halo_kernel / tc_wgrad3x3_kernel (tcgen05 implicit GEMM family)",
+                "how": f"sum of algorithmic FLOPs / sum of CUDA-event durations over every unetk_conv and unetk_wgrad launch "
+                       f"of {prof_steps} instrumented steps; `traffic` is the ncu DRAM byte count of the dominant launch "
+                       "described in `dominant_launch` (profiles/dominant_launch.json)",
+                "dominant_launch": dominant,
                 "share_of_step": kms / prof_steps / step_ms,
                 "ms_per_step_by_kernel": {k: round(v[0], 3) for k, v in sorted(by_kind.items())},
                 "step_tflops": (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12,
