@@ -192,7 +192,7 @@ struct StatRegs {
   }
 };
 
-template <int BLOCK_N, bool HAS_BIAS>
+template <int BLOCK_N, bool HAS_BIAS, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* staging, int bar_id, uint32_t tmem_acc, int q,
                                               int lane, bool valid_row, int n_tile, int w0, int h0, int n0,
                                               StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar) {
@@ -223,7 +223,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
       // accumulator fully drained: hand the TMEM stage back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+      }
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -418,6 +420,158 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// CTA-pair variant of tc_conv_kernel (cta_group::2).  The in-kernel counters showed the single-CTA MMA bound by
+// shared-memory operand fetch (~80 B/cycle: (4096 + 32 N)/80 cycles per M=128 MMA).  A pair of CTAs on adjacent SMs
+// issues ONE tcgen05.mma of M = 256: each CTA supplies the A rows of its own 128-pixel tile and only HALF of the B
+// (weight) rows, so the per-SM operand traffic per MMA drops to 4096 + 16 N bytes.
+//   * cluster (2,1,1); pair p handles (N tile, pixel tiles 2j and 2j+1); CTA rank r owns pixel tile 2j+r
+//   * full barriers live in the leader (rank 0): both producers' TMA loads complete_tx there; count 2
+//   * MMA issued by the leader only; tcgen05.commit multicast releases ring slots / publishes accumulators in BOTH CTAs
+//   * every CTA drains its own 128 TMEM lanes with its two epilogue groups; tmem_empty arrivals go to the leader
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool HAS_BIAS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+    tc_conv2_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBHalfBytes;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars bars(smem + p.off_bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int m_pairs = (p.num_m_tiles + 1) >> 1;
+  const int num_ptiles = m_pairs * p.num_n_tiles;
+  const int ksteps = p.taps * p.chunks_per_tap;
+  const int stages = p.stages;
+
+  cluster_sync_all();  // both CTAs of the pair are resident before any cross-CTA traffic / 2-SM TMEM allocation
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_a[0]);
+    prefetch_tensormap(&p.map_b);
+    prefetch_tensormap(&p.map_y[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&bars.full_a[i], 2);   // one arrival per producer of the pair (used in the leader only)
+      mbar_init(&bars.empty_a[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.tmem_full[i], 1);
+      mbar_init(&bars.tmem_empty[i], 8);  // 4 epilogue warps of each CTA (used in the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<kTmemCols>(bars.tmem_ptr);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *bars.tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;   // a tile past the end is all out-of-bounds: zero fill
+        for (int s = 0; s < ksteps; ++s) {
+          const int t = s / p.chunks_per_tap, chunk = s % p.chunks_per_tap;
+          int dh = 0, dw = 0, mi = 0;
+          if (p.mode == 1) {
+            dh = t / 3 - 1;
+            dw = t % 3 - 1;
+          } else if (p.mode == 3) {
+            mi = t;
+          }
+          mbar_wait(&bars.empty_a[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          if (leader)
+            mbar_arrive_expect_tx(&bars.full_a[stage], 2 * kStageBytes);
+          else
+            mbar_arrive_cluster(&bars.full_a[stage], 0);
+          tma_load_4d_2sm(sa, &p.map_a[mi], &bars.full_a[stage], chunk * kBlockK, w0 + dw, h0 + dh, n0);
+          tma_load_2d_2sm(sa + kABytes, &p.map_b, &bars.full_a[stage], s * kBlockK,
+                          n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int s = 0; s < ksteps; ++s) {
+          mbar_wait(&bars.full_a[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t da = make_smem_desc(sa, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&bars.empty_a[stage]);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&bars.tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs; group g drains the pair tiles with (it & 1) == g) =====================
+    const int g = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;
+    const int row = q * 32 + lane;
+    const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
+    uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    StatRegs<BLOCK_N> st;
+    st.clear();
+    st.n_tile = -1;
+    int it = g;
+    for (int pt = pair_id + g * num_pairs; pt < num_ptiles; pt += 2 * num_pairs, it += 2) {
+      const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+      const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
+      const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&bars.tmem_full[g], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BLOCK_N, HAS_BIAS, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
+                                             valid, n_tile, w0, h0, n0, st, &bars.tmem_empty[g]);
+    }
+    if (p.stat_sum) st.flush(p, lane);
+    if (q == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();   // the peer may still read this CTA's shared memory / signal its barriers until here
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __grid_constant__ ConvParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -606,6 +760,183 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// CTA-pair variant of the halo kernel: each CTA loads the halo of its own 16x8 pixel tile and HALF of the weight rows
+// of every K step (resident or streamed); the leader issues M = 256 MMAs.  Same barrier protocol as tc_conv2_kernel.
+// -------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+    tc_conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kBHalfBytes = (BLOCK_N / 2) * kBlockK * 2;
+  constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars bars(smem + p.off_bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  const int m_pairs = (p.num_m_tiles + 1) >> 1;
+  const int num_ptiles = m_pairs * p.num_n_tiles;
+  const int cpt = p.chunks_per_tap;
+  const int a_stages = p.stages, b_slots = p.b_slots;
+  const bool resident = p.resident_b != 0;
+
+  cluster_sync_all();
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_a[0]);
+    prefetch_tensormap(&p.map_b);
+    prefetch_tensormap(&p.map_y[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a_stages; ++i) {
+      mbar_init(&bars.full_a[i], 2);
+      mbar_init(&bars.empty_a[i], 1);
+    }
+    for (int i = 0; i < b_slots; ++i) {
+      mbar_init(&bars.full_b[i], 2);
+      mbar_init(&bars.empty_b[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.tmem_full[i], 1);
+      mbar_init(&bars.tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<kTmemCols>(bars.tmem_ptr);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *bars.tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first = true;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
+        const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * 8, h0 = th * 16;
+        const int brow = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int chunk = 0; chunk < cpt; ++chunk) {
+          mbar_wait(&bars.empty_a[sa], pa ^ 1);
+          if (leader) mbar_arrive_expect_tx(&bars.full_a[sa], 2 * kHaloBytes); else mbar_arrive_cluster(&bars.full_a[sa], 0);
+          tma_load_4d_2sm(smem + sa * kHaloStride, &p.map_a[0], &bars.full_a[sa], chunk * kBlockK, w0 - 1, h0 - 1, tn);
+          if (++sa == a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+          for (int tap = 0; tap < 9; ++tap) {
+            if (resident) {
+              if (first) {
+                const int slot = chunk * 9 + tap;
+                if (leader) mbar_arrive_expect_tx(&bars.full_b[slot], 2 * kBHalfBytes); else mbar_arrive_cluster(&bars.full_b[slot], 0);
+                tma_load_2d_2sm(smem + p.off_b + slot * kBHalfBytes, &p.map_b, &bars.full_b[slot], (tap * cpt + chunk) * kBlockK, brow);
+              }
+            } else {
+              mbar_wait(&bars.empty_b[sb], pb ^ 1);
+              if (leader) mbar_arrive_expect_tx(&bars.full_b[sb], 2 * kBHalfBytes); else mbar_arrive_cluster(&bars.full_b[sb], 0);
+              tma_load_2d_2sm(smem + p.off_b + sb * kBHalfBytes, &p.map_b, &bars.full_b[sb], (tap * cpt + chunk) * kBlockK, brow);
+              if (++sb == b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+        }
+        first = false;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      bool first = true;
+      int it = 0;
+      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int chunk = 0; chunk < cpt; ++chunk) {
+          mbar_wait(&bars.full_a[sa], pa);
+          tcgen05_fence_after();
+          const uint32_t halo = smem_u32(smem + sa * kHaloStride);
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t bslot;
+            if (resident) {
+              bslot = chunk * 9 + tap;
+              if (first) {
+                mbar_wait(&bars.full_b[bslot], 0);
+                tcgen05_fence_after();
+              }
+            } else {
+              bslot = sb;
+              mbar_wait(&bars.full_b[sb], pb);
+              tcgen05_fence_after();
+            }
+            const uint32_t a0 = halo + ((tap / 3) * 10 + (tap % 3)) * 128;
+            const uint64_t da = make_smem_desc(a0, 0, 10 * 128);
+            const uint64_t db = make_smem_desc(smem_u32(smem + p.off_b + bslot * kBHalfBytes), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if (!resident) {
+              umma_commit_2sm(&bars.empty_b[sb]);
+              if (++sb == b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+          umma_commit_2sm(&bars.empty_a[sa]);
+          if (++sa == a_stages) {
+            sa = 0;
+            pa ^= 1;
+          }
+        }
+        umma_commit_2sm(&bars.tmem_full[acc]);
+        first = false;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2;
+    const int q = (warp - 4) & 3;
+    const int row = q * 32 + lane;
+    const int pw_i = row & 7, ph_i = row >> 3;
+    uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    StatRegs<BLOCK_N> st;
+    st.clear();
+    st.n_tile = -1;
+    int it = g;
+    for (int pt = pair_id + g * num_pairs; pt < num_ptiles; pt += 2 * num_pairs, it += 2) {
+      const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+      const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * 8, h0 = th * 16;
+      const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && tn < p.n;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&bars.tmem_full[g], acc_phase);
+      tcgen05_fence_after();
+      epilogue_tile<BLOCK_N, false, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
+                                          valid, n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
+    }
+    if (p.stat_sum) st.flush(p, lane);
+    if (q == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
   }
 }
 
@@ -977,14 +1308,32 @@ static int set_smem_attr(K kernel, int bytes) {
 constexpr int kMaxSmem = 227 * 1024;
 
 template <int BLOCK_N>
-static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, cudaStream_t stream) {
+static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, bool pair, cudaStream_t stream) {
   static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N, false>, kMaxSmem);
   static int attr_rc1 = set_smem_attr(tc_conv_kernel<BLOCK_N, true>, kMaxSmem);
   static int attr_rc2 = set_smem_attr(tc_conv_halo_kernel<BLOCK_N>, kMaxSmem);
+  static int attr_rc3 = set_smem_attr(tc_conv2_kernel<BLOCK_N, false>, kMaxSmem);
+  static int attr_rc4 = set_smem_attr(tc_conv2_kernel<BLOCK_N, true>, kMaxSmem);
+  static int attr_rc5 = set_smem_attr(tc_conv_halo2_kernel<BLOCK_N>, kMaxSmem);
+  if (attr_rc5) return attr_rc5;
   if (attr_rc) return attr_rc;
   if (attr_rc1) return attr_rc1;
   if (attr_rc2) return attr_rc2;
+  if (attr_rc3) return attr_rc3;
+  if (attr_rc4) return attr_rc4;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
+  if (pair) {
+    const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    const int pairs = ptiles < sm_count() / 2 ? ptiles : sm_count() / 2;
+    if (halo)
+      tc_conv_halo2_kernel<BLOCK_N><<<2 * pairs, kConvThreads, smem_bytes, stream>>>(p);
+    else if (p.bias)
+      tc_conv2_kernel<BLOCK_N, true><<<2 * pairs, kConvThreads, smem_bytes, stream>>>(p);
+    else
+      tc_conv2_kernel<BLOCK_N, false><<<2 * pairs, kConvThreads, smem_bytes, stream>>>(p);
+    UNETK_LAUNCH_CHECK();
+    return UNETK_OK;
+  }
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (halo)
     tc_conv_halo_kernel<BLOCK_N><<<grid, kConvThreads, smem_bytes, stream>>>(p);
@@ -1049,6 +1398,15 @@ bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char**
   return true;
 }
 
+static bool pair_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UNETK_NO_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool halo_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -1093,7 +1451,9 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   } else {
     if ((rc = make_act_map(&p.map_y[0], a->y, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
   }
-  if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, block_n))) return rc;
+  // CTA pairs (cta_group::2) for the per-tap kernel when there are enough pixel tiles to pair up
+  const bool pair = !pair_disabled() && pt.num_tiles() >= 2;
+  if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, pair ? block_n / 2 : block_n))) return rc;
   p.mode = a->mode;
   p.taps = g.taps;
   p.chunks_per_tap = cpt;
@@ -1112,35 +1472,36 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   p.num_staging = 2;
   int ring_bytes;
   if (!halo) {
-    const int stage_bytes = kABytes + b_bytes;
+    const int stage_bytes = kABytes + (pair ? b_bytes / 2 : b_bytes);
     p.stages = budget / stage_bytes;
     if (p.stages > kMaxAStages) p.stages = kMaxAStages;
     ring_bytes = p.stages * stage_bytes;
     p.off_b = 0;
   } else {
     const int ksteps = 9 * cpt;
-    p.resident_b = (p.num_n_tiles == 1 && ksteps <= kMaxBSlots && ksteps * b_bytes + 2 * kHaloStride <= budget) ? 1 : 0;
+    const int bb = pair ? b_bytes / 2 : b_bytes;   // a CTA of a pair holds half of the weight rows
+    p.resident_b = (p.num_n_tiles == 1 && ksteps <= kMaxBSlots && ksteps * bb + 2 * kHaloStride <= budget) ? 1 : 0;
     if (p.resident_b) {
       p.b_slots = ksteps;
-      p.stages = (budget - ksteps * b_bytes) / kHaloStride;
+      p.stages = (budget - ksteps * bb) / kHaloStride;
       if (p.stages > 4) p.stages = 4;
     } else {
       p.stages = 3;
-      p.b_slots = (budget - p.stages * kHaloStride) / b_bytes;
+      p.b_slots = (budget - p.stages * kHaloStride) / bb;
       if (p.b_slots > 9) p.b_slots = 9;
       UNETK_REQUIRE(p.b_slots >= 2, "conv(tc halo): shared-memory plan failed");
     }
     p.off_b = p.stages * kHaloStride;
-    ring_bytes = p.off_b + p.b_slots * b_bytes;
+    ring_bytes = p.off_b + p.b_slots * bb;
   }
   p.off_staging = ring_bytes;
   p.off_stats = 0;
   p.off_bars = p.off_staging + 2 * kStagingBytes;
   const int smem_bytes = p.off_bars + kBarBytes + 1024;
   UNETK_REQUIRE(smem_bytes <= kMaxSmem && p.stages >= 2, "conv(tc): shared-memory plan failed (%d bytes, %d stages)", smem_bytes, p.stages);
-  if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, stream);
-  if (block_n == 128) return launch_conv<128>(p, smem_bytes, halo, stream);
-  return launch_conv<64>(p, smem_bytes, halo, stream);
+  if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, pair, stream);
+  if (block_n == 128) return launch_conv<128>(p, smem_bytes, halo, pair, stream);
+  return launch_conv<64>(p, smem_bytes, halo, pair, stream);
 }
 
 bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
