@@ -1452,7 +1452,11 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
     if ((rc = make_act_map(&p.map_y[0], a->y, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
   }
   // CTA pairs (cta_group::2) for the per-tap kernel when there are enough pixel tiles to pair up
-  const bool pair = !pair_disabled() && pt.num_tiles() >= 2;
+  // Measured on B200 (batch 64): pairs gain 4-10% on the per-tap kernel (N = 256, long main loops) but LOSE 10-30% on the
+  // halo kernel (N <= 128: ~2-5k cycle main loops per tile cannot amortise the cross-CTA accumulator hand-off), so the
+  // halo kernel stays single-CTA unless UNETK_HALO_PAIR=1 asks for the experiment.
+  static const bool halo_pair = getenv("UNETK_HALO_PAIR") && getenv("UNETK_HALO_PAIR")[0] == '1';
+  const bool pair = !pair_disabled() && pt.num_tiles() >= 2 && (!halo || halo_pair);
   if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, pair ? block_n / 2 : block_n))) return rc;
   p.mode = a->mode;
   p.taps = g.taps;
