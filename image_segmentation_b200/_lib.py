@@ -47,7 +47,7 @@ class BnFinalizeArgs(C.Structure):
 class BnBwdArgs(C.Structure):
     _fields_ = [("z", Tensor), ("dy", Tensor), ("dpool", Tensor), ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("mean", C.c_void_p), ("invstd", C.c_void_p), ("sums", C.c_void_p), ("dz", Tensor),
-                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("pool_idx", C.c_void_p)]
 
 
 class WJob(C.Structure):
@@ -90,7 +90,7 @@ def lib():
             "unetk_channel_sum": [P(Tensor), vp, vp],
             "unetk_bn_stats": [P(Tensor), vp, vp, vp],
             "unetk_bn_finalize": [P(BnFinalizeArgs), vp],
-            "unetk_bn_relu_apply": [P(Tensor), vp, vp, P(Tensor), P(Tensor), vp],
+            "unetk_bn_relu_apply": [P(Tensor), vp, vp, P(Tensor), P(Tensor), vp, vp],
             "unetk_bn_relu_bwd_reduce": [P(BnBwdArgs), vp],
             "unetk_bn_relu_bwd_apply": [P(BnBwdArgs), vp],
             "unetk_head_fprop": [P(Tensor), vp, vp, C.c_int32, vp, vp],
@@ -247,14 +247,14 @@ def bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean,
     _run("bn_finalize", 1, 0, lib().unetk_bn_finalize, C.byref(a), stream_ptr())
 
 
-def bn_relu_apply(z, scale, shift, a, pooled=None):
+def bn_relu_apply(z, scale, shift, a, pooled=None, pool_idx=None):
     _run("bn_apply", 1, 0, lib().unetk_bn_relu_apply, C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(),
-         C.byref(nhwc(a)), C.byref(nhwc(pooled)), stream_ptr())
+         C.byref(nhwc(a)), C.byref(nhwc(pooled)), ptr(pool_idx), stream_ptr())
 
 
-def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta):
+def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx=None):
     a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
-                  ptr(dgamma), ptr(dbeta))
+                  ptr(dgamma), ptr(dbeta), ptr(pool_idx))
     s = stream_ptr()
     _run("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, C.byref(a), s)
     _run("bn_bwd_apply", 1, 0, lib().unetk_bn_relu_bwd_apply, C.byref(a), s)

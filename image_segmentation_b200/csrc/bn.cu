@@ -106,7 +106,7 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(kThreads)
     bn_relu_apply_kernel(const T* __restrict__ z, int zld, const float* __restrict__ scale,
                          const float* __restrict__ shift, T* __restrict__ a, int ald, T* __restrict__ pooled, int pld,
-                         int n, int h, int w, int cg) {
+                         uint16_t* __restrict__ pool_idx, int n, int h, int w, int cg) {
   // work item = (pixel or 2x2 window, channel group)
   const int hh = POOL ? h / 2 : h, ww = POOL ? w / 2 : w;
   const int64_t total = (int64_t)n * hh * ww * cg;
@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(kThreads)
       const int img = (int)(p / hh);
       float mx[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mx[k] = 0.f;  // ReLU output is >= 0
+      for (int k = 0; k < 8; ++k) mx[k] = -1.f;  // ReLU output is >= 0: position 0 always wins the first comparison
+      uint32_t arg = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int64_t pix = ((int64_t)img * h + (2 * y + (q >> 1))) * w + (2 * x + (q & 1));
@@ -137,12 +138,17 @@ __global__ void __launch_bounds__(kThreads)
         load8(z + pix * zld + g * 8, v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
-          mx[k] = fmaxf(mx[k], v[k]);
+          v[k] = round_to<T>(fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f));
+          if (v[k] > mx[k]) {   // strict: the first maximum in scan order keeps the gradient (torch's max_pool2d rule)
+            mx[k] = v[k];
+            arg = (arg & ~(3u << (2 * k))) | ((uint32_t)q << (2 * k));
+          }
         }
         store8(a + pix * ald + g * 8, v);
       }
-      store8(pooled + (((int64_t)img * hh + y) * ww + x) * pld + g * 8, mx);
+      const int64_t win = ((int64_t)img * hh + y) * ww + x;
+      store8(pooled + win * pld + g * 8, mx);
+      if (pool_idx) pool_idx[win * cg + g] = (uint16_t)arg;
     }
   }
 }
@@ -155,45 +161,52 @@ struct BwdSrc {
   const T* z; int zld;
   const T* dy; int dyld;      // may be null
   const T* dp; int dpld;      // may be null (POOL variants only)
+  const uint16_t* pidx;       // [N,H/2,W/2,C/8]: 2-bit window position per channel, written by bn_relu_apply (POOL only)
   const float* scale; const float* shift; const float* mean; const float* invstd;
   int n, h, w, cg;
 };
 
-// One 2x2 pooling window, 8 channels: which position holds the (first) maximum of the stored activation, and which
-// positions pass the ReLU.  Packed: bits [2k,2k+2) of `arg` = window position for channel k, bit (4k+q) of `pos` = a>0.
-template <typename T>
-__device__ __forceinline__ void window_scan(const T* __restrict__ z, int zld, const int64_t (&pix)[4], int g,
-                                            const float (&sc)[8], const float (&sh)[8], uint32_t& arg, uint32_t& pos) {
-  float best[8];
+// masked upstream gradient of one pixel, 8 channels:  dy = (dA_full + routed pooled gradient) * [a > 0]
+// POOL: the pooled gradient of window (y/2, x/2) goes to the position recorded by the forward pass (pool_idx: 2 bits per
+// channel, first maximum in scan order), so the backward pass never re-derives the argmax.
+template <typename T, bool POOL>
+__device__ __forceinline__ void load_pixel(const BwdSrc<T>& s, int64_t pix, int g, const float (&sc)[8], const float (&sh)[8],
+                                           float (&zv)[8], float (&dy)[8]) {
+  load8(s.z + pix * s.zld + g * 8, zv);
+  float d[8];
+  if (!POOL || s.dy) {
+    load8(s.dy + pix * s.dyld + g * 8, d);
+  } else {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) best[k] = -INFINITY;
-  arg = 0;
-  pos = 0;
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+  }
+  if (POOL) {
+    const int x = (int)(pix % s.w);
+    const int y = (int)((pix / s.w) % s.h);
+    const int64_t img = pix / ((int64_t)s.w * s.h);
+    const int64_t win = (img * (s.h >> 1) + (y >> 1)) * (s.w >> 1) + (x >> 1);
+    const uint32_t q = (uint32_t)((y & 1) * 2 + (x & 1));
+    const uint32_t arg = s.pidx[win * s.cg + g];
+    float dp[8];
+    load8(s.dp + win * s.dpld + g * 8, dp);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float zv[8];
-    load8(z + pix[q] * zld + g * 8, zv);
+    for (int k = 0; k < 8; ++k) d[k] += (((arg >> (2 * k)) & 3u) == q) ? dp[k] : 0.f;
+  }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-      if (act > best[k]) {
-        best[k] = act;
-        arg = (arg & ~(3u << (2 * k))) | ((uint32_t)q << (2 * k));
-      }
-      if (act > 0.f) pos |= 1u << (4 * k + q);
-    }
+  for (int k = 0; k < 8; ++k) {
+    const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
+    dy[k] = act > 0.f ? d[k] : 0.f;
   }
 }
 
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, 3)
     bn_bwd_reduce_kernel(BwdSrc<T> s, int cgb, int items_per_block, double* __restrict__ s1, double* __restrict__ s2) {
   const int rows = kThreads / cgb;
   const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
   const int cg0 = blockIdx.x * cgb;
   const int g = cg0 + lane_g;
-  const int hh = POOL ? s.h / 2 : s.h, ww = POOL ? s.w / 2 : s.w;
-  const int64_t nitems = (int64_t)s.n * hh * ww;
+  const int64_t nitems = (int64_t)s.n * s.h * s.w;
   const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
   const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
   float sc[8], sh[8];
@@ -204,66 +217,24 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
   float acc[2][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
-  if (!POOL) {
-    // two pixels per iteration: four independent 16-byte loads in flight per thread
-    int64_t it = i0 + row;
-    for (; it + rows < i1; it += 2 * rows) {
-      float za[8], da[8], zb[8], db[8];
-      load8(s.z + it * s.zld + g * 8, za);
-      load8(s.dy + it * s.dyld + g * 8, da);
-      load8(s.z + (it + rows) * s.zld + g * 8, zb);
-      load8(s.dy + (it + rows) * s.dyld + g * 8, db);
+  int64_t it = i0 + row;
+  for (; it + rows < i1; it += 2 * rows) {   // two pixels per iteration: more independent loads in flight
+    float za[8], ya[8], zb[8], yb[8];
+    load_pixel<T, POOL>(s, it, g, sc, sh, za, ya);
+    load_pixel<T, POOL>(s, it + rows, g, sc, sh, zb, yb);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
-        const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
-        const float ya = aa > 0.f ? da[k] : 0.f, yb = ab > 0.f ? db[k] : 0.f;
-        acc[0][k] += ya + yb;
-        acc[1][k] = fmaf(ya, za[k], fmaf(yb, zb[k], acc[1][k]));
-      }
+    for (int k = 0; k < 8; ++k) {
+      acc[0][k] += ya[k] + yb[k];
+      acc[1][k] = fmaf(ya[k], za[k], fmaf(yb[k], zb[k], acc[1][k]));
     }
-    for (; it < i1; it += rows) {
-      float zv[8], d[8];
-      load8(s.z + it * s.zld + g * 8, zv);
-      load8(s.dy + it * s.dyld + g * 8, d);
+  }
+  for (; it < i1; it += rows) {
+    float zv[8], dy[8];
+    load_pixel<T, POOL>(s, it, g, sc, sh, zv, dy);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-        const float dyk = act > 0.f ? d[k] : 0.f;
-        acc[0][k] += dyk;
-        acc[1][k] = fmaf(dyk, zv[k], acc[1][k]);
-      }
-    }
-  } else {
-    for (int64_t it = i0 + row; it < i1; it += rows) {
-      const int x = (int)(it % ww);
-      const int y = (int)((it / ww) % hh);
-      const int img = (int)(it / ((int64_t)ww * hh));
-      int64_t pix[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-      uint32_t arg, pos;
-      window_scan<T>(s.z, s.zld, pix, g, sc, sh, arg, pos);
-      float dp[8];
-      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float zv[8], d[8];
-        load8(s.z + pix[q] * s.zld + g * 8, zv);   // second touch: L1 hit
-        if (s.dy) {
-          load8(s.dy + pix[q] * s.dyld + g * 8, d);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) d[k] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float gsum = d[k] + ((((arg >> (2 * k)) & 3u) == (uint32_t)q) ? dp[k] : 0.f);
-          const float dyk = ((pos >> (4 * k + q)) & 1u) ? gsum : 0.f;
-          acc[0][k] += dyk;
-          acc[1][k] = fmaf(dyk, zv[k], acc[1][k]);
-        }
-      }
+    for (int k = 0; k < 8; ++k) {
+      acc[0][k] += dy[k];
+      acc[1][k] = fmaf(dy[k], zv[k], acc[1][k]);
     }
   }
   {
@@ -281,15 +252,14 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
 // registers.  dz = sc*(dy - m1 - xhat*m2) is evaluated as  A*dy + B*z + C  with
 //   A = sc,  B = -sc*m2*invstd,  C = sc*(m2*invstd*mean - m1).
 template <typename T, bool POOL>
-__global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
+__global__ void __launch_bounds__(kThreads, 3)
     bn_bwd_apply_kernel(BwdSrc<T> s, int cgb, int items_per_block, const double* __restrict__ s1,
                         const double* __restrict__ s2, double inv_count, T* __restrict__ dz, int dzld,
                         float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int rows = kThreads / cgb;
   const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
   const int g = blockIdx.x * cgb + lane_g;
-  const int hh = POOL ? s.h / 2 : s.h, ww = POOL ? s.w / 2 : s.w;
-  const int64_t nitems = (int64_t)s.n * hh * ww;
+  const int64_t nitems = (int64_t)s.n * s.h * s.w;
   const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
   const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
   float sc[8], sh[8], cb[8], cc[8];
@@ -314,66 +284,25 @@ __global__ void __launch_bounds__(kThreads, POOL ? 2 : 3)
       if (dbeta) dbeta[g * 8 + k] = (float)s1[g * 8 + k];
     }
   }
-  if (!POOL) {
-    int64_t it = i0 + row;
-    for (; it + rows < i1; it += 2 * rows) {
-      float za[8], da[8], zb[8], db[8], oa[8], ob[8];
-      load8(s.z + it * s.zld + g * 8, za);
-      load8(s.dy + it * s.dyld + g * 8, da);
-      load8(s.z + (it + rows) * s.zld + g * 8, zb);
-      load8(s.dy + (it + rows) * s.dyld + g * 8, db);
+  int64_t it = i0 + row;
+  for (; it + rows < i1; it += 2 * rows) {
+    float za[8], ya[8], zb[8], yb[8], oa[8], ob[8];
+    load_pixel<T, POOL>(s, it, g, sc, sh, za, ya);
+    load_pixel<T, POOL>(s, it + rows, g, sc, sh, zb, yb);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
-        const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
-        oa[k] = fmaf(sc[k], aa > 0.f ? da[k] : 0.f, fmaf(cb[k], za[k], cc[k]));
-        ob[k] = fmaf(sc[k], ab > 0.f ? db[k] : 0.f, fmaf(cb[k], zb[k], cc[k]));
-      }
-      store8(dz + it * dzld + g * 8, oa);
-      store8(dz + (it + rows) * dzld + g * 8, ob);
+    for (int k = 0; k < 8; ++k) {
+      oa[k] = fmaf(sc[k], ya[k], fmaf(cb[k], za[k], cc[k]));
+      ob[k] = fmaf(sc[k], yb[k], fmaf(cb[k], zb[k], cc[k]));
     }
-    for (; it < i1; it += rows) {
-      float zv[8], d[8], o[8];
-      load8(s.z + it * s.zld + g * 8, zv);
-      load8(s.dy + it * s.dyld + g * 8, d);
+    store8(dz + it * dzld + g * 8, oa);
+    store8(dz + (it + rows) * dzld + g * 8, ob);
+  }
+  for (; it < i1; it += rows) {
+    float zv[8], dy[8], o[8];
+    load_pixel<T, POOL>(s, it, g, sc, sh, zv, dy);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-        o[k] = fmaf(sc[k], act > 0.f ? d[k] : 0.f, fmaf(cb[k], zv[k], cc[k]));
-      }
-      store8(dz + it * dzld + g * 8, o);
-    }
-  } else {
-    for (int64_t it = i0 + row; it < i1; it += rows) {
-      const int x = (int)(it % ww);
-      const int y = (int)((it / ww) % hh);
-      const int img = (int)(it / ((int64_t)ww * hh));
-      int64_t pix[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pix[q] = ((int64_t)img * s.h + (2 * y + (q >> 1))) * s.w + (2 * x + (q & 1));
-      uint32_t arg, pos;
-      window_scan<T>(s.z, s.zld, pix, g, sc, sh, arg, pos);
-      float dp[8];
-      load8(s.dp + (((int64_t)img * hh + y) * ww + x) * s.dpld + g * 8, dp);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float zv[8], d[8], o[8];
-        load8(s.z + pix[q] * s.zld + g * 8, zv);   // second touch: L1 hit
-        if (s.dy) {
-          load8(s.dy + pix[q] * s.dyld + g * 8, d);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) d[k] = 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float gsum = d[k] + ((((arg >> (2 * k)) & 3u) == (uint32_t)q) ? dp[k] : 0.f);
-          const float dyk = ((pos >> (4 * k + q)) & 1u) ? gsum : 0.f;
-          o[k] = fmaf(sc[k], dyk, fmaf(cb[k], zv[k], cc[k]));
-        }
-        store8(dz + pix[q] * dzld + g * 8, o);
-      }
-    }
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], dy[k], fmaf(cb[k], zv[k], cc[k]));
+    store8(dz + it * dzld + g * 8, o);
   }
 }
 
@@ -389,6 +318,7 @@ static BwdSrc<T> make_src(const unetk_bn_bwd_args* a) {
   s.z = (const T*)a->z.ptr; s.zld = a->z.ld;
   s.dy = (const T*)a->dy.ptr; s.dyld = a->dy.ld;
   s.dp = (const T*)a->dpool.ptr; s.dpld = a->dpool.ld;
+  s.pidx = static_cast<const uint16_t*>(a->pool_idx);
   s.scale = a->scale; s.shift = a->shift; s.mean = a->mean; s.invstd = a->invstd;
   s.n = a->z.n; s.h = a->z.h; s.w = a->z.w; s.cg = a->z.c / 8;
   return s;
@@ -406,6 +336,7 @@ static int check_bwd(const unetk_bn_bwd_args* a) {
     UNETK_REQUIRE(tensor_ok(a->dpool) && vec8_ok(a->dpool) && a->dpool.dtype == a->z.dtype && a->dpool.n == a->z.n &&
                       a->dpool.h * 2 == a->z.h && a->dpool.w * 2 == a->z.w && a->dpool.c == a->z.c,
                   "bn_bwd: dpool must be [N,H/2,W/2,C]");
+    UNETK_REQUIRE(a->pool_idx != nullptr, "bn_bwd: dpool needs the pool_idx written by unetk_bn_relu_apply");
   }
   UNETK_REQUIRE(a->scale && a->shift && a->mean && a->invstd && a->sums, "bn_bwd: null statistics");
   return UNETK_OK;
@@ -448,7 +379,7 @@ int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream) {
 }
 
 int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
-                        const unetk_tensor* pooled, void* stream) {
+                        const unetk_tensor* pooled, uint16_t* pool_idx, void* stream) {
   UNETK_REQUIRE(z && a && scale && shift, "bn_relu_apply: null argument");
   UNETK_REQUIRE(tensor_ok(*z) && vec8_ok(*z) && tensor_ok(*a) && vec8_ok(*a), "bn_relu_apply: bad z/a tensor");
   UNETK_REQUIRE(a->dtype == z->dtype && a->n == z->n && a->h == z->h && a->w == z->w && a->c == z->c,
@@ -465,10 +396,10 @@ int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* 
   UNETK_DISPATCH_DTYPE(z->dtype, T, {
     if (pool)
       bn_relu_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, (T*)pooled->ptr, pooled->ld, z->n, z->h, z->w, cg);
+          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, (T*)pooled->ptr, pooled->ld, pool_idx, z->n, z->h, z->w, cg);
     else
       bn_relu_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, nullptr, 0, z->n, z->h, z->w, cg);
+          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, nullptr, 0, nullptr, z->n, z->h, z->w, cg);
   });
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
@@ -479,8 +410,8 @@ int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream) {
   if (rc) return rc;
   const bool pool = a->dpool.ptr != nullptr;
   const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
-  const int64_t nitems = pixels(a->z) / (pool ? 4 : 1);
-  int ipb = rows * (pool ? 8 : 32);
+  const int64_t nitems = pixels(a->z);
+  int ipb = rows * 32;
   if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
   UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_reduce: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));
@@ -506,8 +437,8 @@ int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream) {
   const bool pool = a->dpool.ptr != nullptr;
   UNETK_REQUIRE(pool || a->dy.ptr, "bn_bwd_apply: dy required without dpool");
   const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
-  const int64_t nitems = pixels(a->z) / (pool ? 4 : 1);
-  int ipb = rows * (pool ? 4 : 16);
+  const int64_t nitems = pixels(a->z);
+  int ipb = rows * 16;
   if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
   UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_apply: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));

@@ -43,6 +43,7 @@ class _ConvBN:
         self.z = None        # raw conv output
         self.a = None        # activated output view
         self.pooled = None   # optional max-pooled output
+        self.pool_idx = None  # 2-bit arg-max position per pooled element (written forward, read backward)
         self.wf = self.wd = None
         self.dz = None       # gradient wrt z
         self.g_in = None     # where the data gradient (wrt src) is written; None for the first layer
@@ -120,6 +121,7 @@ class UNetPlan:
             if l < 4:
                 l2.a = self.cat[l][..., :c]
                 l2.pooled = self._act(n, hs[l + 1], ws[l + 1], c)
+                l2.pool_idx = torch.empty((n, hs[l + 1], ws[l + 1], c // 8), dtype=torch.int16, device=dev)
                 prev = l2.pooled
             else:
                 l2.a = self._act(n, hs[l], ws[l], c)
@@ -313,7 +315,7 @@ class UNetPlan:
                           bn.running_mean if track else None, bn.running_var if track else None,
                           bn.num_batches_tracked if (track and training) else None,
                           momentum, bn.eps, l.scale, l.shift, l.mean, l.invstd)
-            L.bn_relu_apply(l.z, l.scale, l.shift, l.a, l.pooled)
+            L.bn_relu_apply(l.z, l.scale, l.shift, l.a, l.pooled, l.pool_idx)
 
         for lvl in range(5):
             conv_bn(self.enc[lvl][0])
@@ -352,7 +354,8 @@ class UNetPlan:
 
         def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
             L.LABEL = l.name
-            L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias])
+            L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias],
+                          pool_idx=l.pool_idx if dpool is not None else None)
             if l.first:
                 L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo, algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout)
             else:

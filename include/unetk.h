@@ -154,12 +154,14 @@ typedef struct unetk_bn_finalize_args {
 } unetk_bn_finalize_args;
 int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream);
 
-/* a = relu(z*scale+shift); optionally pooled = maxpool2x2(a) in the same pass (pooled->ptr may be NULL) */
+/* a = relu(z*scale+shift); optionally pooled = maxpool2x2(a) in the same pass (pooled->ptr may be NULL).
+ * pool_idx (optional, [N,H/2,W/2,C/8] uint16): 2 bits per channel = window position (2*dy+dx) of the FIRST maximum in
+ * scan order -- what torch's max_pool2d backward routes the gradient to; consumed by unetk_bn_relu_bwd_*.            */
 int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift,
-                        const unetk_tensor* a, const unetk_tensor* pooled, void* stream);
+                        const unetk_tensor* a, const unetk_tensor* pooled, uint16_t* pool_idx, void* stream);
 
 /* Backward of (BN train -> ReLU [-> MaxPool]):
- *   dy = dA * [a > 0],  dA = dy_full (optional) + route(dpool) (optional; first max in scan order)
+ *   dy = dA * [a > 0],  dA = dy_full (optional) + route(dpool) (optional; to the position stored in pool_idx)
  *   reduce: sums[0][c] += sum dy, sums[1][c] += sum dy * xhat
  *   apply : dz = scale * (dy - s1/M - xhat * s2/M);  dgamma = s2, dbeta = s1                   */
 typedef struct unetk_bn_bwd_args {
@@ -174,6 +176,7 @@ typedef struct unetk_bn_bwd_args {
   unetk_tensor dz;
   float* dgamma;
   float* dbeta;
+  const void* pool_idx; /* uint16 [N,H/2,W/2,C/8] from unetk_bn_relu_apply; required when dpool is given */
 } unetk_bn_bwd_args;
 int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream);
 int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream);

@@ -178,7 +178,8 @@ def test_bn_relu_pool_forward_backward(dt, pool, n, h, w, c):
     cat = torch.zeros((n, h, w, 2 * c), dtype=dt, device=DEV)
     ad = cat[..., :c]
     pooled = torch.empty((n, h // 2, w // 2, c), dtype=dt, device=DEV) if pool else None
-    L.bn_relu_apply(zd, scale, shift, ad, pooled)
+    pidx = torch.empty((n, h // 2, w // 2, c // 8), dtype=torch.int16, device=DEV) if pool else None
+    L.bn_relu_apply(zd, scale, shift, ad, pooled, pidx)
     assert relerr(ad, a.detach().permute(0, 2, 3, 1)) < TOL[dt]
     assert int(nbt) == 1
     assert relerr(rmd, rm) < 1e-5 and relerr(rvd, rv) < 1e-5
@@ -198,7 +199,8 @@ def test_bn_relu_pool_forward_backward(dt, pool, n, h, w, c):
     sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
     dz = torch.empty((n, h, w, c), dtype=dt, device=DEV)
     dgamma, dbeta = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
-    L.bn_relu_bwd(zd, dy.to(DEV), dp.to(DEV) if pool else None, scale, shift, mean, invstd, sums, dz, dgamma, dbeta)
+    L.bn_relu_bwd(zd, dy.to(DEV), dp.to(DEV) if pool else None, scale, shift, mean, invstd, sums, dz, dgamma, dbeta,
+                  pool_idx=pidx)
     ref_dz = zr.grad.permute(0, 2, 3, 1)
     # ReLU-mask decisions are taken on the stored (dt-rounded) activation: identical to the reference when a_q > 0 <=> a > 0
     assert torch.equal(a_q > 0, a.detach() > 0)
