@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(kThreads)
   const int hh = POOL ? h / 2 : h, ww = POOL ? w / 2 : w;
   const int64_t total = (int64_t)n * hh * ww * cg;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    int64_t p = i / cg;
+    const int g = (int)((uint32_t)i % (uint32_t)cg);
+    int64_t p = (int64_t)((uint32_t)i / (uint32_t)cg);
     float sc[8], sh[8];
     load8(scale + g * 8, sc);
     load8(shift + g * 8, sh);
@@ -123,10 +123,12 @@ __global__ void __launch_bounds__(kThreads)
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
       store8(a + p * ald + g * 8, v);
     } else {
-      const int x = (int)(p % ww);
-      p /= ww;
-      const int y = (int)(p % hh);
-      const int img = (int)(p / hh);
+      const uint32_t p32 = (uint32_t)p, uww = (uint32_t)ww, uhh = (uint32_t)hh;
+      const uint32_t line = p32 / uww;
+      const int x = (int)(p32 - line * uww);
+      const uint32_t img_u = line / uhh;
+      const int y = (int)(line - img_u * uhh);
+      const int img = (int)img_u;
       float mx[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) mx[k] = -1.f;  // ReLU output is >= 0: position 0 always wins the first comparison
@@ -181,11 +183,12 @@ __device__ __forceinline__ void load_pixel(const BwdSrc<T>& s, int64_t pix, int 
     for (int k = 0; k < 8; ++k) d[k] = 0.f;
   }
   if (POOL) {
-    const int x = (int)(pix % s.w);
-    const int y = (int)((pix / s.w) % s.h);
-    const int64_t img = pix / ((int64_t)s.w * s.h);
-    const int64_t win = (img * (s.h >> 1) + (y >> 1)) * (s.w >> 1) + (x >> 1);
-    const uint32_t q = (uint32_t)((y & 1) * 2 + (x & 1));
+    // 32-bit index arithmetic (the host checks pixels < 2^31): 64-bit div/mod made this path compute bound
+    const uint32_t p32 = (uint32_t)pix, uw = (uint32_t)s.w, uh = (uint32_t)s.h;
+    const uint32_t line = p32 / uw, x = p32 - line * uw;
+    const uint32_t img = line / uh, y = line - img * uh;
+    const int64_t win = ((int64_t)(img * (uh >> 1) + (y >> 1))) * (uw >> 1) + (x >> 1);
+    const uint32_t q = (y & 1u) * 2u + (x & 1u);
     const uint32_t arg = s.pidx[win * s.cg + g];
     float dp[8];
     load8(s.dp + win * s.dpld + g * 8, dp);
@@ -199,6 +202,42 @@ __device__ __forceinline__ void load_pixel(const BwdSrc<T>& s, int64_t pix, int 
   }
 }
 
+// POOL: two horizontally adjacent pixels (2*xp, 2*xp+1) of one pooling window share the window's pooled gradient and
+// arg-max word: one index decode, one dpool load and one idx load per pair.
+template <typename T>
+__device__ __forceinline__ void load_pixel_pair(const BwdSrc<T>& s, int64_t pair, int g, const float (&sc)[8],
+                                                const float (&sh)[8], int64_t& pix0, float (&za)[8], float (&ya)[8],
+                                                float (&zb)[8], float (&yb)[8]) {
+  const uint32_t p32 = (uint32_t)pair, hw2 = (uint32_t)s.w >> 1, uh = (uint32_t)s.h;
+  const uint32_t line = p32 / hw2, xp = p32 - line * hw2;
+  const uint32_t img = line / uh, y = line - img * uh;
+  pix0 = (int64_t)line * s.w + 2 * xp;
+  const int64_t win = ((int64_t)(img * (uh >> 1) + (y >> 1))) * hw2 + xp;
+  const uint32_t q0 = (y & 1u) * 2u;
+  const uint32_t arg = s.pidx[win * s.cg + g];
+  float dp[8], da[8], db[8];
+  load8(s.dp + win * s.dpld + g * 8, dp);
+  load8(s.z + pix0 * s.zld + g * 8, za);
+  load8(s.z + (pix0 + 1) * s.zld + g * 8, zb);
+  if (s.dy) {
+    load8(s.dy + pix0 * s.dyld + g * 8, da);
+    load8(s.dy + (pix0 + 1) * s.dyld + g * 8, db);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) da[k] = db[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t a = (arg >> (2 * k)) & 3u;
+    const float ga = da[k] + (a == q0 ? dp[k] : 0.f);
+    const float gb = db[k] + (a == q0 + 1u ? dp[k] : 0.f);
+    const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
+    const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
+    ya[k] = aa > 0.f ? ga : 0.f;
+    yb[k] = ab > 0.f ? gb : 0.f;
+  }
+}
+
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(kThreads, 3)
     bn_bwd_reduce_kernel(BwdSrc<T> s, int cgb, int items_per_block, double* __restrict__ s1, double* __restrict__ s2) {
@@ -206,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 3)
   const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
   const int cg0 = blockIdx.x * cgb;
   const int g = cg0 + lane_g;
-  const int64_t nitems = (int64_t)s.n * s.h * s.w;
+  const int64_t nitems = (int64_t)s.n * s.h * s.w / (POOL ? 2 : 1);
   const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
   const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
   float sc[8], sh[8];
@@ -217,24 +256,38 @@ __global__ void __launch_bounds__(kThreads, 3)
   float acc[2][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
-  int64_t it = i0 + row;
-  for (; it + rows < i1; it += 2 * rows) {   // two pixels per iteration: more independent loads in flight
-    float za[8], ya[8], zb[8], yb[8];
-    load_pixel<T, POOL>(s, it, g, sc, sh, za, ya);
-    load_pixel<T, POOL>(s, it + rows, g, sc, sh, zb, yb);
+  if (POOL) {
+    // items are horizontal pixel pairs
+    for (int64_t it = i0 + row; it < i1; it += rows) {
+      float za[8], ya[8], zb[8], yb[8];
+      int64_t pix0;
+      load_pixel_pair<T>(s, it, g, sc, sh, pix0, za, ya, zb, yb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[0][k] += ya[k] + yb[k];
-      acc[1][k] = fmaf(ya[k], za[k], fmaf(yb[k], zb[k], acc[1][k]));
+      for (int k = 0; k < 8; ++k) {
+        acc[0][k] += ya[k] + yb[k];
+        acc[1][k] = fmaf(ya[k], za[k], fmaf(yb[k], zb[k], acc[1][k]));
+      }
     }
-  }
-  for (; it < i1; it += rows) {
-    float zv[8], dy[8];
-    load_pixel<T, POOL>(s, it, g, sc, sh, zv, dy);
+  } else {
+    int64_t it = i0 + row;
+    for (; it + rows < i1; it += 2 * rows) {   // two pixels per iteration: more independent loads in flight
+      float za[8], ya[8], zb[8], yb[8];
+      load_pixel<T, false>(s, it, g, sc, sh, za, ya);
+      load_pixel<T, false>(s, it + rows, g, sc, sh, zb, yb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[0][k] += dy[k];
-      acc[1][k] = fmaf(dy[k], zv[k], acc[1][k]);
+      for (int k = 0; k < 8; ++k) {
+        acc[0][k] += ya[k] + yb[k];
+        acc[1][k] = fmaf(ya[k], za[k], fmaf(yb[k], zb[k], acc[1][k]));
+      }
+    }
+    for (; it < i1; it += rows) {
+      float zv[8], dy[8];
+      load_pixel<T, false>(s, it, g, sc, sh, zv, dy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[0][k] += dy[k];
+        acc[1][k] = fmaf(dy[k], zv[k], acc[1][k]);
+      }
     }
   }
   {
@@ -259,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 3)
   const int rows = kThreads / cgb;
   const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
   const int g = blockIdx.x * cgb + lane_g;
-  const int64_t nitems = (int64_t)s.n * s.h * s.w;
+  const int64_t nitems = (int64_t)s.n * s.h * s.w / (POOL ? 2 : 1);
   const int64_t i0 = (int64_t)blockIdx.y * items_per_block;
   const int64_t i1 = min(i0 + (int64_t)items_per_block, nitems);
   float sc[8], sh[8], cb[8], cc[8];
@@ -284,25 +337,40 @@ __global__ void __launch_bounds__(kThreads, 3)
       if (dbeta) dbeta[g * 8 + k] = (float)s1[g * 8 + k];
     }
   }
-  int64_t it = i0 + row;
-  for (; it + rows < i1; it += 2 * rows) {
-    float za[8], ya[8], zb[8], yb[8], oa[8], ob[8];
-    load_pixel<T, POOL>(s, it, g, sc, sh, za, ya);
-    load_pixel<T, POOL>(s, it + rows, g, sc, sh, zb, yb);
+  if (POOL) {
+    for (int64_t it = i0 + row; it < i1; it += rows) {
+      float za[8], ya[8], zb[8], yb[8], oa[8], ob[8];
+      int64_t pix0;
+      load_pixel_pair<T>(s, it, g, sc, sh, pix0, za, ya, zb, yb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      oa[k] = fmaf(sc[k], ya[k], fmaf(cb[k], za[k], cc[k]));
-      ob[k] = fmaf(sc[k], yb[k], fmaf(cb[k], zb[k], cc[k]));
+      for (int k = 0; k < 8; ++k) {
+        oa[k] = fmaf(sc[k], ya[k], fmaf(cb[k], za[k], cc[k]));
+        ob[k] = fmaf(sc[k], yb[k], fmaf(cb[k], zb[k], cc[k]));
+      }
+      store8(dz + pix0 * dzld + g * 8, oa);
+      store8(dz + (pix0 + 1) * dzld + g * 8, ob);
     }
-    store8(dz + it * dzld + g * 8, oa);
-    store8(dz + (it + rows) * dzld + g * 8, ob);
-  }
-  for (; it < i1; it += rows) {
-    float zv[8], dy[8], o[8];
-    load_pixel<T, POOL>(s, it, g, sc, sh, zv, dy);
+  } else {
+    int64_t it = i0 + row;
+    for (; it + rows < i1; it += 2 * rows) {
+      float za[8], ya[8], zb[8], yb[8], oa[8], ob[8];
+      load_pixel<T, false>(s, it, g, sc, sh, za, ya);
+      load_pixel<T, false>(s, it + rows, g, sc, sh, zb, yb);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], dy[k], fmaf(cb[k], zv[k], cc[k]));
-    store8(dz + it * dzld + g * 8, o);
+      for (int k = 0; k < 8; ++k) {
+        oa[k] = fmaf(sc[k], ya[k], fmaf(cb[k], za[k], cc[k]));
+        ob[k] = fmaf(sc[k], yb[k], fmaf(cb[k], zb[k], cc[k]));
+      }
+      store8(dz + it * dzld + g * 8, oa);
+      store8(dz + (it + rows) * dzld + g * 8, ob);
+    }
+    for (; it < i1; it += rows) {
+      float zv[8], dy[8], o[8];
+      load_pixel<T, false>(s, it, g, sc, sh, zv, dy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(sc[k], dy[k], fmaf(cb[k], zv[k], cc[k]));
+      store8(dz + it * dzld + g * 8, o);
+    }
   }
 }
 
@@ -339,6 +407,7 @@ static int check_bwd(const unetk_bn_bwd_args* a) {
     UNETK_REQUIRE(a->pool_idx != nullptr, "bn_bwd: dpool needs the pool_idx written by unetk_bn_relu_apply");
   }
   UNETK_REQUIRE(a->scale && a->shift && a->mean && a->invstd && a->sums, "bn_bwd: null statistics");
+  UNETK_REQUIRE(pixels(a->z) < (1LL << 31), "bn_bwd: more than 2^31 pixels");
   return UNETK_OK;
 }
 
@@ -392,6 +461,7 @@ int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* 
   }
   const int cg = z->c / 8;
   const int64_t items = pixels(*z) / (pool ? 4 : 1) * cg;
+  UNETK_REQUIRE(items < (1LL << 32), "bn_relu_apply: tensor too large");
   const int grid = grid_for(items);
   UNETK_DISPATCH_DTYPE(z->dtype, T, {
     if (pool)
@@ -410,8 +480,8 @@ int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream) {
   if (rc) return rc;
   const bool pool = a->dpool.ptr != nullptr;
   const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
-  const int64_t nitems = pixels(a->z);
-  int ipb = rows * 32;
+  const int64_t nitems = pixels(a->z) / (pool ? 2 : 1);
+  int ipb = rows * (pool ? 16 : 32);
   if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
   UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_reduce: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));
@@ -437,8 +507,8 @@ int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream) {
   const bool pool = a->dpool.ptr != nullptr;
   UNETK_REQUIRE(pool || a->dy.ptr, "bn_bwd_apply: dy required without dpool");
   const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
-  const int64_t nitems = pixels(a->z);
-  int ipb = rows * 16;
+  const int64_t nitems = pixels(a->z) / (pool ? 2 : 1);
+  int ipb = rows * (pool ? 8 : 16);
   if ((nitems + ipb - 1) / ipb > 65535) ipb *= 16;
   UNETK_REQUIRE((nitems + ipb - 1) / ipb <= 65535, "bn_bwd_apply: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((nitems + ipb - 1) / ipb));
