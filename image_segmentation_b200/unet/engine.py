@@ -186,6 +186,9 @@ class UNetPlan:
             ct.wd = torch.empty((ct.cin, 4, ct.cout), dtype=dt, device=dev)
 
         self._bwd_ready = False
+        # weight gradients run on a side stream: tensor-bound wgrad kernels overlap the HBM-bound BatchNorm backward
+        # passes of the next layer (set UNETK_WGRAD_STREAM=0 to serialise everything on the caller's stream)
+        self.side_stream = torch.cuda.Stream(device=dev) if os.environ.get("UNETK_WGRAD_STREAM", "1") == "1" else None
 
     # ------------------------------------------------------------------------------------------
     def _build_backward(self):
@@ -352,15 +355,35 @@ class UNetPlan:
         if bucket_hook:
             bucket_hook(self, self.grad_offsets[2])
 
+        main = torch.cuda.current_stream()
+        # per-launch instrumentation (bench.py / tools) needs un-overlapped kernels for meaningful event durations
+        side = self.side_stream if L.PROFILE_HOOK is None else None
+
+        def on_side(fn):
+            """Run `fn` (weight-gradient launches) on the side stream, ordered after everything enqueued so far."""
+            if side is None:
+                fn()
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn()
+
+        def join_side():
+            if side is not None:
+                main.wait_stream(side)
+
         def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
             L.LABEL = l.name
             L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias],
                           pool_idx=l.pool_idx if dpool is not None else None)
             if l.first:
-                L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo, algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout)
+                on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo,
+                                        algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout))
             else:
-                L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo)
+                # data gradient first on the main stream (the next layer's BatchNorm backward waits for it) ...
                 L.conv(l.dz, l.wd, l.g_in, L.MODE_3X3, algo=self.algo)
+                # ... weight gradient on the side stream
+                on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo))
             # conv bias in front of train-mode BN: its gradient is identically zero (flat buffer is zeroed)
 
         grad_a2 = self.g_head_in
@@ -373,11 +396,15 @@ class UNetPlan:
             conv_bn_bwd(l1, l2.g_in)
             ct = self.convts[i]
             L.LABEL = ct.name
-            L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
-            L.channel_sum(ct.g_out, g[ct.mod.bias])
             L.conv(ct.g_out, ct.wd, ct.g_in, L.MODE_CONVT_GATHER, algo=self.algo)
+
+            def ct_grads(ct=ct):
+                L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
+                L.channel_sum(ct.g_out, g[ct.mod.bias])
+            on_side(ct_grads)
             grad_a2 = ct.g_in
             pos += 10
+            join_side()
             L.weights_unpack(self._unpack_jobs[seg], flat)
             seg += 1
             if bucket_hook:
@@ -390,6 +417,7 @@ class UNetPlan:
                 conv_bn_bwd(l2, self.dcat[lvl][..., :ENC_CH[lvl]], dpool=self.enc[lvl + 1][0].g_in)
             conv_bn_bwd(l1, l2.g_in)
             pos += 8
+            join_side()
             L.weights_unpack(self._unpack_jobs[seg], flat)
             seg += 1
             if bucket_hook:
