@@ -246,3 +246,37 @@ def test_forward_metrics_pipeline_matches_oracle():
         tot += np.stack(metrics_oracle.confusion_counts(logits[i].cpu().numpy(), y[i].numpy(), 4))
     got = np.stack([agg.total_tp.numpy(), agg.total_fp.numpy(), agg.total_fn.numpy(), agg.total_tn.numpy()]).astype(np.int64)
     np.testing.assert_array_equal(got, tot)
+
+
+def test_non_power_of_two_resolution_bf16_tc_vs_fp32_tier():
+    """48x80 input (levels 48x80 .. 3x5): partial tiles, halo kernels with clipped boxes, odd level sizes."""
+    x, y = make_batch(3, 48, 80, 3, 4, seed=21)
+    res = {}
+    for precision in ("fp32", "bf16"):
+        m = build(3, 4, precision)
+        logits = m(x.to(DEV))
+        loss = loss_for(4)(logits, y.squeeze(1).to(DEV))
+        loss.backward()
+        res[precision] = (logits.detach(), loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    # fp32 tier against the CPU oracle (fp64)
+    torch.manual_seed(0)
+    sd = unet_oracle.init_state_dict(3, 4)
+    w = torch.tensor(CLASS_W4, dtype=torch.float64)
+    ref_loss, ref_logits, ref_grads, _ = unet_oracle.loss_and_grads(
+        sd, x, y.squeeze(1), lambda lg, t: loss_oracle.dice_ce_loss(lg, t, smooth_dice=1.0, class_weights=w), dtype=torch.float64)
+    assert rel_max(res["fp32"][0], ref_logits) < 1e-4
+    assert abs(res["fp32"][1] - ref_loss.item()) < 1e-4
+    for k in ("output.weight", "up4.upsample.weight", "down1.doubleConvReLU.0.weight", "up1.doubleConv.doubleConvReLU.3.weight"):
+        assert rel_l2(res["fp32"][2][k], ref_grads[k]) < 5e-3, k
+    e = rel_l2(res["bf16"][0], ref_logits)
+    print("48x80 bf16 logits rel-L2 vs fp64 oracle:", e)
+    assert e < 5e-2
+
+
+def test_batch_of_one_and_repeatability():
+    x, y = make_batch(1, 64, 64, 3, 3, seed=4)
+    m = build(3, 3, "bf16")
+    a = m(x.to(DEV)).detach().clone()
+    b = m(x.to(DEV)).detach().clone()
+    # fp64 statistic atomics can reorder; everything else in the forward pass is deterministic
+    assert rel_max(a, b) < 1e-5
