@@ -178,7 +178,8 @@ def run_gpu_arm(args):
     model.precision = "bf16"
     model = model.to(dev).train()
     dp = DataParallelUNet(model) if world > 1 else None
-    opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01, fused=True)   # same update rule, one fused kernel
+    # same update rule as the reference's AdamW; fused = one kernel, capturable = usable inside a CUDA graph
+    opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01, fused=True, capturable=True)
     loss_fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor(CLASS_W3))
     agg = MetricsHistory(3)
     x_cpu, y_cpu = make_batch(B, H, W, 3, 3, seed=1234 + rank)
@@ -229,12 +230,29 @@ def run_gpu_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # single GPU: the whole step replays as ONE CUDA graph (image_segmentation_b200.utils.graph); data parallel: eager
+    graphed = None
+    if world == 1 and not args.no_graph:
+        from image_segmentation_b200.utils.graph import GraphedTrainStep
+        try:
+            L.COUNTERS["launches"] = 0
+            graphed = GraphedTrainStep(model, loss_fn, opt, x_dev, y_dev, metrics=agg, warmup=1)
+            launches_per_step = L.COUNTERS["launches"] // 2      # 1 warm-up step + 1 captured step
+        except Exception as e:   # report and measure the eager path instead
+            print(f"[bench] CUDA graph capture failed, timing the eager path: {e!r}", file=sys.stderr)
+            graphed = None
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    L.COUNTERS["launches"] = 0
-    ms = timed(step_resident, args.steps)
-    launches = L.COUNTERS["launches"]
+    if graphed is not None:
+        for _ in range(3):
+            graphed(x_dev, y_dev)
+        ms = timed(lambda: graphed(x_dev, y_dev), args.steps)
+        launches = launches_per_step * args.steps
+    else:
+        L.COUNTERS["launches"] = 0
+        ms = timed(step_resident, args.steps)
+        launches = L.COUNTERS["launches"]
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
@@ -302,6 +320,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"unet(3,3) 256x256 training step, batch {B}/GPU, bf16 activations + fp32 master weights, "
                                    "WeightedDiceCELoss + AdamW + MetricsHistory",
                        "global_batch": B * world, "parallelism": f"dp{world}",
+                       "launch": "one CUDA graph per step" if graphed is not None else "eager launches",
                        "l2": "per-step working set ~20 GB >> 126 MB L2 (no flush needed)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel(),
@@ -323,6 +342,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

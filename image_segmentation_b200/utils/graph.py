@@ -1,0 +1,73 @@
+"""CUDA-graph replay of one whole training step (forward + loss + backward + optimizer + metrics).
+
+One U-Net step is ~160 kernel launches; captured once into a CUDA graph they replay without any host work or
+launch gaps.  Everything launched through the C ABI is capturable: kernels are enqueued on torch's current
+stream (the capture stream), tensor maps travel by value inside kernel parameters, and every scratch tensor
+comes from the graph's private memory pool, so addresses are stable across replays.
+
+    step = GraphedTrainStep(model, loss_fn, optimizer, X_example, y_example, metrics=agg)
+    for X, y in loader:                       # X [N,3,H,W] fp32, y [N,H,W] or [N,1,H,W] integer labels
+        loss = step(X, y)                     # device scalar; call loss.item() only when a value is needed
+
+Constraints: fixed batch shape; the optimizer must be capturable (e.g. ``torch.optim.AdamW(..., fused=True)``
+or ``capturable=True``); single process (data parallelism uses the eager path).  This is an addition for
+throughput; the reference-compatible ``train_loop`` keeps working without it.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, loss_fn, optimizer, example_x: torch.Tensor, example_y: torch.Tensor, metrics=None,
+                 warmup: int = 3):
+        params = list(model.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
+        self.model, self.loss_fn, self.optimizer, self.metrics = model, loss_fn, optimizer, metrics
+        self.x = example_x.to(dev, dtype=torch.float32).contiguous().clone()
+        y = example_y.to(dev)
+        if y.dim() == 4:
+            y = y[:, 0]
+        self.y = y.long().contiguous().clone()
+        self.loss = None
+        model.train()
+        # warm-up on a side stream (allocator pools, cudaFuncSetAttribute, optimizer state) as torch recommends
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager_step()
+        torch.cuda.synchronize(dev)
+
+    def _eager_step(self):
+        pred = self.model(self.x)
+        loss = self.loss_fn(pred, self.y)
+        loss.backward()
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        if self.metrics is not None:
+            self.metrics.accumulate(pred.detach(), self.y)
+        return loss.detach()
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x, non_blocking=True)
+        if y.dim() == 4:
+            y = y[:, 0]
+        self.y.copy_(y, non_blocking=True)
+        self.graph.replay()
+        # parameters were updated inside the graph without bumping their version counters: force the next EAGER
+        # forward (e.g. evaluation) to re-pack the operand copies of the weights
+        eng = getattr(self.model, "_engine", None)
+        if eng is not None:
+            for pool in eng.plans.values():
+                for plan in pool:
+                    plan._pack_versions = None
+        return self.loss

@@ -99,10 +99,17 @@ class _FusedLossBase(nn.Module):
         if not hasattr(self, "_status") or self._status.dev.device != dev:
             self._status = _Status(dev)
         strict = os.environ.get("UNETK_STRICT_LABELS", "0") == "1"
-        self._status.check(False, type(self).__name__)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._status.check(False, type(self).__name__)
         cw = None
         if class_weights is not None:
-            cw = class_weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+            # device copy of the class weights, cached (a per-call H2D copy would stall the stream and break graph capture)
+            key = (id(class_weights), class_weights._version, str(dev))
+            if getattr(self, "_cw_key", None) != key:
+                self._cw_dev = class_weights.detach().to(device=dev, dtype=torch.float32).contiguous()
+                self._cw_key = key
+            cw = self._cw_dev
             if cw.numel() != c:
                 raise RuntimeError(f"weight tensor should be defined for all {c} classes, got {cw.numel()}")
         if ignore_index is not None and not (-2 ** 62 < int(ignore_index) < 2 ** 62):
@@ -114,9 +121,10 @@ class _FusedLossBase(nn.Module):
         tg = target if (target.dtype == torch.int64 and target.is_contiguous()) else target.long().contiguous()
         with torch.cuda.device(dev):
             loss = _DiceCEFunction.apply(lg, tg, cfg)
-            self._status.publish()
-            if strict:
-                self._status.check(True, type(self).__name__)
+            if not capturing:
+                self._status.publish()
+                if strict:
+                    self._status.check(True, type(self).__name__)
         return loss
 
 

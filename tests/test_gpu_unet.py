@@ -280,3 +280,43 @@ def test_batch_of_one_and_repeatability():
     b = m(x.to(DEV)).detach().clone()
     # fp64 statistic atomics can reorder; everything else in the forward pass is deterministic
     assert rel_max(a, b) < 1e-5
+
+
+def test_cuda_graph_step_matches_eager_training():
+    """GraphedTrainStep (one CUDA graph per step) follows the same loss trajectory as eager stepping."""
+    from image_segmentation_b200.utils.graph import GraphedTrainStep
+    batches = [make_batch(2, 64, 64, 3, 3, seed=100 + i, labels="learnable") for i in range(4)]
+    curves = {}
+    for mode in ("eager", "graph"):
+        m = build(3, 3, "fp32")
+        opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01, fused=True, capturable=True)
+        fn = loss_for(3)
+        losses = []
+        if mode == "graph":
+            # warm-up steps inside GraphedTrainStep would advance the optimiser: use a throw-away copy of the state
+            state = {k: v.clone() for k, v in m.state_dict().items()}
+            step = GraphedTrainStep(m, fn, opt, batches[0][0], batches[0][1], warmup=1)
+            m.load_state_dict(state)
+            opt.state.clear() if False else None
+            for st in opt.state.values():
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        v.zero_()
+            for s in range(12):
+                x, y = batches[s % 4]
+                losses.append(step(x.to(DEV), y.to(DEV)).item())
+        else:
+            for s in range(12):
+                x, y = batches[s % 4]
+                opt.zero_grad()
+                loss = fn(m(x.to(DEV)), y.squeeze(1).to(DEV))
+                loss.backward()
+                opt.step()
+                losses.append(loss.item())
+        curves[mode] = np.array(losses)
+    d = np.abs(curves["eager"] - curves["graph"])
+    print("graph vs eager loss |delta| max", d.max(), curves["eager"][:4], curves["graph"][:4])
+    assert d[:4].max() < 2e-3
+    assert d.max() < 5e-2
+    # an eager forward after graph replays sees the updated weights (operand packs are refreshed)
+    m.eval()
