@@ -29,7 +29,9 @@ class Tensor(C.Structure):
 
 class ConvArgs(C.Structure):
     _fields_ = [("x", Tensor), ("w", C.c_void_p), ("y", Tensor), ("mode", C.c_int32), ("algo", C.c_int32),
-                ("bias", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p)]
+                ("bias", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p),
+                ("bn_z", Tensor), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("bn_mean", C.c_void_p),
+                ("bn_invstd", C.c_void_p), ("bn_sums", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -210,8 +212,16 @@ def weights_unpack(wj: "WeightJobs", dst_base: torch.Tensor):
          stream_ptr())
 
 
-def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None):
-    a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo, ptr(bias), ptr(stat_sum), ptr(stat_sumsq))
+def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None, bn_reduce=None):
+    """bn_reduce = (z, scale, shift, mean, invstd, sums): fuse the BatchNorm-backward reduction of the layer whose
+    activated-output gradient this launch produces (see unetk.h)."""
+    if bn_reduce is None:
+        bnz, bsc, bsh, bmu, bis, bsum = nhwc(None), None, None, None, None, None
+    else:
+        bnz = nhwc(bn_reduce[0])
+        bsc, bsh, bmu, bis, bsum = (t.data_ptr() for t in bn_reduce[1:])
+    a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo, ptr(bias), ptr(stat_sum), ptr(stat_sumsq),
+                 bnz, bsc, bsh, bmu, bis, bsum)
     if algo_flops is None:
         if mode in (MODE_1X1, MODE_3X3):
             algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * (9 if mode == MODE_3X3 else 1) * x.shape[3] * y.shape[3]
@@ -252,11 +262,13 @@ def bn_relu_apply(z, scale, shift, a, pooled=None, pool_idx=None):
          C.byref(nhwc(a)), C.byref(nhwc(pooled)), ptr(pool_idx), stream_ptr())
 
 
-def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx=None):
+def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx=None, reduced=False):
+    """reduced=True: `sums` were already accumulated by the producing unetk_conv launch (bn_reduce=...)."""
     a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
                   ptr(dgamma), ptr(dbeta), ptr(pool_idx))
     s = stream_ptr()
-    _run("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, C.byref(a), s)
+    if not reduced:
+        _run("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, C.byref(a), s)
     _run("bn_bwd_apply", 1, 0, lib().unetk_bn_relu_bwd_apply, C.byref(a), s)
 
 

@@ -1,5 +1,7 @@
 // unetk_conv / unetk_wgrad / unetk_channel_sum: argument validation and dispatch between the fp32 parity tier
 // (CUDA-core kernels) and the bf16 throughput tier (TMA + tcgen05 kernels).  There is no CPU path.
+#include <string.h>
+
 #include "conv_internal.cuh"
 
 namespace unetk {
@@ -63,6 +65,13 @@ int unetk_conv(const unetk_conv_args* a, void* stream) {
   }
   UNETK_REQUIRE((a->stat_sum == nullptr) == (a->stat_sumsq == nullptr), "conv: stat_sum and stat_sumsq come together");
   UNETK_REQUIRE(!(a->stat_sum && a->mode >= 2), "conv: statistics only for modes 0/1");
+  const bool bnred = a->bn_z.ptr != nullptr;
+  if (bnred) {
+    UNETK_REQUIRE(a->mode != 2, "conv: fused BatchNorm-backward reduction is for data-gradient launches (modes 0/1/3)");
+    UNETK_REQUIRE(tensor_ok(a->bn_z) && a->bn_z.dtype == a->y.dtype && a->bn_z.n == a->y.n && a->bn_z.h == a->y.h &&
+                      a->bn_z.w == a->y.w && a->bn_z.c == a->y.c, "conv: bn_z must have the shape and dtype of y");
+    UNETK_REQUIRE(a->bn_scale && a->bn_shift && a->bn_mean && a->bn_invstd && a->bn_sums, "conv: bn_* pointers missing");
+  }
 
   int algo = a->algo;
   if (algo == UNETK_ALGO_AUTO) algo = a->x.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
@@ -77,7 +86,17 @@ int unetk_conv(const unetk_conv_args* a, void* stream) {
   UNETK_REQUIRE(algo == UNETK_ALGO_SIMT, "conv: unknown algo %d", algo);
   int rc = simt_conv(a, g, (cudaStream_t)stream);
   if (rc) return rc;
-  if (a->stat_sum) return unetk_bn_stats(&a->y, a->stat_sum, a->stat_sumsq, stream);
+  if (a->stat_sum && (rc = unetk_bn_stats(&a->y, a->stat_sum, a->stat_sumsq, stream))) return rc;
+  if (bnred) {
+    // CUDA-core tier: same contract, realised with the stand-alone reduction kernel
+    unetk_bn_bwd_args b;
+    memset(&b, 0, sizeof(b));
+    b.z = a->bn_z;
+    b.dy = a->y;
+    b.scale = a->bn_scale; b.shift = a->bn_shift; b.mean = a->bn_mean; b.invstd = a->bn_invstd;
+    b.sums = a->bn_sums;
+    return unetk_bn_relu_bwd_reduce(&b, stream);
+  }
   return UNETK_OK;
 }
 

@@ -141,10 +141,18 @@ struct ConvParams {
   int num_staging;      // 1 or 2 epilogue staging blocks
   uint32_t off_b, off_staging, off_stats, off_bars;
   int stat_channels;    // size of each statistics array in shared memory (0 = none)
+  // fused BatchNorm-backward reduction (data-gradient launches): y is dA of a conv+BN+ReLU layer whose raw output is z
+  CUtensorMap map_z;    // same tiling as map_y[0]
+  uint32_t off_zbuf;    // two 16 KiB blocks (one per epilogue group); 0 when unused
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_invstd;
+  double* bn_sums;      // [2][cout]
 };
 
 // barrier block: [fullA 8][emptyA 8][fullB 24][emptyB 24][tmem_full 2][tmem_empty 2] + tmem pointer
-constexpr int kBarBytes = (2 * kMaxAStages + 2 * kMaxBSlots + 4) * 8 + 16;
+constexpr int kBarBytes = (2 * kMaxAStages + 2 * kMaxBSlots + 6) * 8 + 16;
 
 struct Bars {
   uint64_t* full_a;
@@ -153,6 +161,7 @@ struct Bars {
   uint64_t* empty_b;
   uint64_t* tmem_full;
   uint64_t* tmem_empty;
+  uint64_t* zfull;   // z tile of the fused BatchNorm-backward reduction, one per epilogue group
   uint32_t* tmem_ptr;
   __device__ explicit Bars(uint8_t* base) {
     full_a = reinterpret_cast<uint64_t*>(base);
@@ -161,7 +170,8 @@ struct Bars {
     empty_b = full_b + kMaxBSlots;
     tmem_full = empty_b + kMaxBSlots;
     tmem_empty = tmem_full + 2;
-    tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    zfull = tmem_empty + 2;
+    tmem_ptr = reinterpret_cast<uint32_t*>(zfull + 2);
   }
 };
 
@@ -183,10 +193,19 @@ struct StatRegs {
 #pragma unroll
     for (int i = 0; i < BLOCK_N / 64; ++i) {
       const int ch = n_tile * BLOCK_N + i * 64 + 2 * lane;
-      atomicAdd(p.stat_sum + ch, (double)v[i][0]);
-      atomicAdd(p.stat_sum + ch + 1, (double)v[i][1]);
-      atomicAdd(p.stat_sumsq + ch, (double)v[i][2]);
-      atomicAdd(p.stat_sumsq + ch + 1, (double)v[i][3]);
+      if (p.bn_sums) {
+        // v = {sum dy (ch), sum dy (ch+1), sum dy*z (ch), sum dy*z (ch+1)}; xhat = (z - mean) * invstd
+        const float m0 = p.bn_mean[ch], m1 = p.bn_mean[ch + 1], i0 = p.bn_invstd[ch], i1 = p.bn_invstd[ch + 1];
+        atomicAdd(p.bn_sums + ch, (double)v[i][0]);
+        atomicAdd(p.bn_sums + ch + 1, (double)v[i][1]);
+        atomicAdd(p.bn_sums + p.cout + ch, (double)(i0 * (v[i][2] - m0 * v[i][0])));
+        atomicAdd(p.bn_sums + p.cout + ch + 1, (double)(i1 * (v[i][3] - m1 * v[i][1])));
+      } else {
+        atomicAdd(p.stat_sum + ch, (double)v[i][0]);
+        atomicAdd(p.stat_sum + ch + 1, (double)v[i][1]);
+        atomicAdd(p.stat_sumsq + ch, (double)v[i][2]);
+        atomicAdd(p.stat_sumsq + ch + 1, (double)v[i][3]);
+      }
     }
     clear();
   }
@@ -195,10 +214,12 @@ struct StatRegs {
 template <int BLOCK_N, bool HAS_BIAS, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* staging, int bar_id, uint32_t tmem_acc, int q,
                                               int lane, bool valid_row, int n_tile, int w0, int h0, int n0,
-                                              StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar) {
+                                              StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar, uint8_t* zbuf = nullptr,
+                                              uint64_t* zbar = nullptr, uint32_t* zphase = nullptr) {
   const int row = q * 32 + lane;
   const bool storer = (q == 0 && lane == 0);
-  const bool do_stats = p.stat_sum != nullptr;
+  const bool bnred = p.bn_sums != nullptr;
+  const bool do_stats = p.stat_sum != nullptr || bnred;
   const int col0 = n_tile * BLOCK_N;
   int map_idx = 0, ch0 = col0;
   if (p.mode == 2) {
@@ -215,6 +236,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
   for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
     if (storer) tma_store_wait_read<0>();   // the previous store out of this staging block has been read
     named_bar_sync(bar_id, 128);
+    if (bnred && storer) {
+      // z tile of the layer whose gradient this is (same pixels / channels as the output block), 128B-swizzled like staging
+      mbar_arrive_expect_tx(zbar, kStagingBytes);
+      tma_load_4d(zbuf, &p.map_z, zbar, ch0 + blk * 64, w0, h0, n0);
+    }
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(tmem_acc + blk * 64, r0);
     tmem_ld_32x32(tmem_acc + blk * 64 + 32, r1);
@@ -257,14 +283,37 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
       float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
       const uint32_t base = sbase + (uint32_t)(lane & 3) * 4 + (uint32_t)(q * 32) * 128;
       const uint32_t cgrp = (uint32_t)lane >> 2;
+      if (bnred) {
+        // BatchNorm-backward reduction: dy = dA * [relu(z*scale+shift) > 0]; accumulate sum dy and sum dy*z
+        const int ch = ch0 + blk * 64 + 2 * lane;
+        const float sc0 = __ldg(p.bn_scale + ch), sc1 = __ldg(p.bn_scale + ch + 1);
+        const float sh0 = __ldg(p.bn_shift + ch), sh1 = __ldg(p.bn_shift + ch + 1);
+        const uint32_t zbase = smem_u32(zbuf) + (uint32_t)(lane & 3) * 4 + (uint32_t)(q * 32) * 128;
+        mbar_wait(zbar, *zphase);
+        *zphase ^= 1;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const uint32_t word = ld_shared_u32(base + i * 128 + ((cgrp ^ (uint32_t)(i & 7)) << 4));
-        const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
-        s1a += lo;
-        s1b += hi;
-        s2a = fmaf(lo, lo, s2a);
-        s2b = fmaf(hi, hi, s2b);
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t off = i * 128 + ((cgrp ^ (uint32_t)(i & 7)) << 4);
+          const uint32_t wd = ld_shared_u32(base + off), wz = ld_shared_u32(zbase + off);
+          const float dlo = __uint_as_float(wd << 16), dhi = __uint_as_float(wd & 0xffff0000u);
+          const float zlo = __uint_as_float(wz << 16), zhi = __uint_as_float(wz & 0xffff0000u);
+          const float ylo = fmaf(zlo, sc0, sh0) > 0.f ? dlo : 0.f;
+          const float yhi = fmaf(zhi, sc1, sh1) > 0.f ? dhi : 0.f;
+          s1a += ylo;
+          s1b += yhi;
+          s2a = fmaf(ylo, zlo, s2a);
+          s2b = fmaf(yhi, zhi, s2b);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t word = ld_shared_u32(base + i * 128 + ((cgrp ^ (uint32_t)(i & 7)) << 4));
+          const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
+          s1a += lo;
+          s1b += hi;
+          s2a = fmaf(lo, lo, s2a);
+          s2b = fmaf(hi, hi, s2b);
+        }
       }
       st.v[blk][0] += s1a;
       st.v[blk][1] += s1b;
@@ -295,6 +344,7 @@ __device__ __forceinline__ void init_common(const ConvParams& p, uint8_t* smem, 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.tmem_full[i], 1);
       mbar_init(&bars.tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&bars.zfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -393,6 +443,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     const int row = q * 32 + lane;
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -406,9 +458,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, HAS_BIAS>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
-                                       n_tile, w0, h0, n0, st, &bars.tmem_empty[g]);
+                                       n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
-    if (p.stat_sum) st.flush(p, lane);
+    if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
@@ -462,6 +514,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.tmem_full[i], 1);
       mbar_init(&bars.tmem_empty[i], 8);  // 4 epilogue warps of each CTA (used in the leader only)
+      mbar_init(&bars.zfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -545,6 +598,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     const int row = q * 32 + lane;
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -558,9 +613,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, HAS_BIAS, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
-                                             valid, n_tile, w0, h0, n0, st, &bars.tmem_empty[g]);
+                                             valid, n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
-    if (p.stat_sum) st.flush(p, lane);
+    if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
@@ -723,6 +778,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
     long long dbg_tf = 0, dbg_epi = 0;
     const long long dbg_start = clock64();
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -742,7 +799,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
       {
         DBG_T0();
         epilogue_tile<BLOCK_N, false>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
-                                      n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
+                                      n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
         DBG_ADD(dbg_epi);
       }
     }
@@ -751,7 +808,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
       g_dbg[blockIdx.x * 8 + 6] = dbg_epi;
       g_dbg[blockIdx.x * 8 + 7] = clock64() - dbg_start;
     }
-    if (p.stat_sum) st.flush(p, lane);
+    if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
@@ -803,6 +860,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.tmem_full[i], 1);
       mbar_init(&bars.tmem_empty[i], 8);
+      mbar_init(&bars.zfull[i], 1);
     }
     fence_barrier_init();
   }
@@ -913,6 +971,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     const int row = q * 32 + lane;
     const int pw_i = row & 7, ph_i = row >> 3;
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
+    uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -926,9 +986,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, false, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
-                                          valid, n_tile, w0, h0, tn, st, &bars.tmem_empty[g]);
+                                          valid, n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
-    if (p.stat_sum) st.flush(p, lane);
+    if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
   }
 
@@ -1395,6 +1455,11 @@ bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char**
     return false;
   }
   if (a->stat_sum && g.cout > 4096) { *why = "statistics support at most 4096 channels"; return false; }
+  if (a->bn_z.ptr && (a->bn_z.ld % 8 != 0 || (reinterpret_cast<uintptr_t>(a->bn_z.ptr) & 15) != 0)) {
+    *why = "bn_z must be 16B aligned with a pixel stride multiple of 8";
+    return false;
+  }
+  if (a->bn_z.ptr && a->stat_sum) { *why = "forward statistics and backward reduction are mutually exclusive"; return false; }
   return true;
 }
 
@@ -1471,8 +1536,14 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   p.stat_sum = a->stat_sum;
   p.stat_sumsq = a->stat_sumsq;
   p.stat_channels = 0;
-  // ---- shared-memory plan: operand ring(s) | 2 staging blocks (one per epilogue group) | barriers ----
-  const int budget = kMaxSmem - 1024 /*alignment slack*/ - kBarBytes - 2 * kStagingBytes;
+  const bool bnred = a->bn_z.ptr != nullptr;
+  if (bnred) {
+    if ((rc = make_act_map(&p.map_z, a->bn_z, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
+    p.bn_scale = a->bn_scale; p.bn_shift = a->bn_shift; p.bn_mean = a->bn_mean; p.bn_invstd = a->bn_invstd;
+    p.bn_sums = a->bn_sums;
+  }
+  // ---- shared-memory plan: operand ring(s) | 2 staging blocks (one per epilogue group) [| 2 z blocks] | barriers ----
+  const int budget = kMaxSmem - 1024 /*alignment slack*/ - kBarBytes - (bnred ? 4 : 2) * kStagingBytes;
   p.num_staging = 2;
   int ring_bytes;
   if (!halo) {
@@ -1500,7 +1571,8 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   }
   p.off_staging = ring_bytes;
   p.off_stats = 0;
-  p.off_bars = p.off_staging + 2 * kStagingBytes;
+  p.off_zbuf = p.off_staging + 2 * kStagingBytes;
+  p.off_bars = p.off_zbuf + (bnred ? 2 : 0) * kStagingBytes;
   const int smem_bytes = p.off_bars + kBarBytes + 1024;
   UNETK_REQUIRE(smem_bytes <= kMaxSmem && p.stages >= 2, "conv(tc): shared-memory plan failed (%d bytes, %d stages)", smem_bytes, p.stages);
   if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, pair, stream);

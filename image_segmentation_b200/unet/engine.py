@@ -373,16 +373,24 @@ class UNetPlan:
             if side is not None:
                 main.wait_stream(side)
 
-        def conv_bn_bwd(l: _ConvBN, dy, dpool=None):
+        fuse = os.environ.get("UNETK_FUSE_BN_REDUCE", "1") == "1"
+
+        def bn_red(l: _ConvBN):
+            """Arguments that make a data-gradient launch also accumulate layer l's BatchNorm-backward reductions."""
+            return (l.z, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums) if fuse else None
+
+        def conv_bn_bwd(l: _ConvBN, dy, dpool=None, reduced=False, feeds: Optional[_ConvBN] = None):
+            """`reduced`: this layer's reductions were already fused into the launch that produced `dy`;
+            `feeds`: the layer whose activated-output gradient this layer's dgrad produces (no pooling in between)."""
             L.LABEL = l.name
             L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias],
-                          pool_idx=l.pool_idx if dpool is not None else None)
+                          pool_idx=l.pool_idx if dpool is not None else None, reduced=reduced and fuse)
             if l.first:
                 on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo,
                                         algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout))
             else:
                 # data gradient first on the main stream (the next layer's BatchNorm backward waits for it) ...
-                L.conv(l.dz, l.wd, l.g_in, L.MODE_3X3, algo=self.algo)
+                L.conv(l.dz, l.wd, l.g_in, L.MODE_3X3, algo=self.algo, bn_reduce=bn_red(feeds) if feeds is not None else None)
                 # ... weight gradient on the side stream
                 on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 1, algo=self.algo))
             # conv bias in front of train-mode BN: its gradient is identically zero (flat buffer is zeroed)
@@ -393,11 +401,14 @@ class UNetPlan:
         for i in (3, 2, 1, 0):
             lvl = 3 - i
             l1, l2 = self.dec[i]
-            conv_bn_bwd(l2, grad_a2)
-            conv_bn_bwd(l1, l2.g_in)
+            # grad_a2 comes from the head (i == 3) or from the ConvTranspose data gradient of the level above, which
+            # already accumulated l2's reductions
+            conv_bn_bwd(l2, grad_a2, reduced=(i != 3), feeds=l1)
+            conv_bn_bwd(l1, l2.g_in, reduced=True)
             ct = self.convts[i]
             L.LABEL = ct.name
-            L.conv(ct.g_out, ct.wd, ct.g_in, L.MODE_CONVT_GATHER, algo=self.algo)
+            nxt = self.dec[i - 1][1] if i > 0 else self.enc[4][1]     # layer whose activated output feeds this ConvTranspose
+            L.conv(ct.g_out, ct.wd, ct.g_in, L.MODE_CONVT_GATHER, algo=self.algo, bn_reduce=bn_red(nxt))
 
             def ct_grads(ct=ct):
                 L.wgrad(ct.src, ct.g_out, ct.ws, 2, algo=self.algo)
@@ -413,10 +424,11 @@ class UNetPlan:
         for lvl in (4, 3, 2, 1, 0):
             l1, l2 = self.enc[lvl]
             if lvl == 4:
-                conv_bn_bwd(l2, grad_a2)
+                conv_bn_bwd(l2, grad_a2, reduced=True, feeds=l1)
             else:
-                conv_bn_bwd(l2, self.dcat[lvl][..., :ENC_CH[lvl]], dpool=self.enc[lvl + 1][0].g_in)
-            conv_bn_bwd(l1, l2.g_in)
+                # two gradient sources (skip + max-pool): the stand-alone reduction kernel handles the routing
+                conv_bn_bwd(l2, self.dcat[lvl][..., :ENC_CH[lvl]], dpool=self.enc[lvl + 1][0].g_in, feeds=l1)
+            conv_bn_bwd(l1, l2.g_in, reduced=True)
             pos += 8
             join_side()
             L.weights_unpack(self._unpack_jobs[seg], flat)

@@ -103,7 +103,12 @@ int unetk_weights_unpack(const unetk_wjob* jobs, const int32_t* tiles, int32_t n
  *   mode 3  convT gather  y[p, ci]        = sum_{(a,b),co}  x[2p+(a,b), co]     w[ci][(a,b)][co]
  *           (data gradient of ConvTranspose2d)
  * Optional: bias[C_out]; stat_sum/stat_sumsq[C_out] (double, ACCUMULATED) = per-channel sum and
- * sum of squares of y as stored (BatchNorm batch statistics, unet/unet.py:17,20).            */
+ * sum of squares of y as stored (BatchNorm batch statistics, unet/unet.py:17,20).
+ * Optional (data-gradient launches): when y is the gradient dA w.r.t. the ACTIVATED output of a conv+BN+ReLU layer,
+ * bn_z (that layer's raw conv output, same shape as y) + bn_scale/bn_shift/bn_mean/bn_invstd make the kernel also
+ * accumulate that layer's BatchNorm-backward reductions into bn_sums[2][C] (double):
+ *   dy = dA * [relu(z*scale+shift) > 0];  bn_sums[0][c] += sum dy;  bn_sums[1][c] += sum dy * (z-mean)*invstd
+ * i.e. unetk_bn_relu_bwd_reduce without a separate pass over dA.                                             */
 typedef struct unetk_conv_args {
   unetk_tensor x;
   const void* w; /* same dtype as x */
@@ -113,6 +118,12 @@ typedef struct unetk_conv_args {
   const float* bias;
   double* stat_sum;
   double* stat_sumsq;
+  unetk_tensor bn_z; /* ptr NULL = no fused BatchNorm-backward reduction */
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* bn_mean;
+  const float* bn_invstd;
+  double* bn_sums;
 } unetk_conv_args;
 int unetk_conv(const unetk_conv_args* a, void* stream);
 

@@ -408,3 +408,39 @@ def test_batched_weight_pack_and_unpack():
     assert torch.equal(flat[oT:o1].view(128, 64, 2, 2).cpu(), wsT.cpu().view(128, 2, 2, 64).permute(0, 3, 1, 2))
     assert torch.equal(flat[o1:].view(64, 3, 3, 3).cpu(), ws1.cpu()[:, :27].view(64, 3, 3, 3).permute(0, 3, 1, 2))
     assert float(flat[:7].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("dt,algo", ALGOS, ids=IDS)
+@pytest.mark.parametrize("mode,n,h,w,cin,cout", [("3x3", 2, 32, 16, 64, 64), ("3x3", 1, 16, 16, 128, 256), ("3x3", 3, 8, 8, 64, 128),
+                                                   ("3x3", 2, 48, 24, 128, 128), ("gather", 2, 8, 8, 64, 128)])
+def test_data_gradient_with_fused_bn_backward_reduction(dt, algo, mode, n, h, w, cin, cout):
+    """unetk_conv(bn_reduce=...) must produce the same sums as the stand-alone unetk_bn_relu_bwd_reduce on its output."""
+    g = torch.Generator().manual_seed(90)
+    if mode == "3x3":
+        x = rnd((n, h, w, cin), dt, 91)
+        wt = rnd((cout, 9, cin), dt, 92, 0.05)
+        y = torch.empty((n, h, w, cout), dtype=dt, device=DEV)
+        m = L.MODE_3X3
+    else:
+        x = rnd((n, 2 * h, 2 * w, cin), dt, 91)
+        wt = rnd((cout, 4, cin), dt, 92, 0.05)
+        y = torch.empty((n, h, w, cout), dtype=dt, device=DEV)
+        m = L.MODE_CONVT_GATHER
+    z = rnd((n, h, w, cout), dt, 93, 2.0).to(DEV)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(cout, generator=g) * 0.5).to(DEV)
+    mean = (torch.randn(cout, generator=g) * 0.3).to(DEV)
+    invstd = (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    fused = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    L.conv(x.to(DEV), wt.to(DEV), y, m, algo=algo, bn_reduce=(z, scale, shift, mean, invstd, fused))
+    ref = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    args = L.BnBwdArgs(L.nhwc(z), L.nhwc(y), L.nhwc(None), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                       ref.data_ptr(), L.nhwc(None), None, None, None)
+    L.check(L.lib().unetk_bn_relu_bwd_reduce(__import__("ctypes").byref(args), L.stream_ptr()))
+    torch.cuda.synchronize()
+    scale_ref = ref.abs().max().item()
+    assert (fused - ref).abs().max().item() < 2e-4 * scale_ref, ((fused - ref).abs().max().item(), scale_ref)
+    # and the data gradient itself is unchanged by the fusion
+    y2 = torch.empty_like(y)
+    L.conv(x.to(DEV), wt.to(DEV), y2, m, algo=algo)
+    assert torch.equal(y, y2)
