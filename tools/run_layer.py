@@ -22,16 +22,22 @@ dev = "cuda"
 n, h, w = a.batch, a.hw, a.hw
 bf = torch.bfloat16
 x = torch.randn(n, h, w, a.cin, device=dev).to(bf)
-if a.op in ("conv", "dgrad"):
+if a.op in ("conv", "dgrad", "dgrad_bn"):
     wt = (torch.randn(a.cout, 9, a.cin, device=dev) * 0.05).to(bf)
     y = torch.empty(n, h, w, a.cout, device=dev, dtype=bf)
     s1 = torch.zeros(a.cout, dtype=torch.float64, device=dev)
     s2 = torch.zeros_like(s1)
     flops = 2 * n * h * w * 9 * a.cin * a.cout
 
+    zt = torch.randn(n, h, w, a.cout, device=dev).to(bf)
+    vec = [torch.rand(a.cout, device=dev) + 0.5 for _ in range(4)]
+    sums = torch.zeros(2 * a.cout, dtype=torch.float64, device=dev)
+
     def run():
         if a.op == "conv":
             L.conv(x, wt, y, L.MODE_3X3, stat_sum=s1, stat_sumsq=s2)
+        elif a.op == "dgrad_bn":
+            L.conv(x, wt, y, L.MODE_3X3, bn_reduce=(zt, vec[0], vec[1], vec[2], vec[3], sums))
         else:
             L.conv(x, wt, y, L.MODE_3X3)
 elif a.op == "wgrad":
