@@ -175,17 +175,6 @@ struct Bars {
   }
 };
 
-// fused BatchNorm-backward reduction: per-group state of the z-tile prefetch (one 16 KiB buffer per epilogue group; the
-// tile for the NEXT 64-channel block is requested as soon as every thread has finished reading the current one, so
-// the TMA latency hides behind the next block's TMEM drain)
-struct ZState {
-  uint32_t phase;
-  bool primed;   // a z tile for the upcoming block is already in flight
-};
-struct ZNext {   // first block of this group's next tile
-  int valid, col0, w0, h0, n0;
-};
-
 // Epilogue of one accumulator tile (128 rows x BLOCK_N fp32 in TMEM), executed by ONE of the two epilogue groups
 // (4 warps each; group g serves accumulator stage g, staging block g, named barrier 1+g, so two tiles drain
 // concurrently):  TMEM -> registers (+bias) -> bf16 -> 128B-swizzled staging block in shared memory -> TMA store
@@ -225,8 +214,8 @@ struct StatRegs {
 template <int BLOCK_N, bool HAS_BIAS, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* staging, int bar_id, uint32_t tmem_acc, int q,
                                               int lane, bool valid_row, int n_tile, int w0, int h0, int n0,
-                                              StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar, uint8_t* zbuf, uint64_t* zbar,
-                                              ZState& zs, const ZNext& znext) {
+                                              StatRegs<BLOCK_N>& st, uint64_t* tmem_empty_bar, uint8_t* zbuf = nullptr,
+                                              uint64_t* zbar = nullptr, uint32_t* zphase = nullptr) {
   const int row = q * 32 + lane;
   const bool storer = (q == 0 && lane == 0);
   const bool bnred = p.bn_sums != nullptr;
@@ -247,14 +236,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
   for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
     if (storer) tma_store_wait_read<0>();   // the previous store out of this staging block has been read
     named_bar_sync(bar_id, 128);
-    if (bnred && !zs.primed) {
-      // very first block of this group: nothing was prefetched yet.  z tile of the layer whose gradient this is (same
-      // pixels / channels as the output block), 128B-swizzled like the staging block
-      if (storer) {
-        mbar_arrive_expect_tx(zbar, kStagingBytes);
-        tma_load_4d(zbuf, &p.map_z, zbar, ch0 + blk * 64, w0, h0, n0);
-      }
-      zs.primed = true;
+    if (bnred && storer) {
+      // z tile of the layer whose gradient this is (same pixels / channels as the output block), 128B-swizzled like staging
+      mbar_arrive_expect_tx(zbar, kStagingBytes);
+      tma_load_4d(zbuf, &p.map_z, zbar, ch0 + blk * 64, w0, h0, n0);
     }
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(tmem_acc + blk * 64, r0);
@@ -304,8 +289,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
         const float sc0 = __ldg(p.bn_scale + ch), sc1 = __ldg(p.bn_scale + ch + 1);
         const float sh0 = __ldg(p.bn_shift + ch), sh1 = __ldg(p.bn_shift + ch + 1);
         const uint32_t zbase = smem_u32(zbuf) + (uint32_t)(lane & 3) * 4 + (uint32_t)(q * 32) * 128;
-        mbar_wait(zbar, zs.phase);
-        zs.phase ^= 1;
+        mbar_wait(zbar, *zphase);
+        *zphase ^= 1;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const uint32_t off = i * 128 + ((cgrp ^ (uint32_t)(i & 7)) << 4);
@@ -318,20 +303,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
           s1b += yhi;
           s2a = fmaf(ylo, zlo, s2a);
           s2b = fmaf(yhi, zhi, s2b);
-        }
-        // everybody is done with zbuf: request the z tile of the next block (same tile, or the group's next tile)
-        named_bar_sync(bar_id, 128);
-        const bool more_here = blk + 1 < BLOCK_N / 64;
-        if (more_here || znext.valid) {
-          if (storer) {
-            mbar_arrive_expect_tx(zbar, kStagingBytes);
-            if (more_here)
-              tma_load_4d(zbuf, &p.map_z, zbar, ch0 + (blk + 1) * 64, w0, h0, n0);
-            else
-              tma_load_4d(zbuf, &p.map_z, zbar, znext.col0, znext.w0, znext.h0, znext.n0);
-          }
-        } else {
-          zs.primed = false;
         }
       } else {
 #pragma unroll
@@ -473,7 +444,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
-    ZState zs{0u, false};
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -483,17 +454,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
-      ZNext znext{0, 0, 0, 0, 0};
-      if (p.bn_sums && tile + 2 * (int)gridDim.x < num_tiles) {
-        const int t2 = tile + 2 * gridDim.x, n2 = t2 / p.num_m_tiles, m2 = t2 % p.num_m_tiles;
-        znext = ZNext{1, n2 * BLOCK_N, (m2 % p.tiles_w) * p.pw, ((m2 / p.tiles_w) % p.tiles_h) * p.ph,
-                      (m2 / (p.tiles_w * p.tiles_h)) * p.nb};
-      }
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, HAS_BIAS>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
-                                       n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], zs, znext);
+                                       n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
     if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
@@ -634,7 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     const int pw_i = row % p.pw, ph_i = (row / p.pw) % p.ph, nb_i = row / (p.pw * p.ph);
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
-    ZState zs{0u, false};
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -644,17 +609,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
-      ZNext znext{0, 0, 0, 0, 0};
-      if (p.bn_sums && pt + 2 * num_pairs < num_ptiles) {
-        const int p2 = pt + 2 * num_pairs, n2 = p2 / m_pairs, m2 = 2 * (p2 % m_pairs) + (int)rank;
-        znext = ZNext{1, n2 * BLOCK_N, (m2 % p.tiles_w) * p.pw, ((m2 / p.tiles_w) % p.tiles_h) * p.ph,
-                      (m2 / (p.tiles_w * p.tiles_h)) * p.nb};
-      }
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, HAS_BIAS, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
-                                             valid, n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], zs, znext);
+                                             valid, n_tile, w0, h0, n0, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
     if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
@@ -820,7 +779,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
     const long long dbg_start = clock64();
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
-    ZState zs{0u, false};
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -837,15 +796,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
         DBG_ADD(dbg_tf);
       }
       tcgen05_fence_after();
-      ZNext znext{0, 0, 0, 0, 0};
-      if (p.bn_sums && tile + 2 * (int)gridDim.x < num_tiles) {
-        const int t2 = tile + 2 * gridDim.x, n2 = t2 / p.num_m_tiles, m2 = t2 % p.num_m_tiles;
-        znext = ZNext{1, n2 * BLOCK_N, (m2 % p.tiles_w) * 8, ((m2 / p.tiles_w) % p.tiles_h) * 16, m2 / (p.tiles_w * p.tiles_h)};
-      }
       {
         DBG_T0();
         epilogue_tile<BLOCK_N, false>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane, valid,
-                                      n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], zs, znext);
+                                      n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
         DBG_ADD(dbg_epi);
       }
     }
@@ -1018,7 +972,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     const int pw_i = row & 7, ph_i = row >> 3;
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
-    ZState zs{0u, false};
+    uint32_t zphase = 0;
     StatRegs<BLOCK_N> st;
     st.clear();
     st.n_tile = -1;
@@ -1028,16 +982,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * 8, h0 = th * 16;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && tn < p.n;
-      ZNext znext{0, 0, 0, 0, 0};
-      if (p.bn_sums && pt + 2 * num_pairs < num_ptiles) {
-        const int p2 = pt + 2 * num_pairs, n2 = p2 / m_pairs, m2 = 2 * (p2 % m_pairs) + (int)rank;
-        znext = ZNext{1, n2 * BLOCK_N, (m2 % p.tiles_w) * 8, ((m2 / p.tiles_w) % p.tiles_h) * 16, m2 / (p.tiles_w * p.tiles_h)};
-      }
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&bars.tmem_full[g], acc_phase);
       tcgen05_fence_after();
       epilogue_tile<BLOCK_N, false, true>(p, staging, 1 + g, tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N, q, lane,
-                                          valid, n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], zs, znext);
+                                          valid, n_tile, w0, h0, tn, st, &bars.tmem_empty[g], zbuf, &bars.zfull[g], &zphase);
     }
     if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
