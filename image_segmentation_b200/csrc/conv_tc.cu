@@ -917,14 +917,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
+      long long dbg_fa = 0, dbg_fb = 0, dbg_te = 0;
+      const long long dbg_start = clock64();
       for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+        {
+          DBG_T0();
+          mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+          DBG_ADD(dbg_te);
+        }
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int chunk = 0; chunk < cpt; ++chunk) {
-          mbar_wait(&bars.full_a[sa], pa);
+          {
+            DBG_T0();
+            mbar_wait(&bars.full_a[sa], pa);
+            DBG_ADD(dbg_fa);
+          }
           tcgen05_fence_after();
           const uint32_t halo = smem_u32(smem + sa * kHaloStride);
           for (int tap = 0; tap < 9; ++tap) {
@@ -937,7 +947,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
               }
             } else {
               bslot = sb;
-              mbar_wait(&bars.full_b[sb], pb);
+              {
+                DBG_T0();
+                mbar_wait(&bars.full_b[sb], pb);
+                DBG_ADD(dbg_fb);
+              }
               tcgen05_fence_after();
             }
             const uint32_t a0 = halo + ((tap / 3) * 10 + (tap % 3)) * 128;
@@ -962,6 +976,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
         }
         umma_commit_2sm(&bars.tmem_full[acc]);
         first = false;
+      }
+      if (blockIdx.x < 160) {
+        g_dbg[blockIdx.x * 8 + 1] = dbg_fa;
+        g_dbg[blockIdx.x * 8 + 2] = dbg_fb;
+        g_dbg[blockIdx.x * 8 + 3] = dbg_te;
+        g_dbg[blockIdx.x * 8 + 4] = clock64() - dbg_start;
       }
     }
     __syncwarp();

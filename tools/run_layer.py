@@ -74,6 +74,8 @@ if os.environ.get("UNETK_DBG") == "1":
     L.lib().unetk_debug_counters(buf, 148 * 8)
     import numpy as np
     d = np.array(buf[:]).reshape(148, 8)
+    if os.environ.get("UNETK_HALO_PAIR") == "1":
+        d = d[::2]     # leader CTAs hold the MMA counters
     names = ["prod wait emptyA", "mma wait fullA", "mma wait fullB", "mma wait tmem_empty", "mma total",
              "epi0 wait tmem_full", "epi0 in epilogue", "epi0 total"]
     for i, nm in enumerate(names):
