@@ -103,7 +103,7 @@ def cpu_reference_steps(steps, warmup, batch=4):
     from image_segmentation_b200.utils.synthetic import make_batch
     from oracle import loss_oracle, metrics_oracle, unet_oracle
     torch.manual_seed(0)
-    m = unet_oracle.OracleUNet(3, 3).train()
+    m = unet_oracle.OracleUNet(3, 3, native_ops=True).train()   # the reference's own ATen operators (F.batch_norm, ...)
     opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
     w = torch.tensor(CLASS_W3)
     x, y = make_batch(batch, H, W, 3, 3, seed=1234)
@@ -111,7 +111,7 @@ def cpu_reference_steps(steps, warmup, batch=4):
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         pred = m(x)
-        loss = loss_oracle.dice_ce_loss(pred, y, smooth_dice=1.0, class_weights=w, dtype=torch.float32)
+        loss = loss_oracle.dice_ce_loss(pred, y, smooth_dice=1.0, class_weights=w, dtype=torch.float32)   # fp32 like the reference
         loss.backward()
         opt.step()
         opt.zero_grad()

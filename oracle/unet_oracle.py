@@ -131,11 +131,23 @@ def conv_transpose_2x2(x, w, b):
     return y + b[None, :, None, None]
 
 
-def _double_conv(x, sd, prefix, training, new_buffers):
+def _double_conv(x, sd, prefix, training, new_buffers, native_ops=False):
     for idx_conv, idx_bn in (("0", "1"), ("3", "4")):
         z = F.conv2d(x, sd[f"{prefix}.{idx_conv}.weight"], sd[f"{prefix}.{idx_conv}.bias"], padding=1)
         g, b = sd[f"{prefix}.{idx_bn}.weight"], sd[f"{prefix}.{idx_bn}.bias"]
         rm, rv = sd[f"{prefix}.{idx_bn}.running_mean"], sd[f"{prefix}.{idx_bn}.running_var"]
+        if native_ops:
+            # exactly the ATen calls nn.BatchNorm2d makes (used by the CPU timing legs of bench.py so that the baseline
+            # runs the reference's own operators, not the closed-form restatement below)
+            if training:
+                nbt = sd[f"{prefix}.{idx_bn}.num_batches_tracked"]
+                y = F.batch_norm(z, rm, rv, g, b, True, BN_MOMENTUM, BN_EPS)     # updates rm / rv in place
+                with torch.no_grad():
+                    nbt += 1
+            else:
+                y = F.batch_norm(z, rm, rv, g, b, False, BN_MOMENTUM, BN_EPS)
+            x = torch.relu(y)
+            continue
         if training:
             y, mean, var = batchnorm_train(z, g, b)
             if new_buffers is not None:
@@ -154,7 +166,7 @@ def _double_conv(x, sd, prefix, training, new_buffers):
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True,
             new_buffers: Dict[str, torch.Tensor] | None = None,
-            taps: Dict[str, torch.Tensor] | None = None) -> torch.Tensor:
+            taps: Dict[str, torch.Tensor] | None = None, native_ops: bool = False) -> torch.Tensor:
     """unet.forward (unet/unet.py:93-105).  ``taps`` (optional) receives intermediate activations."""
     def tap(name, t):
         if taps is not None:
@@ -162,17 +174,20 @@ def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool = True,
         return t
 
     skips = []
-    h = tap("x1", _double_conv(x, sd, "down1.doubleConvReLU", training, new_buffers))
+    h = tap("x1", _double_conv(x, sd, "down1.doubleConvReLU", training, new_buffers, native_ops))
     skips.append(h)
     for i in range(2, 6):
         h = F.max_pool2d(h, kernel_size=2, stride=2)
-        h = tap(f"x{i}", _double_conv(h, sd, f"down{i}.maxpool_doubleConv.1.doubleConvReLU", training, new_buffers))
+        h = tap(f"x{i}", _double_conv(h, sd, f"down{i}.maxpool_doubleConv.1.doubleConvReLU", training, new_buffers, native_ops))
         if i < 5:
             skips.append(h)
     for i in range(1, 5):
-        up = conv_transpose_2x2(h, sd[f"up{i}.upsample.weight"], sd[f"up{i}.upsample.bias"])
+        if native_ops:
+            up = F.conv_transpose2d(h, sd[f"up{i}.upsample.weight"], sd[f"up{i}.upsample.bias"], stride=2)
+        else:
+            up = conv_transpose_2x2(h, sd[f"up{i}.upsample.weight"], sd[f"up{i}.upsample.bias"])
         h = torch.cat([skips[4 - i], up], dim=1)           # skip FIRST (unet/unet.py:63)
-        h = tap(f"u{i}", _double_conv(h, sd, f"up{i}.doubleConv.doubleConvReLU", training, new_buffers))
+        h = tap(f"u{i}", _double_conv(h, sd, f"up{i}.doubleConv.doubleConvReLU", training, new_buffers, native_ops))
     return F.conv2d(h, sd["output.weight"], sd["output.bias"])
 
 
@@ -200,8 +215,9 @@ class OracleUNet(torch.nn.Module):
     internally); used by bench.py's CPU baseline leg and by the loss-curve parity tests.
     """
 
-    def __init__(self, din: int, dout: int, gen=None):
+    def __init__(self, din: int, dout: int, gen=None, native_ops: bool = False):
         super().__init__()
+        self.native_ops = native_ops
         sd = init_state_dict(din, dout, gen)
         self._names = list(sd.keys())
         for k, v in sd.items():
@@ -224,6 +240,8 @@ class OracleUNet(torch.nn.Module):
 
     def forward(self, x):
         sd = self.flat()
+        if self.native_ops:
+            return forward(sd, x, training=self.training, native_ops=True)
         new_buffers: Dict[str, torch.Tensor] = {}
         out = forward(sd, x, training=self.training, new_buffers=new_buffers)
         with torch.no_grad():

@@ -173,3 +173,16 @@ def test_oracle_against_live_reference():
         if "doubleConvReLU" in k and k.endswith((".0.bias", ".3.bias")):
             continue
         np.testing.assert_allclose(grads[k].numpy(), p.grad.numpy(), rtol=1e-6, atol=1e-11, err_msg=k)
+
+
+def test_native_ops_variant_equals_closed_form():
+    """The timing variant of the oracle (F.batch_norm / F.conv_transpose2d, as the reference calls them) computes the same thing."""
+    x, y = make_batch(2, 32, 32, 3, 3, seed=8)
+    torch.manual_seed(1)
+    a = unet_oracle.OracleUNet(3, 3).double().train()
+    torch.manual_seed(1)
+    b = unet_oracle.OracleUNet(3, 3, native_ops=True).double().train()
+    ya, yb = a(x.double()), b(x.double())
+    np.testing.assert_allclose(ya.detach().numpy(), yb.detach().numpy(), rtol=1e-9, atol=1e-11)
+    for (ka, va), (kb, vb) in zip(a.reference_state_dict().items(), b.reference_state_dict().items()):
+        np.testing.assert_allclose(va.double().numpy(), vb.double().numpy(), rtol=1e-9, atol=1e-12, err_msg=ka)
