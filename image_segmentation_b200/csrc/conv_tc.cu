@@ -1296,7 +1296,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      // a single 64-channel slab runs as an M = 64 MMA (tools/umma_probe.cu: accumulator row r then lives in TMEM lane
+      // (r/16)*32 + r%16, i.e. the first 16 lanes of every 32-lane quadrant)
+      constexpr uint32_t idesc = make_idesc_bf16(BM_SLABS == 2 ? 128 : 64, BLOCK_N, 1, 1);
       constexpr uint32_t lbo_a = BM_SLABS == 2 ? kABytes : 0;
       int stage = 0;
       uint32_t phase = 0;
@@ -1344,8 +1346,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int cu_idx = cu_t * (BM_SLABS * 64) + row;
-      const bool valid = row < BM_SLABS * 64 && cu_idx < p.cu;
+      const int mrow = BM_SLABS == 2 ? row : q * 16 + lane;          // accumulator row held by this TMEM lane
+      const int cu_idx = cu_t * (BM_SLABS * 64) + mrow;
+      const bool valid = (BM_SLABS == 2 || lane < 16) && cu_idx < p.cu;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t rg[32];

@@ -31,6 +31,7 @@ struct Cfg {
   uint32_t base_offset;  // 3-bit field
   uint32_t a_mn_major;   // 0: K-major A, 1: MN-major A
   uint32_t kadv_bytes;   // start-address advance per UMMA_K step
+  uint32_t m;            // 128 or 64
 };
 
 constexpr int A_ROWS = 512;  // 64 KiB operand region
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const __grid_constant__ C
       return d;
     };
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (cfg.a_mn_major << 15) | (0u << 16) | ((64u >> 3) << 17) |
-                           ((128u >> 4) << 24);
+                           ((cfg.m >> 4) << 24);
     for (int k = 0; k < 4; ++k) {
       const uint64_t da = desc(smem_u32(sa) + cfg.start_bytes + k * cfg.kadv_bytes, cfg.lbo, cfg.sbo, cfg.base_offset);
       const uint64_t db = desc(smem_u32(sb) + k * 32, 0, 1024, 0);
@@ -175,23 +176,25 @@ int main() {
   };
   // K-major: kadv 32 B.  MN-major A: rows = K, kadv = 16 rows * 128 B = 2048, LBO = slab stride (we use 128 rows * 128 B)
   std::vector<Named> cfgs = {
-      {"K  start=0     sbo=1024 bo=0", {0, 0, 1024, 0, 0, 32}},
-      {"K  start=1row  sbo=1024 bo=0", {128, 0, 1024, 0, 0, 32}},
-      {"K  start=1row  sbo=1024 bo=1", {128, 0, 1024, 1, 0, 32}},
-      {"K  start=2row  sbo=1024 bo=0", {256, 0, 1024, 0, 0, 32}},
-      {"K  start=2row  sbo=1024 bo=2", {256, 0, 1024, 2, 0, 32}},
-      {"K  start=0     sbo=2048 bo=0", {0, 0, 2048, 0, 0, 32}},
-      {"K  start=1row  sbo=2048 bo=0", {128, 0, 2048, 0, 0, 32}},
-      {"K  start=1row  sbo=2048 bo=1", {128, 0, 2048, 1, 0, 32}},
-      {"K  start=17row sbo=2048 bo=0", {17 * 128, 0, 2048, 0, 0, 32}},
-      {"K  start=17row sbo=2048 bo=1", {17 * 128, 0, 2048, 1, 0, 32}},
-      {"K  start=0     sbo=1280 bo=0", {0, 0, 1280, 0, 0, 32}},
-      {"K  start=1row  sbo=1280 bo=0", {128, 0, 1280, 0, 0, 32}},
-      {"MN start=0     sbo=1024 lbo=16384 bo=0", {0, 16384, 1024, 0, 1, 2048}},
-      {"MN start=1row  sbo=1024 lbo=16384 bo=0", {128, 16384, 1024, 0, 1, 2048}},
-      {"MN start=1row  sbo=1024 lbo=16384 bo=1", {128, 16384, 1024, 1, 1, 2048}},
-      {"MN start=2row  sbo=1024 lbo=16384 bo=0", {256, 16384, 1024, 0, 1, 2048}},
-      {"MN start=0     sbo=1024 lbo=0     bo=0", {0, 0, 1024, 0, 1, 2048}},
+      {"K  start=0     sbo=1024 bo=0", {0, 0, 1024, 0, 0, 32, 128}},
+      {"K  start=1row  sbo=1024 bo=0", {128, 0, 1024, 0, 0, 32, 128}},
+      {"K  start=1row  sbo=1024 bo=1", {128, 0, 1024, 1, 0, 32, 128}},
+      {"K  start=2row  sbo=1024 bo=0", {256, 0, 1024, 0, 0, 32, 128}},
+      {"K  start=2row  sbo=1024 bo=2", {256, 0, 1024, 2, 0, 32, 128}},
+      {"K  start=0     sbo=2048 bo=0", {0, 0, 2048, 0, 0, 32, 128}},
+      {"K  start=1row  sbo=2048 bo=0", {128, 0, 2048, 0, 0, 32, 128}},
+      {"K  start=1row  sbo=2048 bo=1", {128, 0, 2048, 1, 0, 32, 128}},
+      {"K  start=17row sbo=2048 bo=0", {17 * 128, 0, 2048, 0, 0, 32, 128}},
+      {"K  start=17row sbo=2048 bo=1", {17 * 128, 0, 2048, 1, 0, 32, 128}},
+      {"K  start=0     sbo=1280 bo=0", {0, 0, 1280, 0, 0, 32, 128}},
+      {"K  start=1row  sbo=1280 bo=0", {128, 0, 1280, 0, 0, 32, 128}},
+      {"MN start=0     sbo=1024 lbo=16384 bo=0", {0, 16384, 1024, 0, 1, 2048, 128}},
+      {"MN start=1row  sbo=1024 lbo=16384 bo=0", {128, 16384, 1024, 0, 1, 2048, 128}},
+      {"MN start=1row  sbo=1024 lbo=16384 bo=1", {128, 16384, 1024, 1, 1, 2048, 128}},
+      {"MN start=2row  sbo=1024 lbo=16384 bo=0", {256, 16384, 1024, 0, 1, 2048, 128}},
+      {"MN start=0     sbo=1024 lbo=0     bo=0", {0, 0, 1024, 0, 1, 2048, 128}},
+      {"K  M=64 start=0 sbo=1024 (TMEM lane layout of a 64-row accumulator)", {0, 0, 1024, 0, 0, 32, 64}},
+      {"MN M=64 start=0 sbo=1024 lbo=16384", {0, 16384, 1024, 0, 1, 2048, 64}},
   };
   std::vector<float> o_row(128 * 64), o_col(128 * 64);
   for (auto& nc : cfgs) {
@@ -211,6 +214,10 @@ int main() {
         for (int n = 1; n < 64; ++n) uniform &= o_row[m * 64 + n] == o_row[m * 64];
         printf("%d%s ", (int)o_row[m * 64], uniform ? "" : "*");
       }
+      if (nc.c.m == 64) {
+        printf("\n   TMEM lane -> source row (all 128 lanes, -1 = not written / other): ");
+        for (int m = 0; m < 128; ++m) printf("%d ", (int)o_row[m * 64]);
+      }
       printf("\n   src col of n=0..63 at m=0 : ");
       for (int n = 0; n < 64; n += 1) printf("%d ", (int)o_col[0 * 64 + n]);
       printf("\n   src col of n=0..63 at m=9 : ");
@@ -228,6 +235,11 @@ int main() {
       for (int m = 0; m < 10; ++m) printf("%d ", (int)o_col[m * 64 + 9]);
       printf("\n   row-probe at m=64,n=0..3 (slab 2 rows): %d %d %d %d\n", (int)o_row[64 * 64], (int)o_row[64 * 64 + 1],
              (int)o_row[64 * 64 + 2], (int)o_row[64 * 64 + 3]);
+      if (nc.c.m == 64) {
+        printf("   TMEM lane -> channel (col-probe, n=0), all 128 lanes: ");
+        for (int m = 0; m < 128; ++m) printf("%d ", (int)o_col[m * 64]);
+        printf("\n");
+      }
     }
   }
   return 0;
