@@ -1618,13 +1618,29 @@ bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
 // waves: the largest split count with at most 2 work items per SM (never rounding UP past a wave boundary, which would
 // leave most SMs idle for a third round), at least 4 pixel tiles per item.
 static void choose_splits(int64_t out_tiles, int num_ptiles, int* ptiles_per_split, int* splits_out) {
-  const int64_t slots = 2LL * sm_count();
-  int64_t splits = slots / out_tiles;
-  if (splits < 1) splits = 1;
-  const int64_t max_splits = (num_ptiles + 3) / 4;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int per = (int)((num_ptiles + splits - 1) / splits);
+  // pick the split count whose work-item total fills the persistent grid best: efficiency = items / (rounds * SMs);
+  // ties go to fewer splits (fewer fp32 atomics); at least 4 pixel tiles per item, at most ~3 items per SM
+  const int64_t sms = sm_count();
+  int64_t max_splits = (num_ptiles + 3) / 4;
+  if (max_splits < 1) max_splits = 1;
+  int64_t cap = (3 * sms + out_tiles - 1) / out_tiles;
+  if (cap < 1) cap = 1;
+  if (max_splits > cap) max_splits = cap;
+  int best = 1;
+  double best_eff = -1.0;
+  for (int64_t sp = 1; sp <= max_splits; ++sp) {
+    const int per = (int)((num_ptiles + sp - 1) / sp);
+    const int64_t real = (num_ptiles + per - 1) / per;          // splits actually produced
+    const int64_t items = out_tiles * real;
+    const int64_t rounds = (items + sms - 1) / sms;
+    // work per item is `per` pixel tiles; the grid finishes after rounds * per tile-times
+    const double eff = (double)out_tiles * num_ptiles / ((double)rounds * sms * per);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = (int)real;
+    }
+  }
+  int per = (num_ptiles + best - 1) / best;
   *ptiles_per_split = per;
   *splits_out = (num_ptiles + per - 1) / per;
 }
