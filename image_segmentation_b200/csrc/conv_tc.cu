@@ -1619,7 +1619,7 @@ bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
 // leave most SMs idle for a third round), at least 4 pixel tiles per item.
 static void choose_splits(int64_t out_tiles, int num_ptiles, int* ptiles_per_split, int* splits_out) {
   // pick the split count whose work-item total fills the persistent grid best: efficiency = items / (rounds * SMs);
-  // ties go to fewer splits (fewer fp32 atomics); at least 4 pixel tiles per item, at most ~3 items per SM
+  // near-ties go to fewer splits (fewer fp32 atomics, longer K loops); >= 4 pixel tiles per item, <= ~3 items per SM
   const int64_t sms = sm_count();
   int64_t max_splits = (num_ptiles + 3) / 4;
   if (max_splits < 1) max_splits = 1;
@@ -1635,7 +1635,7 @@ static void choose_splits(int64_t out_tiles, int num_ptiles, int* ptiles_per_spl
     const int64_t rounds = (items + sms - 1) / sms;
     // work per item is `per` pixel tiles; the grid finishes after rounds * per tile-times
     const double eff = (double)out_tiles * num_ptiles / ((double)rounds * sms * per);
-    if (eff > best_eff + 1e-9) {
+    if (eff > best_eff + 0.03) {   // more splits only for a clear (> 3 %) gain in grid fill
       best_eff = eff;
       best = (int)real;
     }
