@@ -65,6 +65,23 @@ class DiceCeArgs(C.Structure):
                 ("dlogits", C.c_void_p)]
 
 
+UNETK_U8, UNETK_I64 = 2, 3      # label dtypes (include/unetk.h)
+
+
+class EvalImage(C.Structure):
+    _fields_ = [("crop_top", C.c_int32), ("crop_left", C.c_int32), ("crop_h", C.c_int32), ("crop_w", C.c_int32),
+                ("out_h", C.c_int32), ("out_w", C.c_int32), ("offset", C.c_int64)]
+
+
+class EvalArgs(C.Structure):
+    _fields_ = [("logits", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32), ("th", C.c_int32), ("tw", C.c_int32),
+                ("images", C.c_void_p), ("max_out_pixels", C.c_int32), ("labels", C.c_void_p),
+                ("label_dtype", C.c_int32), ("class_weights", C.c_void_p), ("has_ignore", C.c_int32),
+                ("ignore_index", C.c_int64), ("dice_weight", C.c_float), ("ce_weight", C.c_float),
+                ("smooth", C.c_float), ("accum", C.c_void_p), ("loss_per_image", C.c_void_p),
+                ("loss_sum", C.c_void_p), ("counts", C.c_void_p), ("status", C.c_void_p)]
+
+
 _lib = None
 
 
@@ -100,6 +117,8 @@ def lib():
             "unetk_dice_ce_fwd": [P(DiceCeArgs), vp],
             "unetk_dice_ce_bwd": [P(DiceCeArgs), vp],
             "unetk_argmax_confusion": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp],
+            "unetk_crop_resize": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp],
+            "unetk_eval_loss_metrics": [P(EvalArgs), vp],
         }
         for name, argtypes in sigs.items():
             fn = getattr(l, name)
@@ -114,7 +133,7 @@ EXPORTED_SYMBOLS = (
     "unetk_weights_pack", "unetk_weights_unpack",
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
-    "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion",
+    "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
 )
 
 
@@ -287,6 +306,32 @@ def dice_ce_fwd(args):
 
 def dice_ce_bwd(args):
     _run("loss", 1, 0, lib().unetk_dice_ce_bwd, C.byref(args), stream_ptr())
+
+
+def eval_image_table(metas, device):
+    """Device array of ``unetk_eval_image`` from the metadata dictionaries of ``resize_with_padding``
+    (utils/utils.py:42-47).  Returns (table tensor, total output pixels, max output pixels)."""
+    rows, off, mx = [], 0, 0
+    for m in metas:
+        left, top, _, _ = m["pad"]
+        new_h, new_w = m["new_size"]
+        oh, ow = m["original_size"]
+        rows.append((int(top) | (int(left) << 32), int(new_h) | (int(new_w) << 32), int(oh) | (int(ow) << 32), off))
+        off += oh * ow
+        mx = max(mx, oh * ow)
+    # four int64 words per image = the 32-byte struct (little endian: low word first)
+    table = torch.tensor(rows, dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+    return table, off, mx
+
+
+def crop_resize(src, table, max_out_pixels, mode, out):
+    n, c, th, tw = src.shape
+    _run("eval", 1, 0, lib().unetk_crop_resize, src.data_ptr(), n, c, th, tw, table.data_ptr(), max_out_pixels, mode,
+         out.data_ptr(), stream_ptr())
+
+
+def eval_loss_metrics(args):
+    _run("eval", 2, 0, lib().unetk_eval_loss_metrics, C.byref(args), stream_ptr())
 
 
 def argmax_confusion(pred, label, n, c, h, w, counts, argmax_out, status):

@@ -9,11 +9,10 @@
 //   head fprop   cin*sizeof(T) + 4*dout                 head bwd   2*cin*sizeof(T) + 4*dout (a read once, da written once)
 //   loss fwd     4*C + 8                                loss bwd   8*C + 8
 //   metrics      4*C + 8
-#include "common.cuh"
+#include "loss_common.cuh"
 
 namespace unetk {
 
-constexpr int kMaxClasses = 8;
 constexpr int kMaxHeadCin = 256;
 
 // ------------------------------------------------------------------------------------------------
@@ -156,36 +155,6 @@ __global__ void __launch_bounds__(TILE) head_bwd_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Dice + CE
 // ------------------------------------------------------------------------------------------------
-struct Softmax {
-  float p[kMaxClasses];
-  float logp_y;
-};
-
-__device__ __forceinline__ void pixel_softmax(const float* __restrict__ logits, int64_t base, int64_t hw, int c, int y,
-                                              Softmax& s) {
-  float x[kMaxClasses];
-  float m = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
-    x[k] = k < c ? logits[base + k * hw] : -INFINITY;
-    m = fmaxf(m, x[k]);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
-    s.p[k] = k < c ? expf(x[k] - m) : 0.f;
-    sum += s.p[k];
-  }
-  const float inv = 1.f / sum;
-  float xy = 0.f;
-#pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
-    s.p[k] *= inv;
-    if (k == y) xy = x[k];
-  }
-  s.logp_y = xy - m - logf(sum);
-}
-
 __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args a) {
   const int c = a.c;
   const int64_t hw = (int64_t)a.h * a.w, npix = (int64_t)a.n * hw;
@@ -250,29 +219,8 @@ __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args 
 
 __global__ void dice_ce_finalize_kernel(unetk_dice_ce_args a) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const int c = a.c;
-  double wsum = 0.0;
-  for (int k = 0; k < c; ++k) {
-    const bool valid = !(a.has_ignore && a.ignore_index >= 0 && a.ignore_index < c && k == a.ignore_index);
-    if (valid) wsum += a.class_weights ? (double)a.class_weights[k] : 1.0;
-  }
-  if (a.class_weights && wsum < 1e-8) wsum = 1e-8;
-  double dice = 0.0;
-  for (int k = 0; k < c; ++k) {
-    const bool valid = !(a.has_ignore && a.ignore_index >= 0 && a.ignore_index < c && k == a.ignore_index);
-    const double I = a.accum[k], P = a.accum[c + k], G = a.accum[2 * c + k];
-    const double den = P + G + (double)a.smooth;
-    const double den_c = den < 1e-8 ? 1e-8 : den;
-    const double dc = (2.0 * I + (double)a.smooth) / den_c;
-    const double ak = valid ? (a.class_weights ? (double)a.class_weights[k] : 1.0) / wsum : 0.0;
-    dice += ak * dc;
-    a.coef[k] = (float)((double)a.dice_weight * ak / den_c);
-    a.coef[c + k] = den < 1e-8 ? 0.f : (float)dc;
-  }
-  const double ce_num = a.accum[3 * c], ce_den = a.accum[3 * c + 1];
-  const double ce = ce_num / ce_den;  // NaN if every pixel is ignored, like torch
-  a.coef[2 * c] = (float)((double)a.ce_weight / ce_den);
-  a.loss[0] = (float)((double)a.dice_weight * (-dice) + (double)a.ce_weight * ce);
+  a.loss[0] = finalize_dice_ce(a.accum, a.c, a.class_weights, a.has_ignore, a.ignore_index, a.smooth, a.dice_weight,
+                               a.ce_weight, a.coef);
 }
 
 __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) {

@@ -68,6 +68,13 @@ class MetricsHistory:
             counts.zero_()
         self._host.zero_()
 
+    def _device_counters(self, dev):
+        """(int64 [4,C] counts, int32 [1] bad-label flag) resident on ``dev``; kernels add into them."""
+        if dev not in self._pending:
+            self._pending[dev] = (torch.zeros(4, self.num_classes, dtype=torch.int64, device=dev),
+                                  torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._pending[dev]
+
     def accumulate(self, pred: torch.Tensor, label: torch.Tensor):
         """pred: logits or probabilities (C,H,W) [or (N,C,H,W) for a whole batch]; label: (H,W), (1,H,W) [or (N,H,W)]."""
         L.require_cuda(pred, label)
@@ -84,10 +91,7 @@ class MetricsHistory:
         pred = pred if (pred.dtype == torch.float32 and pred.is_contiguous()) else pred.float().contiguous()
         label = label if (label.dtype == torch.int64 and label.is_contiguous()) else label.long().contiguous()
         dev = pred.device
-        if dev not in self._pending:
-            self._pending[dev] = (torch.zeros(4, c, dtype=torch.int64, device=dev),
-                                  torch.zeros(1, dtype=torch.int32, device=dev))
-        counts, status = self._pending[dev]
+        counts, status = self._device_counters(dev)
         with torch.cuda.device(dev):
             L.argmax_confusion(pred, label, n, c, h, w, counts, None, status)
 

@@ -12,7 +12,9 @@ import os
 
 import torch
 
+from .. import _lib as L
 from .MetricsHistory import MetricsHistory
+from .weighted_loss import WeightedDiceCELoss
 from .utils import process_batch_forward, process_batch_reverse
 
 try:  # progress bars are optional plumbing
@@ -66,23 +68,91 @@ def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device
     return avg_loss
 
 
+class _EvalTail:
+    """Fused evaluation tail for one epoch (utils/training.py:93-101 + utils/utils.py:101-115): every batch is one
+    ``unetk_eval_loss_metrics`` call that resizes the logits of all its images back to their original sizes on the fly
+    and reduces the per-image Dice+CE losses and the confusion counts on the device.  Nothing is read back until
+    ``finish()``."""
+
+    def __init__(self, loss_fn, agg, device):
+        self.loss_fn, self.agg, self.device = loss_fn, agg, torch.device(device)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.per_image = []
+        cw = loss_fn.class_weights
+        self.cw = None if cw is None else cw.detach().to(device=self.device, dtype=torch.float32).contiguous()
+
+    @staticmethod
+    def supports(loss_fn, agg, preds):
+        return (isinstance(loss_fn, WeightedDiceCELoss) and isinstance(agg, MetricsHistory) and preds.is_cuda
+                and preds.dim() == 4 and preds.shape[1] == agg.get_num_classes() and preds.shape[1] <= 8)
+
+    def batch(self, preds, meta_list, labels):
+        n, c, th, tw = preds.shape
+        if len(labels) != n or len(meta_list) != n:
+            raise ValueError(f"{n} predictions, {len(meta_list)} metas, {len(labels)} labels")
+        flat = []
+        for lab, m in zip(labels, meta_list):
+            oh, ow = m["original_size"]
+            if lab.numel() != oh * ow:
+                raise ValueError(f"Shape mismatch: label {tuple(lab.shape)} vs original size {(oh, ow)}")
+            flat.append(lab.reshape(-1))
+        if not all(f.dtype == torch.uint8 for f in flat):
+            flat = [f.long() for f in flat]
+        packed = torch.cat(flat)
+        if not packed.is_cuda:
+            packed = packed.pin_memory().to(self.device, non_blocking=True)
+        lg = preds.detach()
+        lg = lg if (lg.dtype == torch.float32 and lg.is_contiguous()) else lg.float().contiguous()
+        fn = self.loss_fn
+        ign = fn.ignore_index
+        if self.cw is not None and self.cw.numel() != c:
+            raise RuntimeError(f"weight tensor should be defined for all {c} classes, got {self.cw.numel()}")
+        with torch.cuda.device(self.device):
+            table, _, mx = L.eval_image_table(meta_list, self.device)
+            accum = torch.zeros(n, 3 * c + 2, dtype=torch.float64, device=self.device)
+            per = torch.empty(n, dtype=torch.float32, device=self.device)
+            counts, status = self.agg._device_counters(self.device)
+            args = L.EvalArgs(lg.data_ptr(), n, c, th, tw, table.data_ptr(), mx, packed.data_ptr(),
+                              L.UNETK_U8 if packed.dtype == torch.uint8 else L.UNETK_I64, L.ptr(self.cw),
+                              0 if ign is None else 1, 0 if ign is None else int(ign), float(fn.dice_weight),
+                              float(fn.ce_weight), float(fn.smooth_dice), accum.data_ptr(), per.data_ptr(),
+                              self.loss_sum.data_ptr(), counts.data_ptr(), status.data_ptr())
+            L.eval_loss_metrics(args)
+        self.per_image.append(per)
+        self._keep = (lg, packed, table, accum)          # alive until the next batch is enqueued on the same stream
+
+    def finish(self):
+        return float(self.loss_sum.item())               # the one sync of the epoch
+
+
 def eval_loop(dataloader, model, loss_fn, device, target_size, agg):
     """Evaluation at each image's original resolution: mean loss, macro Dice and mIoU."""
     model.eval()
     num_images_processed = 0
     losses = []
+    tail = None
     agg.reset()
     with torch.no_grad():
         for X, y in _progress(dataloader, desc="Eval"):
             X, meta_list = process_batch_forward(X, target_size=target_size)
             preds = model(X.to(device, non_blocking=True))
+            if _EvalTail.supports(loss_fn, agg, preds):
+                if tail is None:
+                    tail = _EvalTail(loss_fn, agg, preds.device)
+                tail.batch(preds, meta_list, list(y))
+                num_images_processed += len(meta_list)
+                continue
+            # any other loss / metrics object: materialise the resized predictions (one launch) and call it per image
             preds = process_batch_reverse(preds, meta_list, interpolation='bilinear')
             for pred, label in zip(preds, y):
                 label = label.to(device).long()
                 losses.append(loss_fn(pred.unsqueeze(0), label.unsqueeze(0).squeeze(1)))
                 agg.accumulate(pred, label)
                 num_images_processed += 1
-    avg_loss = torch.stack(losses).double().mean().item() if losses else float("nan")   # one sync for the epoch
+    total = tail.finish() if tail is not None else 0.0
+    if losses:
+        total += torch.stack([l.detach().double().reshape(()) for l in losses]).sum().item()
+    avg_loss = total / num_images_processed if num_images_processed else float("nan")
     mean_dice, mean_iou, mean_acc = agg.compute_epoch_metrics()
     per_class_iou = agg.get_last_per_class_iou()
     print(f"\n--- Evaluation Complete ---")

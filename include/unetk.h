@@ -32,6 +32,8 @@ extern "C" {
 
 #define UNETK_F32 0
 #define UNETK_BF16 1
+#define UNETK_U8 2   /* label buffers only */
+#define UNETK_I64 3  /* label buffers only */
 
 #define UNETK_OK 0
 #define UNETK_ERR_INVALID (-1)   /* bad argument / unsupported shape */
@@ -224,6 +226,46 @@ int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
  * counts[4][C] (tp, fp, fn, tn; int64) are ACCUMULATED; argmax_out (optional) receives the hard mask. */
 int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
                            int32_t w, int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream);
+
+/* ---- evaluation tail (utils/utils.py:51-75,101-115; utils/training.py:93-101) ------------------- */
+/* One entry per image of a batch (device array).  The network output [N,C,TH,TW] holds image i in the window
+ * [crop_top, crop_top+crop_h) x [crop_left, crop_left+crop_w) (meta["pad"], meta["new_size"] of
+ * resize_with_padding, utils/utils.py:42-47); (out_h, out_w) is meta["original_size"].  `offset` is the index of
+ * the image's first pixel in the packed label buffer (and, times C, in the packed output of unetk_crop_resize,
+ * where image i is stored as [C,out_h,out_w]). */
+typedef struct unetk_eval_image {
+  int32_t crop_top, crop_left, crop_h, crop_w;
+  int32_t out_h, out_w;
+  int64_t offset;
+} unetk_eval_image;
+
+/* process_batch_reverse (utils/utils.py:101-115): crop + F.interpolate(mode 0 'bilinear', align_corners=False |
+ * mode 1 'nearest') of every image of the batch in one launch.  max_out_pixels = max_i out_h*out_w. */
+int unetk_crop_resize(const float* src_nchw, int32_t n, int32_t c, int32_t th, int32_t tw,
+                      const unetk_eval_image* images, int32_t max_out_pixels, int32_t mode, float* out_packed,
+                      void* stream);
+
+/* eval_loop body (utils/training.py:93-101) for a whole batch: per image, the bilinear-resized logits are reduced
+ * to the Dice+CE loss of WeightedDiceCELoss (batch of one, as the reference calls it) and to argmax confusion
+ * counts, without materialising the resized logits. */
+typedef struct unetk_eval_args {
+  const float* logits; /* NCHW fp32 [N,C,TH,TW] */
+  int32_t n, c, th, tw;
+  const unetk_eval_image* images; /* device [N] */
+  int32_t max_out_pixels;
+  const void* labels;  /* packed, image i at element images[i].offset */
+  int32_t label_dtype; /* UNETK_U8 | UNETK_I64 */
+  const float* class_weights; /* NULL or [C] */
+  int32_t has_ignore;
+  int64_t ignore_index;
+  float dice_weight, ce_weight, smooth;
+  double* accum;         /* [N][3C+2] zeroed by the caller */
+  float* loss_per_image; /* [N] written */
+  double* loss_sum;      /* NULL or [1]: += sum_i (double)loss_i, in image order (total_loss += loss.item()) */
+  int64_t* counts;       /* [4][C] tp, fp, fn, tn ACCUMULATED (MetricsHistory.accumulate) */
+  int32_t* status;       /* |= 1 if a label is outside [0,C) */
+} unetk_eval_args;
+int unetk_eval_loss_metrics(const unetk_eval_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -170,6 +170,68 @@ def gen_curve(ref):
     np.savez_compressed(os.path.join(OUT, "curve.npz"), **out)
 
 
+def gen_eval(ref):
+    """Evaluation tail through the reference's own eval_loop / process_batch_reverse (utils/training.py:67-121,
+    utils/utils.py:13-115): a stub model returns fixed logits so the fixture pins exactly the crop + bilinear
+    resize + per-image loss + confusion counts, not the network."""
+    assert ref.training_mod is not None, getattr(ref, "training_error", None)
+    import contextlib, io
+    tm = ref.training_mod
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    target, c, ign = 48, 4, 3
+    sizes = [[(37, 53), (48, 48), (80, 45)], [(31, 97), (64, 40)]]
+    w = torch.tensor(CLASS_W4)
+    loss_fn = ref.WeightedDiceCELoss(smooth_dice=1, class_weights=w, ignore_index=ign)
+    batches, all_logits = [], []
+    for bi, szs in enumerate(sizes):
+        X = [torch.rand(3, h, ww, generator=g) for h, ww in szs]
+        y = [torch.randint(0, c, (1, h, ww), generator=g).to(torch.uint8) if i % 2 == 0 else
+             torch.randint(0, c, (h, ww), generator=g) for i, (h, ww) in enumerate(szs)]
+        logits = torch.randn(len(szs), c, target, target, generator=g) * 2
+        logits[:, 1, ::5, ::3] = logits[:, 0, ::5, ::3]          # exact ties survive interpolation where taps coincide
+        batches.append((X, y))
+        all_logits.append(logits)
+        out[f"logits_{bi}"] = logits.numpy()
+        for i, lab in enumerate(y):
+            out[f"label_{bi}_{i}"] = lab.numpy()
+        Xp, metas = tm.process_batch_forward(X, target_size=target)
+        out[f"xproc_digest_{bi}"] = tensor_digest(Xp)
+        out[f"xproc_{bi}"] = Xp.numpy().astype(np.float32)
+        for i, img in enumerate(X):
+            out[f"x_{bi}_{i}"] = img.numpy()
+        out[f"meta_{bi}"] = np.array(json.dumps(metas))
+        for mode in ("bilinear", "nearest"):
+            rev = tm.process_batch_reverse(logits, metas, interpolation=mode)
+            for i, r in enumerate(rev):
+                out[f"rev_{mode}_{bi}_{i}"] = r.numpy()
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.k = 0
+
+        def forward(self, x):
+            r = all_logits[self.k]
+            self.k += 1
+            return r
+
+    agg = ref.MetricsHistory(c, ign)
+    with contextlib.redirect_stdout(io.StringIO()):
+        avg_loss, mean_dice, mean_iou = tm.eval_loop(batches, Stub(), loss_fn, torch.device("cpu"), target, agg)
+    out["result"] = np.array([avg_loss, mean_dice, mean_iou])
+    out["counts"] = np.stack([agg.total_tp.numpy(), agg.total_fp.numpy(), agg.total_fn.numpy(), agg.total_tn.numpy()])
+    # per-image losses, as the loop computes them
+    per = []
+    for (X, y), logits in zip(batches, all_logits):
+        _, metas = tm.process_batch_forward(X, target_size=target)
+        for pred, label in zip(tm.process_batch_reverse(logits, metas, interpolation="bilinear"), y):
+            per.append(loss_fn(pred.unsqueeze(0), label.long().unsqueeze(0).squeeze(1)).item())
+    out["per_image_loss"] = np.array(per)
+    out["cfg"] = np.array(json.dumps(dict(target=target, c=c, ignore_index=ign, sizes=sizes, smooth_dice=1.0)))
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), **out)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(8)
@@ -178,6 +240,7 @@ def main():
     gen_loss(ref)
     gen_metrics(ref)
     gen_curve(ref)
+    gen_eval(ref)
     with open(os.path.join(OUT, "meta.json"), "w") as f:
         json.dump(dict(torch=torch.__version__, threads=torch.get_num_threads(),
                        reference="in5omnia/Image_Segmentation @ /root/reference (unmodified, CPU)"), f, indent=1)

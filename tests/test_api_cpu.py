@@ -59,6 +59,8 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(L.BnBwdArgs) == 3 * 32 + 5 * 8 + 32 + 24
     assert ctypes.sizeof(L.BnFinalizeArgs) == 8 * 2 + 8 + 4 + 4 + 6 * 8 + 8 + 4 * 8
     assert ctypes.sizeof(L.DiceCeArgs) == 8 * 2 + 16 + 8 + 8 + 8 + 16 + 8 * 6
+    assert ctypes.sizeof(L.EvalImage) == 32
+    assert ctypes.sizeof(L.EvalArgs) == 136      # static_assert'ed on the C side (csrc/eval.cu)
 
 
 def test_no_cpu_fallback():
@@ -89,5 +91,6 @@ def test_batch_helpers_identity_at_training_resolution():
     small = [torch.rand(3, 20, 30), torch.rand(3, 32, 16)]
     out, metas = process_batch_forward(small, target_size=32)
     assert out.shape == (2, 3, 32, 32)
-    back = process_batch_reverse(out, metas)
-    assert [tuple(b.shape) for b in back] == [(3, 20, 30), (3, 32, 16)]
+    assert [m["original_size"] for m in metas] == [(20, 30), (32, 16)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        process_batch_reverse(out, metas)            # the reverse transform is a CUDA kernel, there is no CPU path

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import loss_oracle, metrics_oracle, ref_shim, unet_oracle
+from oracle import eval_oracle, loss_oracle, metrics_oracle, ref_shim, unet_oracle
 from image_segmentation_b200.utils.synthetic import make_batch
 
 CLASS_W4 = [0.2046795970925636, 1.0271954434416883, 1.2293222812780409, 1.5388026781877073]
@@ -186,3 +186,41 @@ def test_native_ops_variant_equals_closed_form():
     np.testing.assert_allclose(ya.detach().numpy(), yb.detach().numpy(), rtol=1e-9, atol=1e-11)
     for (ka, va), (kb, vb) in zip(a.reference_state_dict().items(), b.reference_state_dict().items()):
         np.testing.assert_allclose(va.double().numpy(), vb.double().numpy(), rtol=1e-9, atol=1e-12, err_msg=ka)
+
+
+def test_eval_tail_oracle_matches_reference_golden(golden):
+    """oracle/eval_oracle.py against the reference's process_batch_forward/reverse + eval_loop (gen_eval)."""
+    g = golden["eval"]
+    cfg = json.loads(str(g["cfg"]))
+    kw = dict(smooth_dice=cfg["smooth_dice"], class_weights=torch.tensor(CLASS_W4), ignore_index=cfg["ignore_index"])
+    batches = []
+    for bi, szs in enumerate(cfg["sizes"]):
+        metas = json.loads(str(g[f"meta_{bi}"]))
+        for i, (h, w) in enumerate(szs):
+            m = eval_oracle.resize_meta(h, w, cfg["target"])
+            assert tuple(m["new_size"]) == tuple(metas[i]["new_size"]) and tuple(m["pad"]) == tuple(metas[i]["pad"])
+            assert m["scale"] == metas[i]["scale"]
+            for mode, tol in (("bilinear", 2e-6), ("nearest", 0.0)):
+                r = eval_oracle.crop_resize(g[f"logits_{bi}"][i], metas[i], mode)
+                np.testing.assert_allclose(r, g[f"rev_{mode}_{bi}_{i}"], rtol=0, atol=tol)
+        batches.append((g[f"logits_{bi}"], metas, [g[f"label_{bi}_{i}"] for i in range(len(szs))]))
+    avg, md, mi, counts = eval_oracle.eval_epoch(batches, cfg["c"], kw, cfg["ignore_index"])
+    np.testing.assert_array_equal(counts.astype(np.float64), g["counts"])
+    np.testing.assert_allclose([avg, md, mi], g["result"], rtol=1e-6)
+    per = np.concatenate([eval_oracle.eval_batch(*b, cfg["c"], kw)[0] for b in batches])
+    np.testing.assert_allclose(per, g["per_image_loss"], rtol=2e-6)
+
+
+def test_process_batch_forward_matches_reference_golden(golden):
+    """Host-side input preparation (resize with antialiasing + centred zero padding, utils/utils.py:13-49,77-99)."""
+    from image_segmentation_b200.utils.utils import process_batch_forward
+    g = golden["eval"]
+    cfg = json.loads(str(g["cfg"]))
+    for bi, szs in enumerate(cfg["sizes"]):
+        X = [torch.from_numpy(g[f"x_{bi}_{i}"]) for i in range(len(szs))]
+        Xp, metas = process_batch_forward(X, target_size=cfg["target"])
+        np.testing.assert_allclose(Xp.numpy(), g[f"xproc_{bi}"], rtol=0, atol=1e-6)
+        want = json.loads(str(g[f"meta_{bi}"]))
+        for m, w in zip(metas, want):
+            assert tuple(m["pad"]) == tuple(w["pad"]) and tuple(m["new_size"]) == tuple(w["new_size"])
+            assert tuple(m["original_size"]) == tuple(w["original_size"]) and m["scale"] == w["scale"]
