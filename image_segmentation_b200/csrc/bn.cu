@@ -158,6 +158,11 @@ __global__ void __launch_bounds__(kThreads)
 // ------------------------------------------------------------------------------------------------
 // backward: dy = (dA_full + routed pool grad) * [a > 0]
 // ------------------------------------------------------------------------------------------------
+// [a > 0] for the activation the forward pass STORED, a = T(max(z*sc + sh, 0)), decided without redoing the rounding:
+// a float v rounds to a positive T exactly when v > threshold (bf16: values up to 2^-134 round to zero, ties to even).
+template <typename T> __device__ __forceinline__ float act_threshold() { return 0.f; }
+template <> __device__ __forceinline__ float act_threshold<__nv_bfloat16>() { return 0x1p-134f; }
+
 template <typename T>
 struct BwdSrc {
   const T* z; int zld;
@@ -196,10 +201,7 @@ __device__ __forceinline__ void load_pixel(const BwdSrc<T>& s, int64_t pix, int 
     for (int k = 0; k < 8; ++k) d[k] += (((arg >> (2 * k)) & 3u) == q) ? dp[k] : 0.f;
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float act = round_to<T>(fmaxf(fmaf(zv[k], sc[k], sh[k]), 0.f));
-    dy[k] = act > 0.f ? d[k] : 0.f;
-  }
+  for (int k = 0; k < 8; ++k) dy[k] = fmaf(zv[k], sc[k], sh[k]) > act_threshold<T>() ? d[k] : 0.f;
 }
 
 // POOL: two horizontally adjacent pixels (2*xp, 2*xp+1) of one pooling window share the window's pooled gradient and
@@ -231,10 +233,8 @@ __device__ __forceinline__ void load_pixel_pair(const BwdSrc<T>& s, int64_t pair
     const uint32_t a = (arg >> (2 * k)) & 3u;
     const float ga = da[k] + (a == q0 ? dp[k] : 0.f);
     const float gb = db[k] + (a == q0 + 1u ? dp[k] : 0.f);
-    const float aa = round_to<T>(fmaxf(fmaf(za[k], sc[k], sh[k]), 0.f));
-    const float ab = round_to<T>(fmaxf(fmaf(zb[k], sc[k], sh[k]), 0.f));
-    ya[k] = aa > 0.f ? ga : 0.f;
-    yb[k] = ab > 0.f ? gb : 0.f;
+    ya[k] = fmaf(za[k], sc[k], sh[k]) > act_threshold<T>() ? ga : 0.f;
+    yb[k] = fmaf(zb[k], sc[k], sh[k]) > act_threshold<T>() ? gb : 0.f;
   }
 }
 

@@ -221,11 +221,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
   const bool bnred = p.bn_sums != nullptr;
   const bool do_stats = p.stat_sum != nullptr || bnred;
   const int col0 = n_tile * BLOCK_N;
-  int map_idx = 0, ch0 = col0;
-  if (p.mode == 2) {
-    map_idx = col0 / p.cout;
-    ch0 = col0 % p.cout;
-  }
   if (do_stats && st.n_tile != n_tile) {
     st.flush(p, lane);
     st.n_tile = n_tile;
@@ -234,48 +229,59 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
   const uint32_t srow = sbase + row * 128;
 #pragma unroll
   for (int blk = 0; blk < BLOCK_N / 64; ++blk) {
-    if (storer) tma_store_wait_read<0>();   // the previous store out of this staging block has been read
-    named_bar_sync(bar_id, 128);
-    if (bnred && storer) {
-      // z tile of the layer whose gradient this is (same pixels / channels as the output block), 128B-swizzled like staging
-      mbar_arrive_expect_tx(zbar, kStagingBytes);
-      tma_load_4d(zbuf, &p.map_z, zbar, ch0 + blk * 64, w0, h0, n0);
+    // first output channel of this 64-wide block; ConvT fprop (mode 2): column = (quadrant, channel), one store map per
+    // quadrant, so an N tile may span several quadrants
+    int map_idx = 0, chb = col0 + blk * 64;
+    if (p.mode == 2) {
+      map_idx = chb / p.cout;
+      chb -= map_idx * p.cout;
     }
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32(tmem_acc + blk * 64, r0);
-    tmem_ld_32x32(tmem_acc + blk * 64 + 32, r1);
-    tmem_ld_wait();
-    if (blk == BLOCK_N / 64 - 1) {
-      // accumulator fully drained: hand the TMEM stage back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+    if (bnred) {
+      named_bar_sync(bar_id, 128);   // every thread is done with the previous z block
+      if (storer) {
+        // z tile of the layer whose gradient this is (same pixels / channels as the output block), 128B-swizzled like staging
+        mbar_arrive_expect_tx(zbar, kStagingBytes);
+        tma_load_4d(zbuf, &p.map_z, zbar, chb, w0, h0, n0);
       }
     }
+    uint32_t packed[32];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      uint32_t packed[16];
+      // 32 columns at a time: at most 32 raw + 32 packed registers live
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_acc + blk * 64 + half * 32, r);
+      tmem_ld_wait();
+      if (half == 1 && blk == BLOCK_N / 64 - 1) {
+        // accumulator fully drained: hand the TMEM stage back to the MMA warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(tmem_empty_bar, 0); else mbar_arrive(tmem_empty_bar);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float lo = __uint_as_float(half ? r1[2 * j] : r0[2 * j]);
-        float hi = __uint_as_float(half ? r1[2 * j + 1] : r0[2 * j + 1]);
+        float lo = __uint_as_float(r[2 * j]), hi = __uint_as_float(r[2 * j + 1]);
         if (HAS_BIAS) {
-          lo += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j);
-          hi += __ldg(p.bias + ch0 + blk * 64 + half * 32 + 2 * j + 1);
+          lo += __ldg(p.bias + chb + half * 32 + 2 * j);
+          hi += __ldg(p.bias + chb + half * 32 + 2 * j + 1);
         }
-        packed[j] = valid_row ? pack_bf16x2(lo, hi) : 0u;
+        packed[half * 16 + j] = valid_row ? pack_bf16x2(lo, hi) : 0u;
       }
+    }
+    // the TMEM read and the conversion above overlap the TMA store of the previous block, which must have finished
+    // READING the staging block before it is overwritten
+    if (storer) tma_store_wait_read<0>();
+    named_bar_sync(bar_id, 128);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t chunk = (uint32_t)(half * 4 + j) ^ (uint32_t)(row & 7);
-        st_shared_v4(srow + chunk * 16, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t chunk = (uint32_t)j ^ (uint32_t)(row & 7);
+      st_shared_v4(srow + chunk * 16, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
     fence_proxy_async_smem();
     named_bar_sync(bar_id, 128);
     if (storer) {
-      tma_store_4d(&p.map_y[map_idx], staging, ch0 + blk * 64, w0, h0, n0);
+      tma_store_4d(&p.map_y[map_idx], staging, chb, w0, h0, n0);
       tma_store_commit();
     }
     if (do_stats) {
@@ -285,7 +291,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint8_t* stag
       const uint32_t cgrp = (uint32_t)lane >> 2;
       if (bnred) {
         // BatchNorm-backward reduction: dy = dA * [relu(z*scale+shift) > 0]; accumulate sum dy and sum dy*z
-        const int ch = ch0 + blk * 64 + 2 * lane;
+        const int ch = chb + 2 * lane;
         const float sc0 = __ldg(p.bn_scale + ch), sc1 = __ldg(p.bn_scale + ch + 1);
         const float sh0 = __ldg(p.bn_shift + ch), sh1 = __ldg(p.bn_shift + ch + 1);
         const uint32_t zbase = smem_u32(zbuf) + (uint32_t)(lane & 3) * 4 + (uint32_t)(q * 32) * 128;
@@ -1510,7 +1516,9 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   memset(&p, 0, sizeof(p));
   int rc;
   // N tile: the widest of 256/128/64 that divides the channel count of one output slice
-  const int nslice = g.cout;  // mode 2: a tile must stay inside one (a,b) quadrant
+  // (mode 2: columns are (quadrant, channel); the epilogue picks the store map per 64-column block, so a tile may span
+  // quadrants and ConvT 128->64 runs as ONE N = 256 tile instead of four N = 64 tiles that each re-read the input)
+  const int nslice = g.cout_total;
   const int block_n = nslice % 256 == 0 ? 256 : (nslice % 128 == 0 ? 128 : 64);
   const int b_bytes = block_n * kBlockK * 2;
   const int64_t ktotal = (int64_t)g.taps * g.cin;
