@@ -107,8 +107,18 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 // [0] producer wait(empty A) [1] mma wait(full A) [2] mma wait(full B) [3] mma wait(tmem empty) [4] mma total
 // [5] epilogue g0 wait(tmem full) [6] epilogue g0 inside epilogue_tile [7] epilogue g0 total
 __device__ long long g_dbg[160 * 8];
+// (compiled in only with -DUNETK_DEBUG_COUNTERS; the default build carries no clock reads in the role loops)
+#ifdef UNETK_DEBUG_COUNTERS
+constexpr bool kDbg = true;
 #define DBG_T0() const long long _t0 = clock64()
 #define DBG_ADD(var) var += clock64() - _t0
+#define DBG_NOW() clock64()
+#else
+constexpr bool kDbg = false;
+#define DBG_T0() do { } while (0)
+#define DBG_ADD(var) do { } while (0)
+#define DBG_NOW() 0LL
+#endif
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                    // bf16 elements per K step = one 128-byte swizzle row
@@ -364,7 +374,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars bars(smem + p.off_bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int ksteps = p.taps * p.chunks_per_tap;
   const int stages = p.stages;
@@ -409,8 +420,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, one elected lane per instruction) =====================
+    {   // whole warp, converged: operands stay warp-uniform, one elected lane issues (see umma_bf16_warp)
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -430,15 +441,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_warp(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&bars.empty_a[stage]);
+          umma_commit_warp(&bars.empty_a[stage]);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&bars.tmem_full[acc]);
+        umma_commit_warp(&bars.tmem_full[acc]);
       }
     }
     __syncwarp();
@@ -497,7 +508,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars bars(smem + p.off_bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
@@ -566,8 +578,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, single thread) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA; whole warp, one elected lane per instruction) =====================
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -586,14 +598,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
           const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2sm(&bars.empty_a[stage]);
+            umma_bf16_2sm_warp(d_tmem, da + 2 * k, db + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm_warp(&bars.empty_a[stage]);
           if (++stage == stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&bars.tmem_full[acc]);
+        umma_commit_2sm_warp(&bars.tmem_full[acc]);
       }
     }
     __syncwarp();
@@ -640,7 +652,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars bars(smem + p.off_bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int cpt = p.chunks_per_tap;
   const int a_stages = p.stages, b_slots = p.b_slots;
@@ -697,18 +710,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
         }
         first = false;
       }
-      if (blockIdx.x < 160) g_dbg[blockIdx.x * 8 + 0] = dbg_a;
+      if (kDbg && lane == 0 && blockIdx.x < 160) g_dbg[blockIdx.x * 8 + 0] = dbg_a;
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: operands stay warp-uniform, one elected lane issues (see umma_bf16_warp)
       constexpr uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
       long long dbg_fa = 0, dbg_fb = 0, dbg_te = 0;
-      const long long dbg_start = clock64();
+      const long long dbg_start = DBG_NOW();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -750,29 +763,29 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
             const uint64_t db = make_smem_desc(smem_u32(smem + p.off_b + bslot * kBBytes), 0, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_warp(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
             if (!resident) {
-              umma_commit(&bars.empty_b[sb]);
+              umma_commit_warp(&bars.empty_b[sb]);
               if (++sb == b_slots) {
                 sb = 0;
                 pb ^= 1;
               }
             }
           }
-          umma_commit(&bars.empty_a[sa]);
+          umma_commit_warp(&bars.empty_a[sa]);
           if (++sa == a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-        umma_commit(&bars.tmem_full[acc]);
+        umma_commit_warp(&bars.tmem_full[acc]);
         first = false;
       }
-      if (blockIdx.x < 160) {
+      if (kDbg && lane == 0 && blockIdx.x < 160) {
         g_dbg[blockIdx.x * 8 + 1] = dbg_fa;
         g_dbg[blockIdx.x * 8 + 2] = dbg_fb;
         g_dbg[blockIdx.x * 8 + 3] = dbg_te;
-        g_dbg[blockIdx.x * 8 + 4] = clock64() - dbg_start;
+        g_dbg[blockIdx.x * 8 + 4] = DBG_NOW() - dbg_start;
       }
     }
     __syncwarp();
@@ -782,7 +795,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
     const int row = q * 32 + lane;
     const int pw_i = row & 7, ph_i = row >> 3;
     long long dbg_tf = 0, dbg_epi = 0;
-    const long long dbg_start = clock64();
+    const long long dbg_start = DBG_NOW();
     uint8_t* staging = smem + p.off_staging + g * kStagingBytes;
     uint8_t* zbuf = smem + p.off_zbuf + g * kStagingBytes;
     uint32_t zphase = 0;
@@ -809,10 +822,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_halo_kernel(const __g
         DBG_ADD(dbg_epi);
       }
     }
-    if (g == 0 && q == 0 && lane == 0 && blockIdx.x < 160) {
+    if (kDbg && g == 0 && q == 0 && lane == 0 && blockIdx.x < 160) {
       g_dbg[blockIdx.x * 8 + 5] = dbg_tf;
       g_dbg[blockIdx.x * 8 + 6] = dbg_epi;
-      g_dbg[blockIdx.x * 8 + 7] = clock64() - dbg_start;
+      g_dbg[blockIdx.x * 8 + 7] = DBG_NOW() - dbg_start;
     }
     if (p.stat_sum || p.bn_sums) st.flush(p, lane);
     if (q == 0 && lane == 0) tma_store_wait_all();
@@ -838,7 +851,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Bars bars(smem + p.off_bars);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
@@ -917,14 +931,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
       long long dbg_fa = 0, dbg_fb = 0, dbg_te = 0;
-      const long long dbg_start = clock64();
+      const long long dbg_start = DBG_NOW();
       for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -965,29 +979,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
             const uint64_t db = make_smem_desc(smem_u32(smem + p.off_b + bslot * kBHalfBytes), 0, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16_2sm_warp(d_tmem, da + 2 * k, db + 2 * k, idesc, (chunk > 0 || tap > 0 || k > 0) ? 1u : 0u);
             if (!resident) {
-              umma_commit_2sm(&bars.empty_b[sb]);
+              umma_commit_2sm_warp(&bars.empty_b[sb]);
               if (++sb == b_slots) {
                 sb = 0;
                 pb ^= 1;
               }
             }
           }
-          umma_commit_2sm(&bars.empty_a[sa]);
+          umma_commit_2sm_warp(&bars.empty_a[sa]);
           if (++sa == a_stages) {
             sa = 0;
             pa ^= 1;
           }
         }
-        umma_commit_2sm(&bars.tmem_full[acc]);
+        umma_commit_2sm_warp(&bars.tmem_full[acc]);
         first = false;
       }
-      if (blockIdx.x < 160) {
+      if (kDbg && lane == 0 && blockIdx.x < 160) {
         g_dbg[blockIdx.x * 8 + 1] = dbg_fa;
         g_dbg[blockIdx.x * 8 + 2] = dbg_fb;
         g_dbg[blockIdx.x * 8 + 3] = dbg_te;
-        g_dbg[blockIdx.x * 8 + 4] = clock64() - dbg_start;
+        g_dbg[blockIdx.x * 8 + 4] = DBG_NOW() - dbg_start;
       }
     }
     __syncwarp();
@@ -1066,7 +1080,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // work item = (cu tile, cs tile, tap, split)
   const int num_items = p.cu_tiles * p.cs_tiles * p.taps * p.splits;
 
@@ -1138,7 +1153,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: operands stay warp-uniform, one elected lane issues (see umma_bf16_warp)
       // M = 128 always; with a single 64-channel slab the descriptor's slab stride is 0 and rows 64..127 of the
       // accumulator duplicate rows 0..63 (ignored by the epilogue)
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
@@ -1166,15 +1181,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < kTileM / 16; ++k) {
             // 16 pixels = 16 rows of 128 B = 2048 bytes: +128 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+            umma_bf16_warp(d_tmem, da + 128 * k, db + 128 * k, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_warp(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        umma_commit_warp(&tmem_full_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -1240,7 +1255,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int num_items = p.cu_tiles * p.cs_tiles * 3 * p.splits;
 
   if (warp == 0 && lane == 0) {
@@ -1301,7 +1317,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    {   // whole warp, converged: operands stay warp-uniform, one elected lane issues (see umma_bf16_warp)
       // a single 64-channel slab runs as an M = 64 MMA (tools/umma_probe.cu: accumulator row r then lives in TMEM lane
       // (r/16)*32 + r%16, i.e. the first 16 lanes of every 32-lane quadrant)
       constexpr uint32_t idesc = make_idesc_bf16(BM_SLABS == 2 ? 128 : 64, BLOCK_N, 1, 1);
@@ -1329,15 +1345,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
             // K block k = image rows 2k, 2k+1 of the patch: U rows 16k..16k+15; band rows (2k)*10 .. , next row +1280 B
             const uint64_t da = make_smem_desc(su + k * 2048, lbo_a, 1024);
             const uint64_t db = make_smem_desc(sband + k * 2560, 128, 1280);
-            umma_bf16(d_tmem, da, db, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+            umma_bf16_warp(d_tmem, da, db, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_warp(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
+        umma_commit_warp(&tmem_full_bar[acc]);
       }
     }
     __syncwarp();

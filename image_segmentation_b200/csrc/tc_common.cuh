@@ -110,6 +110,32 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-collective forms: EVERY lane of a converged warp makes the call with identical (warp-uniform) operands and one
+// elected lane issues.  This is how the MMA warp must issue: from a single-lane branch (`if (lane == 0)`) the compiler
+// cannot prove the descriptors uniform and wraps every UTCHMMA in an ELECT / BRA.U.ANY waterfall loop, which caps
+// the issue rate at one MMA per ~95-115 cycles whatever its shape (tools/umma_rate.cu: N=256 171 -> 128 cycles,
+// N=128 107 -> 64, N=64 93 -> 48 with the warp-uniform form).
+__device__ __forceinline__ void umma_bf16_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -193,6 +219,30 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+// warp-collective forms of the pair instructions (see umma_bf16_warp)
+__device__ __forceinline__ void umma_bf16_2sm_warp(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)),
       "h"((uint16_t)3)
       : "memory");
 }
