@@ -510,7 +510,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   Bars bars(smem + p.off_bars);
   // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // rank in the (2,1,1) cluster == %cluster_ctarank; taken from blockIdx so the compiler knows it is uniform (an asm
+  // output is treated as thread-varying and would put every UTCHMMA of the leader branch in a waterfall loop)
+  const uint32_t rank = blockIdx.x & 1u;
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
@@ -853,7 +855,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   Bars bars(smem + p.off_bars);
   // warp index made provably warp-uniform for the compiler (role branches and everything computed in them stay uniform)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  // rank in the (2,1,1) cluster == %cluster_ctarank; taken from blockIdx so the compiler knows it is uniform (an asm
+  // output is treated as thread-varying and would put every UTCHMMA of the leader branch in a waterfall loop)
+  const uint32_t rank = blockIdx.x & 1u;
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
@@ -937,24 +941,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
-      long long dbg_fa = 0, dbg_fb = 0, dbg_te = 0;
-      const long long dbg_start = DBG_NOW();
       for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        {
-          DBG_T0();
-          mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
-          DBG_ADD(dbg_te);
-        }
+        mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int chunk = 0; chunk < cpt; ++chunk) {
-          {
-            DBG_T0();
-            mbar_wait(&bars.full_a[sa], pa);
-            DBG_ADD(dbg_fa);
-          }
+          mbar_wait(&bars.full_a[sa], pa);
           tcgen05_fence_after();
           const uint32_t halo = smem_u32(smem + sa * kHaloStride);
           for (int tap = 0; tap < 9; ++tap) {
@@ -967,11 +961,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
               }
             } else {
               bslot = sb;
-              {
-                DBG_T0();
-                mbar_wait(&bars.full_b[sb], pb);
-                DBG_ADD(dbg_fb);
-              }
+              mbar_wait(&bars.full_b[sb], pb);
               tcgen05_fence_after();
             }
             const uint32_t a0 = halo + ((tap / 3) * 10 + (tap % 3)) * 128;
@@ -996,12 +986,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
         }
         umma_commit_2sm_warp(&bars.tmem_full[acc]);
         first = false;
-      }
-      if (kDbg && lane == 0 && blockIdx.x < 160) {
-        g_dbg[blockIdx.x * 8 + 1] = dbg_fa;
-        g_dbg[blockIdx.x * 8 + 2] = dbg_fb;
-        g_dbg[blockIdx.x * 8 + 3] = dbg_te;
-        g_dbg[blockIdx.x * 8 + 4] = DBG_NOW() - dbg_start;
       }
     }
     __syncwarp();
@@ -1540,7 +1524,10 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   const int64_t ktotal = (int64_t)g.taps * g.cin;
   const int cpt = g.cin / 64;
   // halo variant: 3x3, N tile <= 128 (the layers whose operand traffic is L2-bound), image at least one tile big
-  const bool halo = a->mode == 1 && block_n <= 128 && g.rows_h >= 16 && g.rows_w >= 8 && !halo_disabled();
+  // halo reuse also for N = 256 (CTA pairs): measured 5-9% faster on the deep layers once the MMA issue path was fixed
+  // (the per-tap pair kernel is then bound by L2->SMEM operand traffic, which the halo tile cuts by ~40%)
+  static const bool halo_n256 = !(getenv("UNETK_HALO_N256") && getenv("UNETK_HALO_N256")[0] == '0');
+  const bool halo = a->mode == 1 && (block_n <= 128 || halo_n256) && g.rows_h >= 16 && g.rows_w >= 8 && !halo_disabled();
   PixelTile pt;
   if (halo) {
     pt.pw = 8; pt.ph = 16; pt.nb = 1;
@@ -1563,12 +1550,13 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   } else {
     if ((rc = make_act_map(&p.map_y[0], a->y, pt.pw, pt.ph, pt.nb, 1, 0, 0))) return rc;
   }
-  // CTA pairs (cta_group::2) for the per-tap kernel when there are enough pixel tiles to pair up
-  // Measured on B200 (batch 64): pairs gain 4-10% on the per-tap kernel (N = 256, long main loops) but LOSE 10-30% on the
-  // halo kernel (N <= 128: ~2-5k cycle main loops per tile cannot amortise the cross-CTA accumulator hand-off), so the
-  // halo kernel stays single-CTA unless UNETK_HALO_PAIR=1 asks for the experiment.
-  static const bool halo_pair = getenv("UNETK_HALO_PAIR") && getenv("UNETK_HALO_PAIR")[0] == '1';
-  const bool pair = !pair_disabled() && pt.num_tiles() >= 2 && (!halo || halo_pair);
+  // CTA pairs (cta_group::2) whenever there are at least two pixel tiles: each CTA then loads only half of the weight rows
+  // per K step.  Measured on B200 (batch 64) with the warp-uniform MMA issue: pairs gain 4-10% on the per-tap kernel and
+  // 8-17% on the halo kernel (N <= 128).  (Before the issue path was fixed the halo kernel LOST 10-30% with pairs: the
+  // single-lane waterfall issue was the bottleneck and the leader CTA had to issue for both.)  UNETK_HALO_PAIR=0 and
+  // UNETK_NO_PAIR=1 keep the single-CTA kernels reachable for experiments.
+  static const bool halo_pair = !(getenv("UNETK_HALO_PAIR") && getenv("UNETK_HALO_PAIR")[0] == '0');
+  const bool pair = !pair_disabled() && pt.num_tiles() >= 2 && (!halo || halo_pair || (halo_n256 && block_n == 256));
   if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, pair ? block_n / 2 : block_n))) return rc;
   p.mode = a->mode;
   p.taps = g.taps;
