@@ -68,6 +68,13 @@ class DiceCeArgs(C.Structure):
 UNETK_U8, UNETK_I64 = 2, 3      # label dtypes (include/unetk.h)
 
 
+class HeadBnBwdArgs(C.Structure):
+    _fields_ = [("z", Tensor), ("dlogits", C.c_void_p), ("w_head", C.c_void_p), ("dout", C.c_int32),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("sums", C.c_void_p), ("dz", Tensor), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+                ("dw_head", C.c_void_p), ("db_head", C.c_void_p)]
+
+
 class EvalImage(C.Structure):
     _fields_ = [("crop_top", C.c_int32), ("crop_left", C.c_int32), ("crop_h", C.c_int32), ("crop_w", C.c_int32),
                 ("out_h", C.c_int32), ("out_w", C.c_int32), ("offset", C.c_int64)]
@@ -117,6 +124,8 @@ def lib():
             "unetk_dice_ce_fwd": [P(DiceCeArgs), vp],
             "unetk_dice_ce_bwd": [P(DiceCeArgs), vp],
             "unetk_argmax_confusion": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp],
+            "unetk_head_bn_bwd_reduce": [P(HeadBnBwdArgs), vp],
+            "unetk_head_bn_bwd_apply": [P(HeadBnBwdArgs), vp],
             "unetk_crop_resize": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp],
             "unetk_eval_loss_metrics": [P(EvalArgs), vp],
         }
@@ -134,6 +143,7 @@ EXPORTED_SYMBOLS = (
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
+    "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply",
 )
 
 
@@ -298,6 +308,15 @@ def head_fprop(a, w, b, dout, logits):
 def head_bwd(dlogits, a, w, dout, da, dw, db):
     _run("head", 1, 0, lib().unetk_head_bwd, dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
          dw.data_ptr(), ptr(db), stream_ptr())
+
+
+def head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head, db_head):
+    """Head backward fused with the BatchNorm backward of the block that feeds the head (two launches)."""
+    a = HeadBnBwdArgs(nhwc(z), dlogits.data_ptr(), w_head.data_ptr(), dout, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                      ptr(sums), nhwc(dz), ptr(dgamma), ptr(dbeta), ptr(dw_head), ptr(db_head))
+    s = stream_ptr()
+    _run("bn_bwd_reduce", 1, 0, lib().unetk_head_bn_bwd_reduce, C.byref(a), s)
+    _run("bn_bwd_apply", 1, 0, lib().unetk_head_bn_bwd_apply, C.byref(a), s)
 
 
 def dice_ce_fwd(args):

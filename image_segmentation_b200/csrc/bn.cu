@@ -411,6 +411,250 @@ static int check_bwd(const unetk_bn_bwd_args* a) {
   return UNETK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Classifier head backward fused with the BatchNorm backward of the layer that feeds it.
+// The head is a 1x1 conv  logits[p][k] = sum_c a[p][c] * Wh[k][c] + bh[k]  with  a = relu(z*scale + shift)  (the stored
+// activation of the last block).  Given dlogits (NCHW fp32) both passes recompute, per pixel and channel,
+//   da = sum_k dlogits[k] * Wh[k][c],   dy = da * [a > 0]
+// so the gradient of the 64-channel activation is never written to or read from HBM:
+//   reduce : reads z + dlogits     -> sum dy, sum dy*xhat, dWh[k][c] = sum_p dlogits[k]*a[c], dbh[k] = sum_p dlogits[k]
+//   apply  : reads z + dlogits     -> writes dz (and dgamma, dbeta, dWh, dbh from the fp64 sums)
+// versus head_bwd (read a, write da) + bn_bwd_reduce (read z, da) + bn_bwd_apply (read z, da, write dz): 3.2 instead of
+// 7 passes over a [N,H,W,64] tensor.
+// ------------------------------------------------------------------------------------------------
+static_assert(sizeof(unetk_head_bn_bwd_args) == 160, "ABI layout (see _lib.py)");
+
+template <int DOUT>
+struct HeadGrad {
+  const float* dl;    // [N, DOUT, H, W]
+  uint32_t hw;
+  float w[DOUT][8];   // this thread's 8 channels of the head weight
+  __device__ __forceinline__ void load_w(const float* wh, int c, int g) {
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) load8(wh + (size_t)k * c + g * 8, w[k]);
+  }
+  __device__ __forceinline__ void load_d(int64_t pix, float (&d)[DOUT]) const {
+    const uint32_t p32 = (uint32_t)pix, img = p32 / hw, off = p32 - img * hw;
+    const float* b = dl + ((size_t)img * DOUT) * hw + off;
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) d[k] = __ldg(b + (size_t)k * hw);
+  }
+};
+
+// 16/32-byte raw loads kept in registers so that several pixels' loads are in flight before any is consumed
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(u[i] << 16);
+      v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+
+constexpr int kHeadUnroll = 4;   // pixels in flight per thread
+
+// Reduction pass.  With mask = [z*scale+shift > 0] only two families of sums are accumulated per pixel,
+//   M[k][c] = sum_p mask * dlogits[p][k]          Z[k][c] = sum_p mask * dlogits[p][k] * z[p][c]
+// and everything else follows per channel at the end (a = mask * (z*scale + shift), da = sum_k dlogits[k] * Wh[k][c]):
+//   sum dy   = sum_k Wh[k][c] * M[k][c]           sum dy*z = sum_k Wh[k][c] * Z[k][c]
+//   dWh[k][c] = scale[c] * Z[k][c] + shift[c] * M[k][c]
+template <typename T, int DOUT>
+__global__ void __launch_bounds__(kThreads, 2)
+    head_bn_bwd_reduce_kernel(const T* __restrict__ z, int zld, int c, int64_t npix, const float* __restrict__ scale,
+                              const float* __restrict__ shift, const float* __restrict__ mean,
+                              const float* __restrict__ invstd, HeadGrad<DOUT> hg, const float* __restrict__ wh, int cgb,
+                              int items_per_block, double* __restrict__ sums) {
+  const int rows = kThreads / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int cg0 = blockIdx.x * cgb;
+  const int g = cg0 + lane_g;
+  const int64_t i0 = (int64_t)blockIdx.y * items_per_block, i1 = min(i0 + (int64_t)items_per_block, npix);
+  float sc[8], sh[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+  float M[DOUT][8], Z[DOUT][8], accb[DOUT];
+#pragma unroll
+  for (int k = 0; k < DOUT; ++k) {
+    accb[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) M[k][j] = Z[k][j] = 0.f;
+  }
+  for (int64_t it = i0 + row; it < i1; it += (int64_t)kHeadUnroll * rows) {
+    Raw8<T> raw[kHeadUnroll];
+    float d[kHeadUnroll][DOUT];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      const int64_t p = it + (int64_t)u * rows;
+      if (p < i1) {
+        raw[u].load(z + p * zld + g * 8);
+        hg.load_d(p, d[u]);
+      } else {
+        raw[u].zero();
+#pragma unroll
+        for (int k = 0; k < DOUT; ++k) d[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      float zv[8];
+      raw[u].unpack(zv);
+#pragma unroll
+      for (int k = 0; k < DOUT; ++k) accb[k] += d[u][k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool pos = fmaf(zv[j], sc[j], sh[j]) > act_threshold<T>();
+#pragma unroll
+        for (int k = 0; k < DOUT; ++k) {
+          const float m = pos ? d[u][k] : 0.f;
+          M[k][j] += m;
+          Z[k][j] = fmaf(m, zv[j], Z[k][j]);
+        }
+      }
+    }
+  }
+  // rows of acc: sum dy | sum dy*xhat | dWh[k] (DOUT rows) | dbh (entries 0..DOUT-1 of the first channel group only)
+  float acc[3 + DOUT][8];
+  {
+    float mu[8], is[8];
+    load8(mean + g * 8, mu);
+    load8(invstd + g * 8, is);
+    hg.load_w(wh, c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < DOUT; ++k) {
+        s1 = fmaf(hg.w[k][j], M[k][j], s1);
+        s2 = fmaf(hg.w[k][j], Z[k][j], s2);
+        acc[2 + k][j] = fmaf(sc[j], Z[k][j], sh[j] * M[k][j]);
+      }
+      acc[0][j] = s1;
+      acc[1][j] = is[j] * (s2 - mu[j] * s1);
+      // bias gradient: the g == 0 column of threads sees every pixel of the block exactly once
+      acc[2 + DOUT][j] = (g == 0 && j < DOUT) ? accb[j < DOUT ? j : 0] : 0.f;
+    }
+  }
+  double* outs[3 + DOUT];
+#pragma unroll
+  for (int q = 0; q < 3 + DOUT; ++q) outs[q] = sums + (size_t)q * c;
+  block_channel_reduce<3 + DOUT>(acc, cgb, row, lane_g, rows, cg0, outs);
+}
+
+template <typename T, int DOUT>
+__global__ void __launch_bounds__(kThreads, 2)
+    head_bn_bwd_apply_kernel(const T* __restrict__ z, int zld, int c, int64_t npix, const float* __restrict__ scale,
+                             const float* __restrict__ shift, const float* __restrict__ mean,
+                             const float* __restrict__ invstd, HeadGrad<DOUT> hg, const float* __restrict__ wh, int cgb,
+                             int items_per_block, const double* __restrict__ sums, double inv_count, T* __restrict__ dz,
+                             int dzld, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dwh,
+                             float* __restrict__ dbh) {
+  const int rows = kThreads / cgb;
+  const int lane_g = threadIdx.x % cgb, row = threadIdx.x / cgb;
+  const int g = blockIdx.x * cgb + lane_g;
+  const int64_t i0 = (int64_t)blockIdx.y * items_per_block, i1 = min(i0 + (int64_t)items_per_block, npix);
+  float sc[8], sh[8], cb[8], cc[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+  hg.load_w(wh, c, g);
+  {
+    float mu[8], is[8];
+    load8(mean + g * 8, mu);
+    load8(invstd + g * 8, is);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float m1 = (float)(sums[g * 8 + k] * inv_count);
+      const float m2 = (float)(sums[c + g * 8 + k] * inv_count);
+      cb[k] = -sc[k] * m2 * is[k];
+      cc[k] = sc[k] * (m2 * is[k] * mu[k] - m1);
+    }
+  }
+  if (blockIdx.y == 0 && row == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (dgamma) dgamma[g * 8 + k] = (float)sums[c + g * 8 + k];
+      if (dbeta) dbeta[g * 8 + k] = (float)sums[g * 8 + k];
+#pragma unroll
+      for (int q = 0; q < DOUT; ++q) dwh[(size_t)q * c + g * 8 + k] = (float)sums[(size_t)(2 + q) * c + g * 8 + k];
+    }
+    if (g == 0 && dbh) {
+#pragma unroll
+      for (int q = 0; q < DOUT; ++q) dbh[q] = (float)sums[(size_t)(2 + DOUT) * c + q];
+    }
+  }
+  // dz = scale*dy + cb*z + cc with dy = mask * sum_k dlogits[k]*Wh[k][c]: fold scale into the head weights
+#pragma unroll
+  for (int k = 0; k < DOUT; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hg.w[k][j] *= sc[j];
+  for (int64_t it = i0 + row; it < i1; it += (int64_t)kHeadUnroll * rows) {
+    Raw8<T> raw[kHeadUnroll];
+    float d[kHeadUnroll][DOUT];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      const int64_t p = it + (int64_t)u * rows;
+      if (p < i1) {
+        raw[u].load(z + p * zld + g * 8);
+        hg.load_d(p, d[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      const int64_t p = it + (int64_t)u * rows;
+      if (p < i1) {
+        float zv[8], o[8];
+        raw[u].unpack(zv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float da = 0.f;
+#pragma unroll
+          for (int k = 0; k < DOUT; ++k) da = fmaf(d[u][k], hg.w[k][j], da);
+          const float base = fmaf(cb[j], zv[j], cc[j]);
+          o[j] = fmaf(zv[j], sc[j], sh[j]) > act_threshold<T>() ? base + da : base;
+        }
+        store8(dz + p * dzld + g * 8, o);
+      }
+    }
+  }
+}
+
+static int check_head_bn(const unetk_head_bn_bwd_args* a) {
+  UNETK_REQUIRE(a != nullptr, "head_bn_bwd: null args");
+  UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "head_bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
+  UNETK_REQUIRE(a->dlogits && a->w_head && a->scale && a->shift && a->mean && a->invstd && a->sums,
+                "head_bn_bwd: null pointer");
+  UNETK_REQUIRE(pixels(a->z) < (1LL << 31), "head_bn_bwd: more than 2^31 pixels");
+  if (a->dout < 1 || a->dout > 4) {
+    set_error("head_bn_bwd: fused path supports 1..4 classes, got %d (use unetk_head_bwd + unetk_bn_relu_bwd_*)", a->dout);
+    return UNETK_ERR_UNSUPPORTED;
+  }
+  return UNETK_OK;
+}
+
+#define UNETK_DISPATCH_DOUT(dout, D, ...)   \
+  switch (dout) {                           \
+    case 1: { constexpr int D = 1; __VA_ARGS__ } break; \
+    case 2: { constexpr int D = 2; __VA_ARGS__ } break; \
+    case 3: { constexpr int D = 3; __VA_ARGS__ } break; \
+    default: { constexpr int D = 4; __VA_ARGS__ } break; \
+  }
+
 }  // namespace unetk
 
 using namespace unetk;
@@ -521,6 +765,58 @@ int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream) {
       bn_bwd_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
     else
       bn_bwd_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(s, cgb, ipb, s1, s2, inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta);
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream) {
+  int rc = check_head_bn(a);
+  if (rc) return rc;
+  const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
+  const int64_t npix = pixels(a->z);
+  int ipb = rows * 64;
+  if ((npix + ipb - 1) / ipb > 65535) ipb *= 16;
+  UNETK_REQUIRE((npix + ipb - 1) / ipb <= 65535, "head_bn_bwd_reduce: tensor too large");
+  dim3 grid(cg / cgb, (unsigned)((npix + ipb - 1) / ipb));
+  UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
+    UNETK_DISPATCH_DOUT(a->dout, D, {
+      HeadGrad<D> hg;
+      hg.dl = a->dlogits;
+      hg.hw = (uint32_t)(a->z.h * a->z.w);
+      const size_t smem = (size_t)(3 + D) * rows * cgb * 8 * sizeof(float);
+      if (smem > 48 * 1024)
+        UNETK_CUDA(cudaFuncSetAttribute(head_bn_bwd_reduce_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      head_bn_bwd_reduce_kernel<T, D><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+          (const T*)a->z.ptr, a->z.ld, a->z.c, npix, a->scale, a->shift, a->mean, a->invstd, hg, a->w_head, cgb, ipb, a->sums);
+    });
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream) {
+  int rc = check_head_bn(a);
+  if (rc) return rc;
+  UNETK_REQUIRE(tensor_ok(a->dz) && vec8_ok(a->dz) && a->dz.dtype == a->z.dtype && a->dz.n == a->z.n &&
+                    a->dz.h == a->z.h && a->dz.w == a->z.w && a->dz.c == a->z.c, "head_bn_bwd_apply: dz must match z");
+  UNETK_REQUIRE(a->dw_head != nullptr, "head_bn_bwd_apply: dw_head required");
+  const int cg = a->z.c / 8, cgb = choose_cgb(cg), rows = kThreads / cgb;
+  const int64_t npix = pixels(a->z);
+  int ipb = rows * 16;
+  if ((npix + ipb - 1) / ipb > 65535) ipb *= 16;
+  UNETK_REQUIRE((npix + ipb - 1) / ipb <= 65535, "head_bn_bwd_apply: tensor too large");
+  dim3 grid(cg / cgb, (unsigned)((npix + ipb - 1) / ipb));
+  const double inv_count = 1.0 / (double)npix;
+  UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
+    UNETK_DISPATCH_DOUT(a->dout, D, {
+      HeadGrad<D> hg;
+      hg.dl = a->dlogits;
+      hg.hw = (uint32_t)(a->z.h * a->z.w);
+      head_bn_bwd_apply_kernel<T, D><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const T*)a->z.ptr, a->z.ld, a->z.c, npix, a->scale, a->shift, a->mean, a->invstd, hg, a->w_head, cgb, ipb, a->sums,
+          inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta, a->dw_head, a->db_head);
+    });
   });
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;

@@ -168,7 +168,10 @@ class UNetPlan:
             off += c
         self._tot_c = tot_c
         # backward reduction sums [2][C] per layer, contiguous per layer
-        self.bwd64 = torch.zeros(2 * tot_c, dtype=torch.float64, device=dev)
+        # + the sums of the fused head/BatchNorm backward: (3 + dout) rows of the last block's channel count
+        self.head_rows = 3 + self.dout
+        self.bwd64 = torch.zeros(2 * tot_c + self.head_rows * ENC_CH[0], dtype=torch.float64, device=dev)
+        self.head_sums = self.bwd64[2 * tot_c:]
         off = 0
         for l in self.layers:
             l.bwd_sums = self.bwd64[off:off + 2 * l.cout]
@@ -352,8 +355,12 @@ class UNetPlan:
         self.flat_grad = flat
         dlogits = dlogits.contiguous()
 
-        L.head_bwd(dlogits, self.head_in, m.output.weight, self.dout, self.g_head_in, g[m.output.weight], g[m.output.bias])
-        if bucket_hook:
+        # head backward: fused with the BatchNorm backward of the last block when the class count allows it
+        fuse_head = self.dout <= 4 and os.environ.get("UNETK_FUSE_HEAD", "1") == "1"
+        if not fuse_head:
+            L.head_bwd(dlogits, self.head_in, m.output.weight, self.dout, self.g_head_in, g[m.output.weight],
+                       g[m.output.bias])
+        if bucket_hook and not fuse_head:
             bucket_hook(self, self.grad_offsets[2])
 
         main = torch.cuda.current_stream()
@@ -379,12 +386,19 @@ class UNetPlan:
             """Arguments that make a data-gradient launch also accumulate layer l's BatchNorm-backward reductions."""
             return (l.z, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums) if fuse else None
 
-        def conv_bn_bwd(l: _ConvBN, dy, dpool=None, reduced=False, feeds: Optional[_ConvBN] = None):
+        def conv_bn_bwd(l: _ConvBN, dy, dpool=None, reduced=False, feeds: Optional[_ConvBN] = None, from_head=False):
             """`reduced`: this layer's reductions were already fused into the launch that produced `dy`;
-            `feeds`: the layer whose activated-output gradient this layer's dgrad produces (no pooling in between)."""
+            `feeds`: the layer whose activated-output gradient this layer's dgrad produces (no pooling in between);
+            `from_head`: l feeds the classifier head and dy is never materialised (fused head + BatchNorm backward)."""
             L.LABEL = l.name
-            L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight], g[l.bn.bias],
-                          pool_idx=l.pool_idx if dpool is not None else None, reduced=reduced and fuse)
+            if from_head:
+                L.head_bn_bwd(dlogits, l.z, m.output.weight, self.dout, l.scale, l.shift, l.mean, l.invstd, self.head_sums,
+                              l.dz, g[l.bn.weight], g[l.bn.bias], g[m.output.weight], g[m.output.bias])
+                if bucket_hook:
+                    bucket_hook(self, self.grad_offsets[2])
+            else:
+                L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight],
+                              g[l.bn.bias], pool_idx=l.pool_idx if dpool is not None else None, reduced=reduced and fuse)
             if l.first:
                 on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo,
                                         algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout))
@@ -403,7 +417,7 @@ class UNetPlan:
             l1, l2 = self.dec[i]
             # grad_a2 comes from the head (i == 3) or from the ConvTranspose data gradient of the level above, which
             # already accumulated l2's reductions
-            conv_bn_bwd(l2, grad_a2, reduced=(i != 3), feeds=l1)
+            conv_bn_bwd(l2, grad_a2, reduced=(i != 3), feeds=l1, from_head=(i == 3 and fuse_head))
             conv_bn_bwd(l1, l2.g_in, reduced=True)
             ct = self.convts[i]
             L.LABEL = ct.name

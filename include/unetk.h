@@ -227,6 +227,31 @@ int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
 int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
                            int32_t w, int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream);
 
+/* ---- head backward fused with the BatchNorm backward of the last block (unet/unet.py:91 <- :21-25) ----------- */
+/* z is the raw conv output of the layer whose activation a = relu(z*scale+shift) feeds the 1x1 head.  Both passes
+ * recompute da = dlogits . w_head per pixel, so the [N,H,W,C] activation gradient never touches memory.
+ * sums: [(3+dout)*C] doubles zeroed by the caller: sum dy | sum dy*xhat | dW_head[k][c] (dout rows) | db_head[k] in the
+ * first dout entries of the last row.
+ * dout 1..4 (UNETK_ERR_UNSUPPORTED otherwise: use unetk_head_bwd + unetk_bn_relu_bwd_*). */
+typedef struct unetk_head_bn_bwd_args {
+  unetk_tensor z;
+  const float* dlogits; /* NCHW fp32 [N,dout,H,W] */
+  const float* w_head;  /* [dout][C] */
+  int32_t dout;
+  const float* scale;
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  double* sums;
+  unetk_tensor dz; /* apply only */
+  float* dgamma;   /* apply only, [C] (may be NULL) */
+  float* dbeta;
+  float* dw_head;  /* apply only, [dout][C] */
+  float* db_head;  /* apply only, [dout] (may be NULL) */
+} unetk_head_bn_bwd_args;
+int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream);
+int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream);
+
 /* ---- evaluation tail (utils/utils.py:51-75,101-115; utils/training.py:93-101) ------------------- */
 /* One entry per image of a batch (device array).  The network output [N,C,TH,TW] holds image i in the window
  * [crop_top, crop_top+crop_h) x [crop_left, crop_left+crop_w) (meta["pad"], meta["new_size"] of

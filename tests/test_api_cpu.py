@@ -59,6 +59,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(L.BnBwdArgs) == 3 * 32 + 5 * 8 + 32 + 24
     assert ctypes.sizeof(L.BnFinalizeArgs) == 8 * 2 + 8 + 4 + 4 + 6 * 8 + 8 + 4 * 8
     assert ctypes.sizeof(L.DiceCeArgs) == 8 * 2 + 16 + 8 + 8 + 8 + 16 + 8 * 6
+    assert ctypes.sizeof(L.HeadBnBwdArgs) == 32 + 8 + 8 + 8 + 4 * 8 + 8 + 32 + 4 * 8
     assert ctypes.sizeof(L.EvalImage) == 32
     assert ctypes.sizeof(L.EvalArgs) == 136      # static_assert'ed on the C side (csrc/eval.cu)
 

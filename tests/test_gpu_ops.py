@@ -250,16 +250,67 @@ def test_head_forward_backward(dt, dout):
     assert relerr(db, br.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 12, 20, 64), (4, 3, 6, 10, 128), (3, 1, 64, 64, 64)])
+def test_fused_head_and_batchnorm_backward(dt, dout, n, h, w, c):
+    """unetk_head_bn_bwd_reduce/apply against autograd (float64) through  z -> BN(batch stats) -> ReLU -> 1x1 head."""
+    z = rnd((n, h, w, c), dt, 60)
+    gamma = rnd((c,), torch.float32, 61).abs() + 0.5
+    beta = rnd((c,), torch.float32, 62, 0.3)
+    wh = rnd((dout, c, 1, 1), torch.float32, 63, 0.2)
+    bh = rnd((dout,), torch.float32, 64)
+    dl = rnd((n, dout, h, w), torch.float32, 65)
+    zr = nhwc_to_nchw(z.double()).requires_grad_(True)
+    gr, br_ = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    whr, bhr = wh.double().requires_grad_(True), bh.double().requires_grad_(True)
+    a = F.relu(F.batch_norm(zr, None, None, gr, br_, training=True, eps=1e-5))
+    F.conv2d(a, whr, bhr).backward(dl.double())
+    mean = z.double().mean((0, 1, 2))
+    var = z.double().var((0, 1, 2), unbiased=False)
+    invstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale = (gamma.double() * invstd).float().to(DEV)
+    shift = (beta.double() - mean * gamma.double() * invstd).float().to(DEV)
+    sums = torch.zeros((3 + dout) * c, dtype=torch.float64, device=DEV)
+    dz = torch.empty((n, h, w, c), dtype=dt, device=DEV)
+    dgamma, dbeta = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
+    dwh, dbh = torch.empty(dout, c, device=DEV), torch.empty(dout, device=DEV)
+    L.head_bn_bwd(dl.to(DEV), z.to(DEV), wh.to(DEV), dout, scale, shift, mean.float().to(DEV), invstd.float().to(DEV), sums,
+                  dz, dgamma, dbeta, dwh, dbh)
+    tol = TOL[dt]
+    assert relerr(dz, zr.grad.permute(0, 2, 3, 1)) < tol
+    assert relerr(dgamma, gr.grad) < tol and relerr(dbeta, br_.grad) < tol
+    assert relerr(dwh, whr.grad.view(dout, c)) < tol
+    assert relerr(dbh, bhr.grad) < 1e-5
+    if c != 64:
+        return
+    # and against the unfused head kernel on the same inputs (the U-Net head has 64 input channels)
+    a_dev = torch.empty((n, h, w, c), dtype=dt, device=DEV)
+    L.bn_relu_apply(z.to(DEV), scale, shift, a_dev, None, None)
+    da = torch.empty((n, h, w, c), dtype=dt, device=DEV)
+    dw2, db2 = torch.zeros(dout, c, device=DEV), torch.zeros(dout, device=DEV)
+    L.head_bwd(dl.to(DEV), a_dev, wh.to(DEV), dout, da, dw2, db2)
+    assert relerr(dwh, dw2) < tol and relerr(dbh, db2) < 1e-5
+
+
+def test_fused_head_rejects_more_than_four_classes():
+    z = torch.zeros((1, 4, 4, 64), dtype=torch.float32, device=DEV)
+    f = torch.zeros(64, device=DEV)
+    with pytest.raises(RuntimeError, match="1..4 classes"):
+        L.head_bn_bwd(torch.zeros((1, 5, 4, 4), device=DEV), z, torch.zeros((5, 64), device=DEV), 5, f, f, f, f,
+                      torch.zeros(8 * 64, dtype=torch.float64, device=DEV), torch.empty_like(z), f.clone(), f.clone(),
+                      torch.zeros((5, 64), device=DEV), torch.zeros(5, device=DEV))
+
+
 def test_im2col_first_and_permute3():
-    n, cin, h, w = 2, 3, 8, 8
-    x = rnd((n, cin, h, w), torch.float32, 50)
-    for dt in (torch.float32, torch.bfloat16):
-        out = torch.empty((n, h, w, 64), dtype=dt, device=DEV)
-        L.im2col3x3_first(x.to(DEV), out)
-        cols = F.unfold(x, 3, padding=1).view(n, cin, 9, h, w)          # [n][ci][t][h][w]
-        ref = torch.zeros(n, h, w, 64)
-        ref[..., :27] = cols.permute(0, 3, 4, 2, 1).reshape(n, h, w, 27)  # k = t*cin + ci
-        assert torch.equal(out.cpu().float(), ref.to(dt).float())
+    for n, cin, h, w in ((2, 3, 8, 8), (2, 3, 5, 150), (1, 4, 70, 67)):     # strips of 64 columns: ragged last strip
+        x = rnd((n, cin, h, w), torch.float32, 50)
+        for dt in (torch.float32, torch.bfloat16):
+            out = torch.empty((n, h, w, 64), dtype=dt, device=DEV)
+            L.im2col3x3_first(x.to(DEV), out)
+            cols = F.unfold(x, 3, padding=1).view(n, cin, 9, h, w)          # [n][ci][t][h][w]
+            ref = torch.zeros(n, h, w, 64)
+            ref[..., :9 * cin] = cols.permute(0, 3, 4, 2, 1).reshape(n, h, w, 9 * cin)  # k = t*cin + ci
+            assert torch.equal(out.cpu().float(), ref.to(dt).float())
     wt = rnd((8, 5, 9), torch.float32, 51)
     dst = torch.empty((5, 9, 8), dtype=torch.float32, device=DEV)
     # [co][ci][t] -> [ci][8-t][co]
