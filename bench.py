@@ -295,7 +295,7 @@ def run_gpu_arm(args):
                 "frac": achieved / peaks["sustained"], "frac_of_burst": achieved / peaks["burst"],
                 "traffic": dominant["traffic_bytes"] if dominant else None,
                 "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a long step)",
-                "kernel": "tc::tc_conv_kernel / tc_conv_halo_kernel / tc_wgrad3x3_kernel (tcgen05 implicit GEMM family)",
+                "kernel": "tc::tc_conv_halo2_kernel / tc_conv2_kernel / tc_wgrad3x3_kernel (tcgen05 implicit GEMM family)",
                 "how": f"sum of algorithmic FLOPs / sum of CUDA-event durations over every unetk_conv and unetk_wgrad launch "
                        f"of {prof_steps} instrumented steps; `traffic` is the ncu DRAM byte count of the dominant launch "
                        "described in `dominant_launch` (profiles/dominant_launch.json)",

@@ -39,6 +39,9 @@ def _stale(out: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a and link libunetk.so next to the package. Returns its path."""
     nvcc = find_nvcc()
+    # UNETK_NVCC_EXTRA="-DUNETK_DEBUG_COUNTERS" builds the instrumented halo kernel (tools/run_layer.py, UNETK_DBG=1)
+    extra = os.environ.get("UNETK_NVCC_EXTRA", "").split()
+    force = force or bool(extra)
     os.makedirs(BUILD_DIR, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(PKG_DIR), "include", "unetk.h"))
@@ -48,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(BUILD_DIR, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
