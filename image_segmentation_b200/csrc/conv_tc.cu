@@ -1381,6 +1381,169 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
   }
 }
 
+// =================================================================================================
+// 3x3 weight gradient for a 64-channel gradient operand (cu == 64: the 256x256 layers), all nine taps per stage.
+// An M = 64 MMA runs at half the tensor rate, so instead of one M=64 x N=192 MMA per kernel row (the kernel above) the
+// second half of an M = 128 tile is filled with the SAME 64 channels one image row further down:
+//     A = [ U(p) ; U(p + 1 row) ]   (MN-major descriptor with LBO = 8 pixels = 1024 B: "atom 1" is the row-shifted view)
+//     D[0:64]   = sum_p U[p]      * S[p + (0, s-1)] = dw[r=1, s]
+//     D[64:128] = sum_p U[p + 1r] * S[p + (0, s-1)] = sum_p' U[p'] * S[p' + (-1, s-1)] = dw[r=0, s]
+// (the terms the shift drops or adds multiply zero padding, so the result is exact) and a second, M = 64 MMA on the
+// view shifted one row UP gives dw[r=2].  All three kernel rows therefore share ONE band of S (16 x 10 pixels) and
+// one 18 x 8 pixel patch of U per 128-pixel block: 38 KB into shared memory per block instead of 3 x 36 KB, and
+// 192 instead of 288 tensor cycles per K step.  Accumulators: 192 + 192 TMEM columns, single buffered (the epilogue of
+// an item -- a few microseconds of fp32 atomics -- no longer overlaps the next item; items last ~100x longer).
+// Work item = (64-channel cs slab, pixel split).
+// =================================================================================================
+constexpr int kUPatchBytes = 18 * 8 * 128;   // 18432: rows h0-1 .. h0+16 of the 8-pixel-wide patch
+
+__global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int kStageBytes = kUPatchBytes + kBandBytes;   // 38912
+  constexpr int kStages = 5;
+  constexpr int BLOCK_N = 192;
+  constexpr uint32_t kTmemCols = 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int num_items = p.cs_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&p.map_u);
+    prefetch_tensormap(&p.map_s[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item % p.splits, cs_t = item / p.splits;
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int tw = pt % p.tiles_w, th = (pt / p.tiles_w) % p.tiles_h, tn = pt / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * 8, h0 = th * 16;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* su = smem + stage * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_4d(su, &p.map_u, &full_bar[stage], 0, w0, h0 - 1, tn);                       // 18 x 8 patch of U
+          tma_load_4d(su + kUPatchBytes, &p.map_s[0], &full_bar[stage], cs_t * 64, w0 - 1, h0, tn);   // band, r = 1
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    {   // whole warp, converged (see umma_bf16_warp)
+      constexpr uint32_t idesc128 = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      constexpr uint32_t idesc64 = make_idesc_bf16(64, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int split = item % p.splits;
+        const int pt0 = split * p.ptiles_per_split;
+        const int pt1 = min(pt0 + p.ptiles_per_split, p.num_ptiles);
+        mbar_wait(tmem_empty_bar, (uint32_t)(it & 1) ^ 1);
+        tcgen05_fence_after();
+        for (int pt = pt0; pt < pt1; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t su = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sband = su + kUPatchBytes;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // K block k = image rows 2k, 2k+1 of the 16 x 8 block.  U patch row j = image row h0-1+j (8 pixels = 1024 B each)
+            const uint64_t db = make_smem_desc(sband + k * 2560, 128, 1280);
+            const uint64_t da_mid = make_smem_desc(su + 1024 + k * 2048, 1024, 1024);   // atoms: rows h0.. and h0+1..
+            const uint64_t da_up = make_smem_desc(su + k * 2048, 0, 1024);              // rows h0-1..
+            const uint32_t accum = (pt > pt0 || k > 0) ? 1u : 0u;
+            umma_bf16_warp(tmem_base, da_mid, db, idesc128, accum);
+            umma_bf16_warp(tmem_base + 256, da_up, db, idesc64, accum);
+          }
+          umma_commit_warp(&empty_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_warp(tmem_full_bar);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int cs_t = item / p.splits;
+      mbar_wait(tmem_full_bar, (uint32_t)(it & 1));
+      tcgen05_fence_after();
+      // accumulator 1 (M = 128): lanes 0..63 = dw[r=1] of channel `lane`, lanes 64..127 = dw[r=0] of channel lane-64
+      {
+        const int cu_idx = row & 63, r = row < 64 ? 1 : 0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, rg);
+          tmem_ld_wait();
+          float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+        }
+      }
+      // accumulator 2 (M = 64): row m lives in TMEM lane (m/16)*32 + m%16 -> dw[r=2]
+      {
+        const int cu_idx = q * 16 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t rg[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + c * 32, rg);
+          tmem_ld_wait();
+          if (lane < 16) {
+            float* dst = p.dw + ((int64_t)cu_idx * 9 + (6 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
 template <int BM_SLABS>
 constexpr int wgrad3x3_smem_bytes() {
   constexpr int stage = BM_SLABS * kABytes + kBandBytes;
@@ -1454,6 +1617,17 @@ static int launch_wgrad3x3(const WgradParams& p, cudaStream_t stream) {
   const int items = p.cu_tiles * p.cs_tiles * 3 * p.splits;
   const int grid = items < sm_count() ? items : sm_count();
   tc_wgrad3x3_kernel<BM_SLABS><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+static int launch_wgrad3x3_c64(const WgradParams& p, cudaStream_t stream) {
+  constexpr int smem_bytes = 5 * (kUPatchBytes + kBandBytes) + 256 + 1024;
+  static int attr_rc = set_smem_attr(tc_wgrad3x3_c64_kernel, smem_bytes);
+  if (attr_rc) return attr_rc;
+  const int items = p.cs_tiles * p.splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  tc_wgrad3x3_c64_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(p);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
@@ -1662,7 +1836,9 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = make_act_map(&p.map_u, a->u, 8, 16, 1, 1, 0, 0))) return rc;
+  static const bool no_c64 = getenv("UNETK_WGRAD_C64") && getenv("UNETK_WGRAD_C64")[0] == '0';
+  const bool c64 = a->u.c == 64 && !no_c64;   // nine taps per stage (tc_wgrad3x3_c64_kernel): U patch with a row of halo
+  if ((rc = make_act_map(&p.map_u, a->u, 8, c64 ? 18 : 16, 1, 1, 0, 0))) return rc;
   if ((rc = make_act_map(&p.map_s[0], a->s, 10, 16, 1, 1, 0, 0))) return rc;
   const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1;
   p.mode = 1;
@@ -1676,10 +1852,11 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   p.cu = a->u.c; p.cs = a->s.c;
   p.cu_tiles = a->u.c / (64 * bm_slabs);
   p.cs_tiles = a->s.c / 64;
-  const int64_t out_tiles = (int64_t)p.cu_tiles * p.cs_tiles * 3;
+  const int64_t out_tiles = c64 ? (int64_t)p.cs_tiles : (int64_t)p.cu_tiles * p.cs_tiles * 3;
   choose_splits(out_tiles, p.num_ptiles, &p.ptiles_per_split, &p.splits);
   UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
   p.dw = a->dw;
+  if (c64) return launch_wgrad3x3_c64(p, stream);
   return bm_slabs == 2 ? launch_wgrad3x3<2>(p, stream) : launch_wgrad3x3<1>(p, stream);
 }
 
