@@ -1197,7 +1197,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4) red_add_v4(dst + c * 32 + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
       }
       tcgen05_fence_before();
@@ -1364,7 +1364,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
           const int s_tap = c >> 1;
           float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + s_tap)) * p.cs + cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+          for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
         }
       }
       tcgen05_fence_before();
@@ -1394,6 +1394,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
 // 192 instead of 288 tensor cycles per K step.  Accumulators: 192 + 192 TMEM columns, single buffered (the epilogue of
 // an item -- a few microseconds of fp32 atomics -- no longer overlaps the next item; items last ~100x longer).
 // Work item = (64-channel cs slab, pixel split).
+// (The same sharing for 128-channel tiles -- two kernel rows per stage, 2 x 192 TMEM columns -- was measured 5-15 % SLOWER
+// than tc_wgrad3x3_kernel<2>: with the accumulators single buffered the reduction epilogue of every item is exposed, and
+// those layers have short items.  Not kept.)
 // =================================================================================================
 constexpr int kUPatchBytes = 18 * 8 * 128;   // 18432: rows h0-1 .. h0+16 of the 8-pixel-wide patch
 
@@ -1512,7 +1515,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const _
           tmem_ld_wait();
           float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+          for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
         }
       }
       // accumulator 2 (M = 64): row m lives in TMEM lane (m/16)*32 + m%16 -> dw[r=2]
@@ -1526,7 +1529,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const _
           if (lane < 16) {
             float* dst = p.dw + ((int64_t)cu_idx * 9 + (6 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rg[j]));
+            for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
           }
         }
       }
