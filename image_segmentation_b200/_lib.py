@@ -124,6 +124,7 @@ def lib():
             "unetk_dice_ce_fwd": [P(DiceCeArgs), vp],
             "unetk_dice_ce_bwd": [P(DiceCeArgs), vp],
             "unetk_argmax_confusion": [vp, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp],
+            "unetk_bn_relu_head_fprop": [P(Tensor), vp, vp, P(Tensor), vp, vp, C.c_int32, vp, vp],
             "unetk_head_bn_bwd_reduce": [P(HeadBnBwdArgs), vp],
             "unetk_head_bn_bwd_apply": [P(HeadBnBwdArgs), vp],
             "unetk_crop_resize": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp],
@@ -143,7 +144,7 @@ EXPORTED_SYMBOLS = (
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
-    "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply",
+    "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply", "unetk_bn_relu_head_fprop",
 )
 
 
@@ -308,6 +309,12 @@ def head_fprop(a, w, b, dout, logits):
 def head_bwd(dlogits, a, w, dout, da, dw, db):
     _run("head", 1, 0, lib().unetk_head_bwd, dlogits.data_ptr(), C.byref(nhwc(a)), w.data_ptr(), dout, C.byref(nhwc(da)),
          dw.data_ptr(), ptr(db), stream_ptr())
+
+
+def bn_relu_head_fprop(z, scale, shift, a, w_head, b_head, dout, logits):
+    """BatchNorm apply + ReLU of the last block fused with the head forward; ``a=None`` skips storing the activation."""
+    _run("bn_apply", 1, 0, lib().unetk_bn_relu_head_fprop, C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(),
+         C.byref(nhwc(a)), w_head.data_ptr(), ptr(b_head), dout, logits.data_ptr(), stream_ptr())
 
 
 def head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head, db_head):

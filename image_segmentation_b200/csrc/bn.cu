@@ -470,6 +470,38 @@ template <> struct Raw8<float> {
 
 constexpr int kHeadUnroll = 4;   // pixels in flight per thread
 
+// BatchNorm apply + ReLU without pooling, four 16-byte loads in flight per thread (the generic kernel above keeps one)
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    bn_relu_apply_stream_kernel(const T* __restrict__ z, int zld, const float* __restrict__ scale,
+                                const float* __restrict__ shift, T* __restrict__ a, int ald, int64_t npix, int cg) {
+  const int64_t total = npix * cg;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // the host makes it a multiple of cg
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)((uint32_t)first % (uint32_t)cg);
+  const uint32_t pstride = (uint32_t)(stride / cg);
+  float sc[8], sh[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+  uint32_t p = (uint32_t)(first / cg);
+  for (int64_t i0 = first; i0 < total; i0 += (int64_t)kHeadUnroll * stride, p += kHeadUnroll * pstride) {
+    Raw8<T> raw[kHeadUnroll];
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u)
+      if (i0 + (int64_t)u * stride < total) raw[u].load(z + (int64_t)(p + u * pstride) * zld + g * 8);
+#pragma unroll
+    for (int u = 0; u < kHeadUnroll; ++u) {
+      if (i0 + (int64_t)u * stride < total) {
+        float v[8];
+        raw[u].unpack(v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
+        store8(a + (int64_t)(p + u * pstride) * ald + g * 8, v);
+      }
+    }
+  }
+}
+
 // Reduction pass.  With mask = [z*scale+shift > 0] only two families of sums are accumulated per pixel,
 //   M[k][c] = sum_p mask * dlogits[p][k]          Z[k][c] = sum_p mask * dlogits[p][k] * z[p][c]
 // and everything else follows per channel at the end (a = mask * (z*scale + shift), da = sum_k dlogits[k] * Wh[k][c]):
@@ -634,6 +666,72 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BatchNorm apply + ReLU of the last block fused with the 1x1 classifier head (unet/unet.py:20-21 -> :91):
+// logits[p][k] = bh[k] + sum_c Wh[k][c] * a[p][c],  a = T(relu(z*scale + shift)).  The C/8 threads that own one pixel
+// are adjacent lanes, so the dot product finishes with log2(C/8) shuffles.  `a` itself is written only on request: with
+// the fused head backward (head_bn_bwd_*) nothing reads it again, which saves a [N,H,W,C] write and the head's read.
+// ------------------------------------------------------------------------------------------------
+// C = 64 (8 channel groups): a warp owns 32 consecutive pixels.  Sub-iteration t covers pixels base + 4t + lane/8 with
+// channel group lane%8 (512 contiguous bytes per load instruction, all eight loads issued before the first is used);
+// the per-pixel dot products are finished with three shuffles and routed so that lane L ends up with the logits of
+// pixel base + L, which makes the NCHW logits stores fully coalesced.
+template <typename T, int DOUT>
+__global__ void __launch_bounds__(kThreads)
+    bn_relu_head_kernel(const T* __restrict__ z, int zld, const float* __restrict__ scale, const float* __restrict__ shift,
+                        T* __restrict__ a, int ald, const float* __restrict__ wh, const float* __restrict__ bh,
+                        float* __restrict__ logits, int64_t npix, uint32_t hw) {
+  constexpr int C = 64;
+  const int lane = threadIdx.x & 31, g = lane & 7, sub = lane >> 3;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float sc[8], sh[8], w[DOUT][8], b[DOUT];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sh);
+#pragma unroll
+  for (int k = 0; k < DOUT; ++k) {
+    load8(wh + (size_t)k * C + g * 8, w[k]);
+    b[k] = bh ? bh[k] : 0.f;
+  }
+  for (int64_t base = warp_id * 32; base < npix; base += nwarps * 32) {
+    Raw8<T> raw[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int64_t p = base + 4 * t + sub;
+      if (p < npix) raw[t].load(z + p * zld + g * 8); else raw[t].zero();
+    }
+    float out[DOUT];
+#pragma unroll
+    for (int k = 0; k < DOUT; ++k) out[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int64_t p = base + 4 * t + sub;
+      float v[8];
+      raw[t].unpack(v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = round_to<T>(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f));
+      if (a && p < npix) store8(a + p * ald + g * 8, v);
+#pragma unroll
+      for (int k = 0; k < DOUT; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(v[j], w[k][j], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        const float routed = __shfl_sync(0xffffffffu, s, (lane & 3) * 8);   // pixel base + 4t + (lane & 3)
+        if ((lane >> 2) == t) out[k] = routed;
+      }
+    }
+    const int64_t p = base + lane;
+    if (p < npix) {
+      const uint32_t p32 = (uint32_t)p, img = p32 / hw, off = p32 - img * hw;
+#pragma unroll
+      for (int k = 0; k < DOUT; ++k) logits[((size_t)img * DOUT + k) * hw + off] = out[k] + b[k];
+    }
+  }
+}
+
 static int check_head_bn(const unetk_head_bn_bwd_args* a) {
   UNETK_REQUIRE(a != nullptr, "head_bn_bwd: null args");
   UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "head_bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
@@ -711,6 +809,9 @@ int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* 
     if (pool)
       bn_relu_apply_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, (T*)pooled->ptr, pooled->ld, pool_idx, z->n, z->h, z->w, cg);
+    else if ((kThreads % cg) == 0 && pixels(*z) < (1LL << 31))
+      bn_relu_apply_stream_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, pixels(*z), cg);
     else
       bn_relu_apply_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)z->ptr, z->ld, scale, shift, (T*)a->ptr, a->ld, nullptr, 0, nullptr, z->n, z->h, z->w, cg);
@@ -816,6 +917,32 @@ int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream) {
       head_bn_bwd_apply_kernel<T, D><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
           (const T*)a->z.ptr, a->z.ld, a->z.c, npix, a->scale, a->shift, a->mean, a->invstd, hg, a->w_head, cgb, ipb, a->sums,
           inv_count, (T*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta, a->dw_head, a->db_head);
+    });
+  });
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
+int unetk_bn_relu_head_fprop(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
+                             const float* w_head, const float* b_head, int32_t dout, float* logits_nchw, void* stream) {
+  UNETK_REQUIRE(z && scale && shift && w_head && logits_nchw, "bn_relu_head_fprop: null argument");
+  UNETK_REQUIRE(tensor_ok(*z) && vec8_ok(*z), "bn_relu_head_fprop: bad z tensor");
+  const bool store_a = a && a->ptr;
+  if (store_a)
+    UNETK_REQUIRE(tensor_ok(*a) && vec8_ok(*a) && a->dtype == z->dtype && a->n == z->n && a->h == z->h && a->w == z->w &&
+                      a->c == z->c, "bn_relu_head_fprop: a must match z");
+  if (dout < 1 || dout > 4 || z->c != 64) {
+    set_error("bn_relu_head_fprop: fused path needs 1..4 classes and C == 64 (use unetk_bn_relu_apply + unetk_head_fprop)");
+    return UNETK_ERR_UNSUPPORTED;
+  }
+  UNETK_REQUIRE(pixels(*z) < (1LL << 31), "bn_relu_head_fprop: more than 2^31 pixels");
+  const int64_t npix = pixels(*z);
+  const int grid = grid_for(npix);   // one thread per pixel: a warp owns 32 pixels per round
+  UNETK_DISPATCH_DTYPE(z->dtype, T, {
+    UNETK_DISPATCH_DOUT(dout, D, {
+      bn_relu_head_kernel<T, D><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const T*)z->ptr, z->ld, scale, shift, store_a ? (T*)a->ptr : nullptr, store_a ? a->ld : 0, w_head, b_head,
+          logits_nchw, npix, (uint32_t)(z->h * z->w));
     });
   });
   UNETK_LAUNCH_CHECK();

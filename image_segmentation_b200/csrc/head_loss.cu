@@ -351,6 +351,7 @@ int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float
   UNETK_REQUIRE(dout * a->c <= 2 * TILE, "head_bwd: dout*cin must be <= 512");
   const size_t es = a->dtype == UNETK_BF16 ? 2 : 4;
   const size_t smem = (size_t)TILE * a->c * es + (size_t)kMaxClasses * TILE * 4 + (size_t)dout * a->c * 4;
+  UNETK_REQUIRE(smem <= 100 * 1024, "head_bwd: activation tile does not fit shared memory (cin * element size too large)");
   const int64_t ntiles = (npix + TILE - 1) / TILE;
   int64_t grid = ntiles < (int64_t)sm_count() * 3 ? ntiles : (int64_t)sm_count() * 3;
   if (grid < 1) grid = 1;

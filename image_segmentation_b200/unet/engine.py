@@ -309,6 +309,12 @@ class UNetPlan:
         L.im2col3x3_first(x, self.xcol)
         n = self.n
 
+        # last block: BatchNorm apply + ReLU fused with the head; its activation is stored only if a later pass reads it
+        # (the unfused head backward for dout > 4)
+        fuse_head = self.dout <= 4 and os.environ.get("UNETK_FUSE_HEAD", "1") == "1"
+        last = self.dec[3][1]
+        logits = torch.empty((n, self.dout, self.h, self.w), dtype=torch.float32, device=self.device)
+
         def conv_bn(l: _ConvBN):
             count = n * l.h * l.w
             L.LABEL = l.name
@@ -322,7 +328,10 @@ class UNetPlan:
                           bn.running_mean if track else None, bn.running_var if track else None,
                           bn.num_batches_tracked if (track and training) else None,
                           momentum, bn.eps, l.scale, l.shift, l.mean, l.invstd)
-            L.bn_relu_apply(l.z, l.scale, l.shift, l.a, l.pooled, l.pool_idx)
+            if l is last and fuse_head:
+                L.bn_relu_head_fprop(l.z, l.scale, l.shift, None, m.output.weight, m.output.bias, self.dout, logits)
+            else:
+                L.bn_relu_apply(l.z, l.scale, l.shift, l.a, l.pooled, l.pool_idx)
 
         for lvl in range(5):
             conv_bn(self.enc[lvl][0])
@@ -333,8 +342,8 @@ class UNetPlan:
             L.conv(ct.src, ct.wf, ct.out, L.MODE_CONVT, bias=ct.mod.bias, algo=self.algo)
             conv_bn(self.dec[i][0])
             conv_bn(self.dec[i][1])
-        logits = torch.empty((n, self.dout, self.h, self.w), dtype=torch.float32, device=self.device)
-        L.head_fprop(self.head_in, m.output.weight, m.output.bias, self.dout, logits)
+        if not fuse_head:
+            L.head_fprop(self.head_in, m.output.weight, m.output.bias, self.dout, logits)
         return logits
 
     # ------------------------------------------------------------------------------------------

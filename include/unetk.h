@@ -227,6 +227,12 @@ int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
 int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
                            int32_t w, int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream);
 
+/* BatchNorm apply + ReLU of the last block fused with the head forward (unet/unet.py:20-21 -> :91).  `a` may be NULL
+ * (or a->ptr NULL): the activation is then not stored at all -- with unetk_head_bn_bwd_* nothing reads it again.
+ * dout 1..4 and C == 64 (the U-Net head), else UNETK_ERR_UNSUPPORTED (use unetk_bn_relu_apply + unetk_head_fprop). */
+int unetk_bn_relu_head_fprop(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
+                             const float* w_head, const float* b_head, int32_t dout, float* logits_nchw, void* stream);
+
 /* ---- head backward fused with the BatchNorm backward of the last block (unet/unet.py:91 <- :21-25) ----------- */
 /* z is the raw conv output of the layer whose activation a = relu(z*scale+shift) feeds the 1x1 head.  Both passes
  * recompute da = dlogits . w_head per pixel, so the [N,H,W,C] activation gradient never touches memory.

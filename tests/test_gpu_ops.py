@@ -292,6 +292,31 @@ def test_fused_head_and_batchnorm_backward(dt, dout, n, h, w, c):
     assert relerr(dwh, dw2) < tol and relerr(dbh, db2) < 1e-5
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 5, 7, 64), (4, 1, 3, 3, 64), (3, 1, 64, 64, 64), (2, 3, 37, 3, 64)])
+def test_fused_bn_relu_head_forward(dt, dout, n, h, w, c):
+    """unetk_bn_relu_head_fprop == unetk_bn_relu_apply followed by unetk_head_fprop (same stored activation)."""
+    z = rnd((n, h, w, c), dt, 70).to(DEV)
+    scale = (rnd((c,), torch.float32, 71).abs() + 0.5).to(DEV)
+    shift = rnd((c,), torch.float32, 72, 0.3).to(DEV)
+    wh = rnd((dout, c, 1, 1), torch.float32, 73, 0.2).to(DEV)
+    bh = rnd((dout,), torch.float32, 74).to(DEV)
+    a_ref = torch.empty((n, h, w, c), dtype=dt, device=DEV)
+    L.bn_relu_apply(z, scale, shift, a_ref, None, None)
+    want = torch.empty((n, dout, h, w), dtype=torch.float32, device=DEV)
+    L.head_fprop(a_ref, wh, bh, dout, want)
+    for store in (False, True):
+        a = torch.zeros((n, h, w, c), dtype=dt, device=DEV) if store else None
+        got = torch.full((n, dout, h, w), float("nan"), dtype=torch.float32, device=DEV)
+        L.bn_relu_head_fprop(z, scale, shift, a, wh, bh, dout, got)
+        assert relerr(got, want) < 1e-5            # same products, different summation order
+        if store:
+            assert torch.equal(a, a_ref)
+    ref = F.conv2d(nhwc_to_nchw(torch.relu(z.double().cpu() * scale.double().cpu() + shift.double().cpu())), wh.double().cpu(),
+                   bh.double().cpu())
+    assert relerr(want, ref) < TOL[dt]
+
+
 def test_fused_head_rejects_more_than_four_classes():
     z = torch.zeros((1, 4, 4, 64), dtype=torch.float32, device=DEV)
     f = torch.zeros(64, device=DEV)
