@@ -14,6 +14,7 @@ import torch
 
 from .. import _lib as L
 from .MetricsHistory import MetricsHistory
+from .prefetch import AsyncScalarReader, DevicePrefetcher
 from .weighted_loss import WeightedDiceCELoss
 from .utils import process_batch_forward, process_batch_reverse
 
@@ -38,31 +39,109 @@ def _progress(iterable, **kw):
     return _tqdm(iterable, **kw)
 
 
+def _graph_eligible(model, loss_fn, optimizer, accumulation_steps, scheduler, device) -> bool:
+    """Whole-step CUDA-graph replay inside train_loop needs: this package's unet + fused loss on a CUDA device, one
+    micro-batch per optimiser step, no LR scheduler, and an optimizer whose step is capturable
+    (``torch.optim.AdamW(..., capturable=True)`` / ``fused=True``).  ``UNETK_TRAIN_GRAPH=0`` turns it off."""
+    from ..unet.unet import unet as _unet
+    from .weighted_loss import WeightedDiceCELoss as _Loss
+    if os.environ.get("UNETK_TRAIN_GRAPH", "1") != "1" or torch.device(device).type != "cuda":
+        return False
+    if accumulation_steps != 1 or scheduler is not None or not isinstance(model, _unet) or not isinstance(loss_fn, _Loss):
+        return False
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        return False
+    return all(g.get("capturable", False) for g in optimizer.param_groups)
+
+
+def _invalidate_weight_packs(model):
+    """Host-side bookkeeping done during an aborted capture (weight-pack versions) must not survive it: the captured
+    pack kernel never ran."""
+    eng = getattr(model, "_engine", None)
+    if eng is not None:
+        for pool in eng.plans.values():
+            for plan in pool:
+                plan._pack_versions = None
+
+
+def _graph_for(model, loss_fn, optimizer, X, y):
+    """Captured step for this (model, loss, optimizer, batch shape); cached on the model across epochs."""
+    from .graph import GraphedTrainStep
+    key = (id(loss_fn), id(optimizer), tuple(X.shape), tuple(y.shape))
+    cached = getattr(model, "_train_graph", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    try:
+        g = GraphedTrainStep(model, loss_fn, optimizer, X, y, metrics=None, warmup=0)
+    except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
+        print(f"[train_loop] CUDA graph capture unavailable, staying eager: {e!r}")
+        _invalidate_weight_packs(model)
+        optimizer.zero_grad(set_to_none=True)
+        return None
+    model._train_graph = (key, g)
+    return g
+
+
 def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device, scheduler=None, target_size=None):
     """One epoch of training with gradient accumulation; returns the mean logged loss per optimiser step."""
     model.train()
     total_loss, processed_batches = 0.0, 0
     num_batches = len(dataloader)
     optimizer.zero_grad()
-    pbar = _progress(enumerate(dataloader), total=num_batches, desc="Training")
+    def host_batches():
+        for X, y in dataloader:
+            if target_size is not None:
+                X, _ = process_batch_forward(X, target_size=target_size)
+                y, _ = process_batch_forward(y, target_size=target_size, interpolation="nearest")
+            yield X, y
+
+    # the copy of batch i+1 overlaps the step on batch i (utils/prefetch.py); results are unchanged
+    if torch.device(device).type == "cuda":
+        batches = DevicePrefetcher(host_batches(), device)
+    else:
+        batches = ((X.to(device), y.to(device).long()) for X, y in host_batches())
+    pbar = _progress(enumerate(batches), total=num_batches, desc="Training")
+    # the logged loss of every optimiser step is read back one step late (AsyncScalarReader): same values, same order
+    reader = AsyncScalarReader(device) if torch.device(device).type == "cuda" else None
+    graph_ok = _graph_eligible(model, loss_fn, optimizer, accumulation_steps, scheduler, device)
+    graphed = None
     for batch_idx, (X, y) in pbar:
-        if target_size is not None:
-            X, _ = process_batch_forward(X, target_size=target_size)
-            y, _ = process_batch_forward(y, target_size=target_size, interpolation="nearest")
-        X = X.to(device, non_blocking=True)
-        y = y.to(device, non_blocking=True).long()
-        pred = model(X)
-        loss = loss_fn(pred, y.squeeze(1))
-        (loss / accumulation_steps).backward()
-        if (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches:
-            optimizer.step()
-            if scheduler:
-                scheduler.step()
-            optimizer.zero_grad()
-            value = loss.item()
+        if graph_ok and batch_idx >= 1 and graphed is None:
+            # the first (eager) step of the epoch doubled as warm-up; from the second batch on the whole step
+            # (forward + loss + backward + optimizer) replays as one CUDA graph -- same kernels, no launch gaps
+            graphed = _graph_for(model, loss_fn, optimizer, X, y)
+            graph_ok = graphed is not None
+        use_graph = graphed is not None and tuple(X.shape) == tuple(graphed.x.shape)
+        step_now = (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches
+        if use_graph:
+            loss = graphed(X, y)                         # optimizer.step() and zero_grad() are part of the graph
+        else:
+            pred = model(X)
+            loss = loss_fn(pred, y.squeeze(1))
+            (loss / accumulation_steps).backward()
+            # drop the autograd graph now: a graph kept alive by `loss` would pin its AccumulateGrad nodes to this
+            # stream and invalidate the CUDA-graph capture of the next step
+            loss = loss.detach()
+            del pred
+            if step_now:
+                optimizer.step()
+                if scheduler:
+                    scheduler.step()
+                optimizer.zero_grad()
+        if step_now:
+            if reader is not None:
+                reader.push(loss)
+                values = reader.ready()
+            else:
+                values = [loss.item()]
+            for value in values:
+                total_loss += value
+                processed_batches += 1
+                pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
+    if reader is not None:
+        for value in reader.drain():
             total_loss += value
             processed_batches += 1
-            pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
     avg_loss = total_loss / processed_batches if processed_batches > 0 else 0
     print(f"Training Avg loss (per effective batch): {avg_loss:>8f}")
     return avg_loss

@@ -231,6 +231,29 @@ def test_train_loop_drop_in_matches_reference_train_loop(golden, capsys):
     assert d.max() < 0.1
 
 
+def test_train_loop_graph_replay_equals_eager(monkeypatch, capsys):
+    """With a capturable optimizer train_loop replays every step after the first as one CUDA graph; the per-epoch
+    losses and the final weights must match the eager loop (same kernels, same order)."""
+    hw, n = 32, 2
+    batches = [make_batch(n, hw, hw, 3, 3, seed=300 + i, labels="learnable") for i in range(5)]
+    loader = [(x, y.to(torch.uint8)) for x, y in batches]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("UNETK_TRAIN_GRAPH", mode)
+        m = build(3, 3, "fp32")
+        opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01, capturable=True)
+        fn = loss_for(3)
+        losses = [train_loop(loader, m, fn, opt, 1, torch.device(DEV), None, hw) for _ in range(3)]
+        assert (getattr(m, "_train_graph", None) is not None) == (mode == "1")
+        res[mode] = (np.array(losses), {k: v.detach().float().cpu() for k, v in m.state_dict().items()})
+    # fp32 atomics make two eager runs differ by ~1e-5 per step already, and 15 AdamW steps amplify that
+    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=0, atol=5e-3)
+    for k, v in res["0"][1].items():
+        if v.dim() == 4 and v.numel() > 10000:           # convolution weights (small BN vectors drift chaotically)
+            assert rel_l2(res["1"][1][k], v) < 5e-2, k
+    assert int(res["1"][1]["down1.doubleConvReLU.1.num_batches_tracked"]) == 15
+
+
 def test_forward_metrics_pipeline_matches_oracle():
     """argmax masks and confusion counts are bit-exact given identical logits."""
     x, y = make_batch(2, 32, 32, 3, 4, seed=9)
