@@ -248,9 +248,10 @@ def run_gpu_arm(args):
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
-    # single GPU: the whole step replays as ONE CUDA graph (image_segmentation_b200.utils.graph); data parallel: eager
+    # the whole step replays as ONE CUDA graph (image_segmentation_b200.utils.graph)
     graphed = None
-    if world == 1 and not args.no_graph:
+    # (data parallel: the bucketed NCCL all-reduces are captured with the step; UNETK_DP_GRAPH=0 keeps N > 1 eager)
+    if not args.no_graph and (world == 1 or os.environ.get("UNETK_DP_GRAPH", "1") == "1"):
         from image_segmentation_b200.utils.graph import GraphedTrainStep
         try:
             L.COUNTERS["launches"] = 0
@@ -351,7 +352,13 @@ def run_gpu_arm(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down without ncclCommDestroy: a live CUDA graph that captured collectives makes destroy_process_group()
+        # hang (seen on 2 x B200).  Every rank has finished its work once the barrier returns; leave immediately.
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
