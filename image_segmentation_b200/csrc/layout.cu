@@ -167,50 +167,62 @@ __global__ void __launch_bounds__(256) im2col_first_kernel_v2(const float* __res
 // memory with coalesced row reads (zeros outside the image), then every thread assembles 8 consecutive K values of a
 // pixel from it and writes 16 bytes; consecutive threads write consecutive 16-byte chunks.  The gather kernel above
 // needed ~12 L1 wavefronts per load instruction and ran at 1.3 TB/s; this one is bound by the im2col write.
-constexpr int kStripW = 64;
+constexpr int kStripW = 64;   // pixels per strip row
+constexpr int kStripH = 4;    // image rows per strip: every input row is staged once per 4 output rows
 constexpr int kMaxFirstCin = 8;
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_first_kernel_v3(const float* __restrict__ x, int n, int cin, int h, int w,
-                                                              T* __restrict__ out, int kpad, int ld) {
-  __shared__ float tile[kMaxFirstCin * 3 * (kStripW + 2)];
+                                                              T* __restrict__ out, int kpad, int ld, int greal) {
+  // tile rows: (ci, r) -> kStripW+2 columns, r = 0 .. kStripH+1; a trailing block of zeros serves the padding K values
+  constexpr int kPitch = kStripW + 2, kRows = kStripH + 2;
+  __shared__ float tile[kMaxFirstCin * kRows * kPitch + kRows * kPitch];
   const int kg = kpad / 8;
-  const int g = threadIdx.x % kg;
-  const int pix_lane = threadIdx.x / kg, lanes = 256 / kg;
-  int off[8];   // offset of K value jj inside the tile for pixel 0 of the strip; -1 = padding column
+  // thread = (pixel of the strip row, REAL channel group gi < greal = ceil(9*cin/8)); it also writes the all-zero groups
+  // gi + greal, gi + 2*greal, ... so that no warp diverges between "gather" and "zero fill" lanes
+  const int gi = threadIdx.x % greal, pix_lane = threadIdx.x / greal, lanes = 256 / greal;
+  const int tile_elems = cin * kRows * kPitch;
+  const int zero_base = tile_elems;
+  for (int e = threadIdx.x; e < kRows * kPitch; e += 256) tile[zero_base + e] = 0.f;
+  int off[8];
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
-    const int k = g * 8 + jj;
+    const int k = gi * 8 + jj;
     if (k < 9 * cin) {
       const int t = k / cin, ci = k % cin;
-      off[jj] = (ci * 3 + t / 3) * (kStripW + 2) + t % 3;
+      off[jj] = (ci * kRows + t / 3) * kPitch + t % 3;
     } else {
-      off[jj] = -1;
+      off[jj] = zero_base;
     }
   }
-  const int strips_w = (w + kStripW - 1) / kStripW;
-  const int64_t strips = (int64_t)n * h * strips_w;
-  const int64_t hw = (int64_t)h * w;
-  const int tile_elems = cin * 3 * (kStripW + 2);
+  const int strips_w = (w + kStripW - 1) / kStripW, strips_h = (h + kStripH - 1) / kStripH;
+  const int64_t strips = (int64_t)n * strips_h * strips_w;
+  const int hw = h * w;
+  const float zeros[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t sidx = blockIdx.x; sidx < strips; sidx += gridDim.x) {
     const int sx = (int)(sidx % strips_w);
-    const int y = (int)((sidx / strips_w) % h);
-    const int64_t img = sidx / ((int64_t)strips_w * h);
-    const int x0 = sx * kStripW;
-    const float* xi = x + img * cin * hw;
-    __syncthreads();   // previous strip fully consumed
+    const int sy = (int)((sidx / strips_w) % strips_h);
+    const int64_t img = sidx / ((int64_t)strips_w * strips_h);
+    const int x0 = sx * kStripW, y0 = sy * kStripH;
+    const float* xi = x + img * cin * (int64_t)hw;
+    __syncthreads();   // previous strip fully consumed (and the zero block written, first time round)
     for (int e = threadIdx.x; e < tile_elems; e += 256) {
-      const int col = e % (kStripW + 2), rc = e / (kStripW + 2);
-      const int r = rc % 3, ci = rc / 3;
-      const int yy = y + r - 1, xx = x0 + col - 1;
-      tile[e] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + ci * hw + (int64_t)yy * w + xx) : 0.f;
+      const int col = e % kPitch, rc = e / kPitch;
+      const int r = rc % kRows, ci = rc / kRows;
+      const int yy = y0 + r - 1, xx = x0 + col - 1;
+      tile[e] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + ci * hw + yy * w + xx) : 0.f;
     }
     __syncthreads();
-    const int64_t p0 = (img * h + y) * (int64_t)w + x0;
-    for (int pl = pix_lane; pl < kStripW && x0 + pl < w; pl += lanes) {
-      float v[8];
+    const int npl = min(kStripW, w - x0), nrow = min(kStripH, h - y0);
+    for (int r = 0; r < nrow; ++r) {
+      T* orow = out + ((img * h + y0 + r) * (int64_t)w + x0) * ld;
+      for (int pl = pix_lane; pl < npl; pl += lanes) {
+        float v[8];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) v[jj] = off[jj] >= 0 ? tile[off[jj] + pl] : 0.f;
-      store8(out + (p0 + pl) * ld + g * 8, v);
+        for (int jj = 0; jj < 8; ++jj) v[jj] = tile[off[jj] + r * kPitch + pl];
+        T* o = orow + (int64_t)pl * ld;
+        store8(o + gi * 8, v);
+        for (int gz = gi + greal; gz < kg; gz += greal) store8(o + gz * 8, zeros);
+      }
     }
   }
 }
@@ -232,11 +244,13 @@ int unetk_im2col3x3_first(const float* x_nchw, int32_t n, int32_t cin, int32_t h
   const int64_t cap = (int64_t)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   const int kg = out->c / 8;
-  if (256 % kg == 0 && cin <= kMaxFirstCin) {
-    int64_t strips = (int64_t)n * h * ((w + kStripW - 1) / kStripW);
+  const int greal = (9 * cin + 7) / 8;   // channel groups that hold real K values
+  if (256 % greal == 0 && cin <= kMaxFirstCin && (int64_t)cin * h * w < (1LL << 31)) {
+    int64_t strips = (int64_t)n * ((h + kStripH - 1) / kStripH) * ((w + kStripW - 1) / kStripW);
     if (strips > cap) strips = cap;
     UNETK_DISPATCH_DTYPE(out->dtype, T, {
-      im2col_first_kernel_v3<T><<<(int)strips, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (T*)out->ptr, out->c, out->ld);
+      im2col_first_kernel_v3<T><<<(int)strips, 256, 0, (cudaStream_t)stream>>>(x_nchw, n, cin, h, w, (T*)out->ptr, out->c, out->ld,
+                                                                              greal);
     });
   } else if (256 % kg == 0) {
     const int lanes = 256 / kg;
