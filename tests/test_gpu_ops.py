@@ -520,3 +520,61 @@ def test_data_gradient_with_fused_bn_backward_reduction(dt, algo, mode, n, h, w,
     y2 = torch.empty_like(y)
     L.conv(x.to(DEV), wt.to(DEV), y2, m, algo=algo)
     assert torch.equal(y, y2)
+
+
+def _guarded(shape, dtype, fill=0.0):
+    """A tensor view with 4096 sentinel elements on either side (out-of-bounds writes become visible)."""
+    n = int(np.prod(shape))
+    base = torch.full((n + 8192,), 12345.0, dtype=dtype, device=DEV)
+    view = base[4096:4096 + n].view(*shape)
+    view.fill_(fill)
+    return base, view
+
+
+def _guards_intact(base, n):
+    return bool((base[:4096] == 12345.0).all()) and bool((base[4096 + n:] == 12345.0).all())
+
+
+def test_new_kernels_do_not_write_outside_their_outputs():
+    """Sentinel regions around every output of the kernels added late in round 1 (compute-sanitizer is not available on
+    the GPU pool): tiled im2col, nine-tap 64-channel wgrad, fused head forward / backward, ragged crop-resize."""
+    # im2col: ragged strip and row remainders
+    n, cin, h, w = 2, 3, 19, 83
+    x = rnd((n, cin, h, w), torch.float32, 80).to(DEV)
+    base, out = _guarded((n, h, w, 64), torch.bfloat16)
+    L.im2col3x3_first(x, out)
+    assert _guards_intact(base, out.numel())
+    # 64-channel 3x3 weight gradient with partial tiles (h, w not multiples of 16 / 8)
+    n, h, w = 2, 40, 20
+    dy = rnd((n, h, w, 64), torch.bfloat16, 81).to(DEV)
+    xa = rnd((n, h, w, 128), torch.bfloat16, 82).to(DEV)
+    base, dw = _guarded((64, 9, 128), torch.float32)
+    L.wgrad(dy, xa, dw, 1, algo=L.ALGO_TC)
+    assert _guards_intact(base, dw.numel())
+    ref = torch.zeros(64, 9, 128, dtype=torch.float64)
+    xp = F.pad(nhwc_to_nchw(xa.double().cpu()), (1, 1, 1, 1))
+    dyc = nhwc_to_nchw(dy.double().cpu())
+    for t in range(9):
+        r, s_ = t // 3, t % 3
+        ref[:, t, :] = torch.einsum("nchw,ndhw->cd", dyc, xp[:, :, r:r + h, s_:s_ + w])
+    assert relerr(dw, ref) < 1e-4
+    # fused head forward / backward
+    n, h, w, c, dout = 2, 9, 11, 64, 3
+    z = rnd((n, h, w, c), torch.bfloat16, 83).to(DEV)
+    vec = [(rnd((c,), torch.float32, 84 + i).abs() + 0.5).to(DEV) for i in range(4)]
+    wh, bh = rnd((dout, c), torch.float32, 90, 0.2).to(DEV), rnd((dout,), torch.float32, 91).to(DEV)
+    base, logits = _guarded((n, dout, h, w), torch.float32)
+    L.bn_relu_head_fprop(z, vec[0], vec[1], None, wh, bh, dout, logits)
+    assert _guards_intact(base, logits.numel())
+    base, dz = _guarded((n, h, w, c), torch.bfloat16)
+    sums = torch.zeros((3 + dout) * c, dtype=torch.float64, device=DEV)
+    dl = rnd((n, dout, h, w), torch.float32, 92).to(DEV)
+    outs = [torch.empty(c, device=DEV), torch.empty(c, device=DEV), torch.empty(dout, c, device=DEV), torch.empty(dout, device=DEV)]
+    L.head_bn_bwd(dl, z, wh, dout, vec[0], vec[1], vec[2], vec[3], sums, dz, *outs)
+    assert _guards_intact(base, dz.numel())
+    # ragged crop-resize
+    from image_segmentation_b200.utils.utils import process_batch_reverse
+    metas = [{"original_size": (33, 21), "new_size": (16, 10), "pad": (3, 0, 3, 0), "scale": 0.5},
+             {"original_size": (7, 50), "new_size": (2, 16), "pad": (0, 7, 0, 7), "scale": 0.3}]
+    res = process_batch_reverse(rnd((2, 4, 16, 16), torch.float32, 93).to(DEV), metas)
+    assert [tuple(r.shape) for r in res] == [(4, 33, 21), (4, 7, 50)] and all(torch.isfinite(r).all() for r in res)
