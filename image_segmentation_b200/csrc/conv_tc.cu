@@ -1,10 +1,12 @@
 // bf16 implicit-GEMM contractions on the 5th-generation tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, 128B swizzle, OOB zero fill = conv padding) -> shared-memory ring
-//   -> tcgen05.mma (one issuing thread, fp32 accumulators in TMEM, double buffered)
-//   -> tcgen05.ld epilogue (bias, bf16 rounding, BatchNorm batch statistics, NHWC / convT-scatter stores).
+//   -> tcgen05.mma (fp32 accumulators in TMEM, double buffered; issued warp-uniformly, see umma_bf16_warp in tc_common.cuh)
+//   -> tcgen05.ld epilogue (bias, bf16 rounding, BatchNorm batch statistics or BatchNorm-backward sums, TMA stores:
+//      NHWC / convT pixel shuffle into the concat slice).
 //
-// Persistent, warp-specialised CTAs (one per SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Persistent, warp-specialised CTAs (one per SM, usually paired into 2-CTA clusters for cta_group::2 MMAs):
+// warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-11 = two epilogue groups
+// (warp w of a group owns TMEM lanes 32*(w%4)..+31; the weight-gradient kernels have one group).
 //
 // Reference call sites replaced: unet/unet.py:16,19 (Conv2d 3x3 p1 forward, and its data gradient with the
 // flipped/transposed weight pack), unet/unet.py:59 (ConvTranspose2d k2 s2 forward / data gradient), and the
@@ -96,8 +98,9 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 
 // =================================================================================================
 // forward-family kernels: y[rows, N] = A[rows, K] * B[N, K]^T, both operands K-major in shared memory
-//   tc_conv_kernel       : one TMA box per (tap, 64-channel chunk) -- every mode
-//   tc_conv_halo_kernel  : 3x3 only; ONE (18 x 10 pixel) halo box per 64-channel chunk feeds all 9 taps through
+//   tc_conv_kernel       : one TMA box per (tap, 64-channel chunk) -- every mode; tc_conv2_kernel = its CTA-pair form
+//   tc_conv_halo2_kernel : the default for 3x3: halo reuse (below) + CTA pairs, every N tile
+//   tc_conv_halo_kernel  : single-CTA halo kernel (one pixel tile, or UNETK_HALO_PAIR=0); 3x3 only; ONE (18 x 10 pixel) halo box per 64-channel chunk feeds all 9 taps through
 //                          row-shifted UMMA descriptors (start + (r*10+s)*128 B, SBO = 10*128 B).  tools/umma_probe.cu
 //                          established on B200 that 128B swizzling is a function of the absolute shared-memory address,
 //                          so shifted starts and a 1280-byte group stride address the TMA-written tile consistently.
