@@ -53,6 +53,11 @@ __global__ void __launch_bounds__(256) permute3_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 constexpr int kWT = 32;
 
+__device__ __forceinline__ void store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b);
+}
+
 template <typename T, bool PACK>
 __global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restrict__ jobs, const int32_t* __restrict__ tiles,
                                                       uint8_t* dst_base) {
@@ -87,22 +92,22 @@ __global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restri
     __syncthreads();
     T* wf = reinterpret_cast<T*>(j.dst0);
     T* wd = reinterpret_cast<T*>(j.dst1);
-    for (int i = tid; i < kWT * run; i += 256) {
-      const int t = (i / kWT) % taps;
-      if (j.kind == 0) {
-        // wf[co][t][ci]: consecutive threads -> consecutive ci
-        { const int co = i / run, ci = i % kWT;
-          wf[((size_t)(a0 + co) * 9 + t) * j.cin + b0 + ci] = from_f<T>(sm[co][ci * 9 + t]); }
-        // wd[ci][8-t][co]: consecutive threads -> consecutive co
-        { const int ci = i / run, co = i % kWT;
-          wd[((size_t)(b0 + ci) * 9 + (8 - t)) * j.cout + a0 + co] = from_f<T>(sm[co][ci * 9 + t]); }
-      } else {
-        // convT: sm[ci][co*4 + ab];  wf[(ab*cout + co)][ci]: consecutive threads -> consecutive ci
-        { const int co = i / run, ci = i % kWT;
-          wf[((size_t)t * j.cout + b0 + co) * j.cin + a0 + ci] = from_f<T>(sm[ci][co * 4 + t]); }
-        // wd[ci][ab][co]: consecutive threads -> consecutive co
-        { const int ci = i / run, co = i % kWT;
-          wd[((size_t)(a0 + ci) * 4 + t) * j.cout + b0 + co] = from_f<T>(sm[ci][co * 4 + t]); }
+    // two adjacent elements per store (4 bytes of bf16 / 8 bytes of fp32); tap counts are compile-time in each branch
+    if (j.kind == 0) {
+      for (int i = tid; i < kWT * 9 * (kWT / 2); i += 256) {
+        const int cp = i % (kWT / 2), t = (i / (kWT / 2)) % 9, row = i / (9 * (kWT / 2));
+        // wf[co][t][ci]: consecutive threads -> consecutive ci pairs
+        store2(wf + ((size_t)(a0 + row) * 9 + t) * j.cin + b0 + 2 * cp, sm[row][(2 * cp) * 9 + t], sm[row][(2 * cp + 1) * 9 + t]);
+        // wd[ci][8-t][co]: consecutive threads -> consecutive co pairs
+        store2(wd + ((size_t)(b0 + row) * 9 + (8 - t)) * j.cout + a0 + 2 * cp, sm[2 * cp][row * 9 + t], sm[2 * cp + 1][row * 9 + t]);
+      }
+    } else {
+      for (int i = tid; i < kWT * 4 * (kWT / 2); i += 256) {
+        const int cp = i % (kWT / 2), t = (i / (kWT / 2)) % 4, row = i / (4 * (kWT / 2));
+        // convT: sm[ci][co*4 + ab];  wf[(ab*cout + co)][ci]: consecutive threads -> consecutive ci pairs
+        store2(wf + ((size_t)t * j.cout + b0 + row) * j.cin + a0 + 2 * cp, sm[2 * cp][row * 4 + t], sm[2 * cp + 1][row * 4 + t]);
+        // wd[ci][ab][co]: consecutive threads -> consecutive co pairs
+        store2(wd + ((size_t)(a0 + row) * 4 + t) * j.cout + b0 + 2 * cp, sm[row][(2 * cp) * 4 + t], sm[row][(2 * cp + 1) * 4 + t]);
       }
     }
   } else {
