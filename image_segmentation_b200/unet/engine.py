@@ -261,6 +261,7 @@ class UNetPlan:
         for lvl in (4, 3, 2, 1, 0):
             segments.append([self.enc[lvl][1], self.enc[lvl][0]])
         self._unpack_jobs = []
+        all_jobs = []
         for items in segments:
             jobs = []
             for item in items:
@@ -273,6 +274,10 @@ class UNetPlan:
                 else:
                     jobs.append((item.ws.data_ptr(), 4 * off_of[id(item.mod.weight)], None, 1, item.cout, item.cin, 0))
             self._unpack_jobs.append(L.WeightJobs(jobs, self.device))
+            all_jobs += jobs
+        # single process: one launch over every segment at the end of backward (the nine per-segment launches are
+        # latency-bound, 2-3 blocks per SM each; they exist so that data-parallel buckets can leave early)
+        self._unpack_all = L.WeightJobs(all_jobs, self.device)
         self._bwd_ready = True
 
     # ------------------------------------------------------------------------------------------
@@ -440,10 +445,10 @@ class UNetPlan:
             grad_a2 = ct.g_in
             pos += 10
             join_side()
-            L.weights_unpack(self._unpack_jobs[seg], flat)
-            seg += 1
             if bucket_hook:
+                L.weights_unpack(self._unpack_jobs[seg], flat)
                 bucket_hook(self, self.grad_offsets[pos])
+            seg += 1
         for lvl in (4, 3, 2, 1, 0):
             l1, l2 = self.enc[lvl]
             if lvl == 4:
@@ -454,10 +459,12 @@ class UNetPlan:
             conv_bn_bwd(l1, l2.g_in, reduced=True)
             pos += 8
             join_side()
-            L.weights_unpack(self._unpack_jobs[seg], flat)
-            seg += 1
             if bucket_hook:
+                L.weights_unpack(self._unpack_jobs[seg], flat)
                 bucket_hook(self, self.grad_offsets[pos])
+            seg += 1
+        if not bucket_hook:
+            L.weights_unpack(self._unpack_all, flat)
         return g
 
 
