@@ -155,12 +155,13 @@ __global__ void __launch_bounds__(TILE) head_bwd_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 // Dice + CE
 // ------------------------------------------------------------------------------------------------
+template <int CM>
 __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args a) {
   const int c = a.c;
   const int64_t hw = (int64_t)a.h * a.w, npix = (int64_t)a.n * hw;
-  float I[kMaxClasses], P[kMaxClasses], G[kMaxClasses], cen = 0.f, ced = 0.f;
+  float I[CM], P[CM], G[CM], cen = 0.f, ced = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) I[k] = P[k] = G[k] = 0.f;
+  for (int k = 0; k < CM; ++k) I[k] = P[k] = G[k] = 0.f;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
     const int64_t yl = a.target[p];
     if (yl < 0 || yl >= c) {
@@ -169,10 +170,10 @@ __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args 
     }
     const int y = (int)yl;
     const int64_t img = p / hw, off = p % hw;
-    Softmax s;
-    pixel_softmax(a.logits, img * c * hw + off, hw, c, y, s);
+    SoftmaxT<CM> s;
+    pixel_softmax<CM>(a.logits, img * c * hw + off, hw, c, y, s);
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < CM; ++k) {
       // utils/weighted_loss.py:50-58: with C == 1 the reference uses y.float() itself as the "one-hot"
       const float oh = c == 1 ? (float)y : (k == y ? 1.f : 0.f);
       if (k < c) {
@@ -188,30 +189,30 @@ __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args 
       ced += wy;
     }
   }
-  __shared__ float red[8][3 * kMaxClasses + 2];
+  __shared__ float red[8][3 * CM + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < CM; ++k) {
     const float i = warp_sum(I[k]), pp = warp_sum(P[k]), g = warp_sum(G[k]);
     if (lane == 0) {
       red[warp][k] = i;
-      red[warp][kMaxClasses + k] = pp;
-      red[warp][2 * kMaxClasses + k] = g;
+      red[warp][CM + k] = pp;
+      red[warp][2 * CM + k] = g;
     }
   }
   cen = warp_sum(cen);
   ced = warp_sum(ced);
   if (lane == 0) {
-    red[warp][3 * kMaxClasses] = cen;
-    red[warp][3 * kMaxClasses + 1] = ced;
+    red[warp][3 * CM] = cen;
+    red[warp][3 * CM + 1] = ced;
   }
   __syncthreads();
-  if (threadIdx.x < 3 * kMaxClasses + 2) {
+  if (threadIdx.x < 3 * CM + 2) {
     float s = 0.f;
     for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
-    const int q = threadIdx.x / kMaxClasses, k = threadIdx.x % kMaxClasses;
-    if (threadIdx.x >= 3 * kMaxClasses)
-      atomicAdd(a.accum + 3 * c + (threadIdx.x - 3 * kMaxClasses), (double)s);
+    const int q = threadIdx.x / CM, k = threadIdx.x % CM;
+    if (threadIdx.x >= 3 * CM)
+      atomicAdd(a.accum + 3 * c + (threadIdx.x - 3 * CM), (double)s);
     else if (k < c)
       atomicAdd(a.accum + q * c + k, (double)s);
   }
@@ -223,10 +224,11 @@ __global__ void dice_ce_finalize_kernel(unetk_dice_ce_args a) {
                                a.ce_weight, a.coef);
 }
 
+template <int CM>
 __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) {
   const int c = a.c;
   const int64_t hw = (int64_t)a.h * a.w, npix = (int64_t)a.n * hw;
-  __shared__ float coef[2 * kMaxClasses + 1];
+  __shared__ float coef[2 * CM + 1];
   if (threadIdx.x < 2 * c + 1) coef[threadIdx.x] = a.coef[threadIdx.x];
   __syncthreads();
   const float go = a.grad_out ? a.grad_out[0] : 1.f;
@@ -240,11 +242,11 @@ __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) 
       continue;
     }
     const int y = (int)yl;
-    Softmax s;
-    pixel_softmax(a.logits, base, hw, c, y, s);
-    float g[kMaxClasses], dot = 0.f;
+    SoftmaxT<CM> s;
+    pixel_softmax<CM>(a.logits, base, hw, c, y, s);
+    float g[CM], dot = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < CM; ++k) {
       const float oh = c == 1 ? (float)y : (k == y ? 1.f : 0.f);
       g[k] = k < c ? -coef[k] * (2.f * oh - coef[c + k]) : 0.f;
       dot = fmaf(s.p[k], g[k], dot);
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) 
     const bool valid = !(a.has_ignore && yl == a.ignore_index);
     const float wy = valid ? (a.class_weights ? a.class_weights[y] : 1.f) * ce_scale : 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) {
+    for (int k = 0; k < CM; ++k) {
       if (k < c) {
         const float gx = s.p[k] * (g[k] - dot) + wy * (s.p[k] - (k == y ? 1.f : 0.f));
         a.dlogits[base + k * hw] = gx * go;
@@ -379,7 +381,10 @@ int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream) {
   if (rc) return rc;
   UNETK_REQUIRE(a->accum && a->loss, "dice_ce_fwd: null accum/loss");
   const int64_t npix = (int64_t)a->n * a->h * a->w;
-  dice_ce_reduce_kernel<<<grid_pixels(npix, 4), 256, 0, (cudaStream_t)stream>>>(*a);
+  if (a->c <= 4)
+    dice_ce_reduce_kernel<4><<<grid_pixels(npix, 4), 256, 0, (cudaStream_t)stream>>>(*a);
+  else
+    dice_ce_reduce_kernel<kMaxClasses><<<grid_pixels(npix, 4), 256, 0, (cudaStream_t)stream>>>(*a);
   dice_ce_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
@@ -390,7 +395,10 @@ int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream) {
   if (rc) return rc;
   UNETK_REQUIRE(a->dlogits, "dice_ce_bwd: null dlogits");
   const int64_t npix = (int64_t)a->n * a->h * a->w;
-  dice_ce_bwd_kernel<<<grid_pixels(npix, 2), 256, 0, (cudaStream_t)stream>>>(*a);
+  if (a->c <= 4)
+    dice_ce_bwd_kernel<4><<<grid_pixels(npix, 2), 256, 0, (cudaStream_t)stream>>>(*a);
+  else
+    dice_ce_bwd_kernel<kMaxClasses><<<grid_pixels(npix, 2), 256, 0, (cudaStream_t)stream>>>(*a);
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }

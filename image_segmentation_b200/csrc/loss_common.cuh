@@ -6,38 +6,44 @@ namespace unetk {
 
 constexpr int kMaxClasses = 8;
 
-struct Softmax {
-  float p[kMaxClasses];
+// CM = compile-time bound on the class count (4 for the U-Net's 1/3/4 classes, kMaxClasses otherwise): the softmax
+// costs CM exponentials per pixel, so the bound matters (the loss kernels are instruction-bound, not memory-bound)
+template <int CM>
+struct SoftmaxT {
+  float p[CM];
   float logp_y;
 };
+using Softmax = SoftmaxT<kMaxClasses>;
 
 // softmax over x[0..c) (entries >= c must be -inf) and log p[y]
-__device__ __forceinline__ void softmax_of(const float (&x)[kMaxClasses], int c, int y, Softmax& s) {
+template <int CM>
+__device__ __forceinline__ void softmax_of(const float (&x)[CM], int c, int y, SoftmaxT<CM>& s) {
   float m = -INFINITY;
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) m = fmaxf(m, x[k]);
+  for (int k = 0; k < CM; ++k) m = fmaxf(m, x[k]);
   float sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < CM; ++k) {
     s.p[k] = k < c ? expf(x[k] - m) : 0.f;
     sum += s.p[k];
   }
   const float inv = 1.f / sum;
   float xy = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) {
+  for (int k = 0; k < CM; ++k) {
     s.p[k] *= inv;
     if (k == y) xy = x[k];
   }
   s.logp_y = xy - m - logf(sum);
 }
 
+template <int CM>
 __device__ __forceinline__ void pixel_softmax(const float* __restrict__ logits, int64_t base, int64_t hw, int c, int y,
-                                              Softmax& s) {
-  float x[kMaxClasses];
+                                              SoftmaxT<CM>& s) {
+  float x[CM];
 #pragma unroll
-  for (int k = 0; k < kMaxClasses; ++k) x[k] = k < c ? logits[base + k * hw] : -INFINITY;
-  softmax_of(x, c, y, s);
+  for (int k = 0; k < CM; ++k) x[k] = k < c ? logits[base + k * hw] : -INFINITY;
+  softmax_of<CM>(x, c, y, s);
 }
 
 // torch.argmax over x[0..c): first maximum wins, NaN counts as the largest value (utils/MetricsHistory.py:65)
