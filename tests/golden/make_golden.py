@@ -232,6 +232,65 @@ def gen_eval(ref):
     np.savez_compressed(os.path.join(OUT, "eval.npz"), **out)
 
 
+def start_fixture(seed=31, target=32):
+    """Deterministic tiny train / validation loaders shared by gen_start and tests/test_gpu_start.py."""
+    g = torch.Generator().manual_seed(seed)
+    train = []
+    for i in range(3):
+        x, y = make_batch(2, target, target, 3, 4, seed=400 + i, labels="learnable")
+        train.append((x, y.to(torch.uint8)))
+    val = []
+    for szs in ([(40, 28), (32, 32)], [(25, 50)]):
+        X = [torch.rand(3, h, w, generator=g) for h, w in szs]
+        y = [(X[i].mean(0) * 3.999).floor().to(torch.uint8) for i in range(len(szs))]      # labels 0..3 tied to the image
+        val.append((X, y))
+    return train, val
+
+
+def gen_start(ref):
+    """Two epochs of the reference's start() (utils/training.py:453-617): train_loop + eval_loop + checkpointing."""
+    import contextlib, io, tempfile
+    tm = ref.training_mod
+    train, val = start_fixture()
+    torch.manual_seed(0)
+    m = ref.unet(3, 4)
+    opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
+    w = torch.tensor(CLASS_W4)
+    loss_fn = ref.WeightedDiceCELoss(smooth_dice=1, class_weights=w, ignore_index=3)
+    agg = ref.MetricsHistory(4, 3)
+    buf = io.StringIO()
+    # start() pickles the MetricsHistory object: its defining module must be importable under its own name meanwhile
+    import types
+    saved = {k: sys.modules.get(k) for k in ("utils", "utils.MetricsHistory")}
+    pkg = types.ModuleType("utils")
+    pkg.MetricsHistory = ref.metrics_mod
+    sys.modules["utils"], sys.modules["utils.MetricsHistory"] = pkg, ref.metrics_mod
+    try:
+        _run_start(tm, ref, m, opt, train, val, loss_fn, agg, buf)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def _run_start(tm, ref, m, opt, train, val, loss_fn, agg, buf):
+    import contextlib, tempfile
+    scratch = os.path.join(ROOT, "build")            # git-ignored scratch directory inside the repository
+    os.makedirs(scratch, exist_ok=True)
+    with tempfile.TemporaryDirectory(dir=scratch) as d, contextlib.redirect_stdout(buf):
+        tm.start(d, "ck.pt", m, opt, train, val, 1, torch.device("cpu"), loss_fn, loss_fn, 32, None, agg, True, True, 4, 3, 2)
+        ck = torch.load(os.path.join(d, "ck.pt"), weights_only=True)
+        files = sorted(os.listdir(d)) + sorted("metrics/" + f for f in os.listdir(os.path.join(d, "metrics")))
+    text = buf.getvalue()
+    out = {"stdout": np.array(text), "files": np.array(json.dumps(files)), "ck_keys": np.array(json.dumps(sorted(ck.keys()))),
+           "ck_epoch": np.array(ck["epoch"]),
+           "ck_best": np.array([ck["best_dev_dice"], ck["best_dev_miou"], ck["best_dev_loss"]]),
+           "miou_history": np.array(agg.get_mean_iou_history()), "dice_history": np.array(agg.get_mean_dice_history())}
+    np.savez_compressed(os.path.join(OUT, "start.npz"), **out)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(8)
@@ -241,6 +300,7 @@ def main():
     gen_metrics(ref)
     gen_curve(ref)
     gen_eval(ref)
+    gen_start(ref)
     with open(os.path.join(OUT, "meta.json"), "w") as f:
         json.dump(dict(torch=torch.__version__, threads=torch.get_num_threads(),
                        reference="in5omnia/Image_Segmentation @ /root/reference (unmodified, CPU)"), f, indent=1)
