@@ -34,6 +34,7 @@ class GraphedTrainStep:
         self.loss = None
         model.train()
         # warm-up on a side stream (allocator pools, cudaFuncSetAttribute, optimizer state) as torch recommends
+        optimizer.zero_grad(set_to_none=True)      # stale .grad tensors would be accumulated into by the warm-up step
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
