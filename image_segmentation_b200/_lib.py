@@ -221,7 +221,7 @@ class WeightJobs:
         arr = (WJob * len(jobs))(*[WJob(*j) for j in jobs])
         tiles = []
         for ji, (_, _, _, kind, cout, cin, _) in enumerate(jobs):
-            if kind == 2:
+            if kind in (2, 3):
                 tiles.append((ji, 0, 0, 0))
                 continue
             na, nb = (cout, cin) if kind == 0 else (cin, cout)

@@ -67,6 +67,24 @@ __global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restri
   if (dst_base) j.dst0 = dst_base + reinterpret_cast<uintptr_t>(j.dst0);
   const int a0 = tl.y, b0 = tl.z;
   const int tid = threadIdx.x;
+  if (j.kind == 3) {
+    // first layer in pixel-pair form (see engine.py): the GEMM row is a PAIR of horizontally adjacent pixels, K = 2 x kpad/2
+    // (each pixel's padded 3x3xCin patch) and N = 2 x cout, with the block-diagonal weight  [[W 0] [0 W]]  of pitch kpad.
+    // pack: W -> both diagonal blocks; unpack: the gradient is the sum of the two diagonal blocks of dW'.
+    const int total = j.cout * j.cin * 9, half = j.kpad / 2;
+    for (int i = tid; i < total; i += 256) {
+      const int co = i / (j.cin * 9), r = i % (j.cin * 9), ci = r / 9, t = r % 9, k = t * j.cin + ci;
+      if (PACK) {
+        const T v = from_f<T>(reinterpret_cast<const float*>(j.src)[i]);
+        reinterpret_cast<T*>(j.dst0)[(size_t)co * j.kpad + k] = v;
+        reinterpret_cast<T*>(j.dst0)[(size_t)(j.cout + co) * j.kpad + half + k] = v;
+      } else {
+        const float* ws2 = reinterpret_cast<const float*>(j.src);
+        reinterpret_cast<float*>(j.dst0)[i] = ws2[(size_t)co * j.kpad + k] + ws2[(size_t)(j.cout + co) * j.kpad + half + k];
+      }
+    }
+    return;
+  }
   if (j.kind == 2) {
     // tiny first layer: [co][ci][9] <-> [co][kpad], k = t*cin + ci
     const int total = j.cout * j.cin * 9;

@@ -83,10 +83,24 @@ class UNetPlan:
     def _act(self, n, h, w, c):
         return torch.empty((n, h, w, c), dtype=self.dt, device=self.device)
 
+    @staticmethod
+    def _pairs(t):
+        """[N,H,W,C] contiguous -> the same memory as [N,H,W/2,2C] (two horizontally adjacent pixels per row)."""
+        n, h, w, c = t.shape
+        return t.view(n, h, w // 2, 2 * c)
+
     def _build(self):
         m, n, dev, dt = self.model, self.n, self.device, self.dt
         H, W = self.h, self.w
         self.kpad = ((9 * self.din + 63) // 64) * 64
+        # First layer in pixel-pair form (bf16 tier): with K padded to 32 per pixel, two horizontally adjacent pixels make
+        # one 64-wide GEMM row, and the block-diagonal weight [[W 0] [0 W]] (N = 128) writes both pixels' 64 output
+        # channels -- which IS the NHWC layout of the pair.  The im2col buffer and its two readers (this conv and the
+        # first-layer weight gradient) move half the bytes of the K = 64 padding; all three kernels are HBM-bound.
+        self.pair_first = (dt == torch.bfloat16 and W % 2 == 0 and 9 * self.din <= 32
+                           and os.environ.get("UNETK_FIRST_PAIR", "1") == "1")
+        if self.pair_first:
+            self.kpad = 32
         self.xcol = self._act(n, H, W, self.kpad)
         hs = [H >> i for i in range(5)]
         ws = [W >> i for i in range(5)]
@@ -154,7 +168,9 @@ class UNetPlan:
 
         # ---- per-channel scratch: fp64 accumulators (zeroed once per pass) and fp32 vectors ----
         tot_c = sum(l.cout for l in self.layers)
-        self.acc64 = torch.zeros(4 * tot_c, dtype=torch.float64, device=dev)  # sum, sumsq, bwd s1, s2
+        # sum, sumsq, bwd s1, s2 (+ 2 x 128 for the pixel-pair first layer, whose statistics arrive as two halves)
+        self.acc64 = torch.zeros(4 * tot_c + 256, dtype=torch.float64, device=dev)
+        self.first_stats = self.acc64[4 * tot_c:]
         self.vec32 = torch.empty(4 * tot_c, dtype=torch.float32, device=dev)  # scale, shift, mean, invstd
         off = 0
         for l in self.layers:
@@ -179,7 +195,9 @@ class UNetPlan:
 
         # ---- operand packs ----
         for l in self.layers:
-            if l.first:
+            if l.first and self.pair_first:
+                l.wf = torch.zeros((2 * l.cout, 2 * self.kpad), dtype=dt, device=dev)
+            elif l.first:
                 l.wf = torch.zeros((l.cout, self.kpad), dtype=dt, device=dev)
             else:
                 l.wf = torch.empty((l.cout, 9, l.cin), dtype=dt, device=dev)
@@ -243,7 +261,10 @@ class UNetPlan:
         ws_sizes = []
         for item in seq:
             if isinstance(item, _ConvBN):
-                ws_sizes.append(item.cout * (self.kpad if item.first else 9 * item.cin))
+                if item.first and self.pair_first:
+                    ws_sizes.append(2 * item.cout * 2 * self.kpad)
+                else:
+                    ws_sizes.append(item.cout * (self.kpad if item.first else 9 * item.cin))
             else:
                 ws_sizes.append(item.cin * 4 * item.cout)
         self.ws_total = sum(ws_sizes)
@@ -267,7 +288,9 @@ class UNetPlan:
             for item in items:
                 if isinstance(item, _ConvBN):
                     dst = 4 * off_of[id(item.conv.weight)]
-                    if item.first:
+                    if item.first and self.pair_first:
+                        jobs.append((item.ws.data_ptr(), dst, None, 3, item.cout, item.cin, 2 * self.kpad))
+                    elif item.first:
                         jobs.append((item.ws.data_ptr(), dst, None, 2, item.cout, item.cin, self.kpad))
                     else:
                         jobs.append((item.ws.data_ptr(), dst, None, 0, item.cout, item.cin, 0))
@@ -292,7 +315,9 @@ class UNetPlan:
             jobs = []
             for l in self.layers:
                 w = l.conv.weight
-                if l.first:
+                if l.first and self.pair_first:
+                    jobs.append((w.data_ptr(), l.wf.data_ptr(), None, 3, l.cout, l.cin, 2 * self.kpad))
+                elif l.first:
                     jobs.append((w.data_ptr(), l.wf.data_ptr(), None, 2, l.cout, l.cin, self.kpad))
                 else:
                     jobs.append((w.data_ptr(), l.wf.data_ptr(), l.wd.data_ptr(), 0, l.cout, l.cin, 0))
@@ -323,9 +348,18 @@ class UNetPlan:
         def conv_bn(l: _ConvBN):
             count = n * l.h * l.w
             L.LABEL = l.name
-            L.conv(l.src, l.wf, l.z, L.MODE_1X1 if l.first else L.MODE_3X3,
-                   stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
-                   algo=self.algo, algo_flops=(2 * count * 9 * l.cin * l.cout) if l.first else None)
+            if l.first and self.pair_first:
+                fs = self.first_stats
+                L.conv(self._pairs(l.src), l.wf, self._pairs(l.z), L.MODE_1X1,
+                       stat_sum=fs[:128] if training else None, stat_sumsq=fs[128:] if training else None,
+                       algo=self.algo, algo_flops=2 * count * 9 * l.cin * l.cout)
+                if training:     # the two pixels of a pair are the same 64 BatchNorm channels
+                    torch.add(fs[:64], fs[64:128], out=l.stat_sum)
+                    torch.add(fs[128:192], fs[192:], out=l.stat_sumsq)
+            else:
+                L.conv(l.src, l.wf, l.z, L.MODE_1X1 if l.first else L.MODE_3X3,
+                       stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
+                       algo=self.algo, algo_flops=(2 * count * 9 * l.cin * l.cout) if l.first else None)
             bn = l.bn
             momentum = bn.momentum if bn.momentum is not None else 0.1
             track = bn.track_running_stats and bn.running_mean is not None
@@ -413,7 +447,11 @@ class UNetPlan:
             else:
                 L.bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz, g[l.bn.weight],
                               g[l.bn.bias], pool_idx=l.pool_idx if dpool is not None else None, reduced=reduced and fuse)
-            if l.first:
+            if l.first and self.pair_first:
+                # dW' [2*cout][2*kpad] over pixel pairs; weights_unpack (kind 3) adds its two diagonal blocks
+                on_side(lambda: L.wgrad(self._pairs(l.dz), self._pairs(l.src), l.ws, 0, algo=self.algo,
+                                        algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout))
+            elif l.first:
                 on_side(lambda: L.wgrad(l.dz, l.src, l.ws, 0, algo=self.algo,
                                         algo_flops=2 * self.n * l.h * l.w * 9 * l.cin * l.cout))
             else:
