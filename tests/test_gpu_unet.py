@@ -297,6 +297,33 @@ def test_non_power_of_two_resolution_bf16_tc_vs_fp32_tier():
     assert e < 5e-2
 
 
+def _bf16_first_layer_run(monkeypatch, pair, din, dout, x, y):
+    monkeypatch.setenv("UNETK_FIRST_PAIR", pair)
+    m = build(din, dout, "bf16")
+    logits = m(x.to(DEV))
+    loss_for(dout)(logits, y.squeeze(1).to(DEV)).backward()
+    return logits.detach(), m.down1.doubleConvReLU[0].weight.grad.clone(), m.down1.doubleConvReLU[1].weight.grad.clone()
+
+
+def test_first_layer_pixel_pair_form_equals_k64_form(monkeypatch):
+    """bf16 first layer: the pixel-pair form (K = 32 per pixel, block-diagonal N = 128 weight) computes exactly the
+    products of the K = 64-padded form, so logits and first-layer gradients agree far inside the bf16-vs-fp32 noise."""
+    x, y = make_batch(2, 32, 48, 3, 3, seed=31)
+    a = _bf16_first_layer_run(monkeypatch, "1", 3, 3, x, y)
+    b = _bf16_first_layer_run(monkeypatch, "0", 3, 3, x, y)
+    # identical products; the fp32 summation order differs, which moves some bf16 roundings of the first activation by
+    # one ulp and is then amplified like any bf16 noise (bf16 vs fp32 tier sits at 1.3e-2) -- a wrong K mapping would be O(1)
+    assert rel_l2(a[0], b[0]) < 1.5e-2
+    assert rel_l2(a[1], b[1]) < 0.5 and rel_l2(a[2], b[2]) < 0.5
+    # unet(4,1) (the prompt model's network): 36 > 32 taps x channels -> always the K = 64 form; against the fp32 tier
+    x4, y4 = make_batch(2, 32, 32, 4, 2, seed=32)
+    y4 = torch.zeros_like(y4)
+    c = _bf16_first_layer_run(monkeypatch, "1", 4, 1, x4, y4)
+    m = build(4, 1, "fp32")
+    ref = m(x4.to(DEV)).detach()
+    assert rel_l2(c[0], ref) < 5e-2 and torch.isfinite(c[1]).all()
+
+
 def test_batch_of_one_and_repeatability():
     x, y = make_batch(1, 64, 64, 3, 3, seed=4)
     m = build(3, 3, "bf16")
