@@ -102,6 +102,12 @@ def cpu_reference_steps(steps, warmup, batch=4):
     import torch
     from image_segmentation_b200.utils.synthetic import make_batch
     from oracle import loss_oracle, metrics_oracle, unet_oracle
+    # every host core: torchrun exports OMP_NUM_THREADS=1 for its workers, which would time the CPU path on one thread
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores))
     torch.manual_seed(0)
     m = unet_oracle.OracleUNet(3, 3, native_ops=True).train()   # the reference's own ATen operators (F.batch_norm, ...)
     opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
