@@ -21,25 +21,20 @@ class MetricsHistory:
     and computes Dice, IoU, and Accuracy metrics.
     """
 
+    _HISTORIES = ("mean_dice", "mean_iou", "mean_acc", "per_class_dice", "per_class_iou", "per_class_acc")
+
     def __init__(self, num_classes: int, ignore_index: int = None, device: str = 'cpu'):
-        self.num_classes = num_classes
-        self.ignore_index = ignore_index
-        self._host = torch.zeros(4, num_classes, dtype=torch.float64)      # synced totals (tp, fp, fn, tn)
+        self.num_classes, self.ignore_index = num_classes, ignore_index
+        self._host = torch.zeros(4, num_classes, dtype=torch.float64)      # synced totals: rows tp, fp, fn, tn
         self._pending = {}                                                  # device -> (int64 [4,C], status)
-
-        self.epoch_mean_dice_history = []
-        self.epoch_mean_iou_history = []
-        self.epoch_mean_acc_history = []
-        self.epoch_per_class_dice_history = []
-        self.epoch_per_class_iou_history = []
-        self.epoch_per_class_acc_history = []
-        self.last_per_class_iou = None
-        self.last_per_class_dice = None
-        self.last_per_class_acc = None
-
-        self.mask = torch.ones(num_classes, dtype=torch.bool)
-        if self.ignore_index is not None and 0 <= self.ignore_index < self.num_classes:
-            self.mask[self.ignore_index] = False
+        for name in self._HISTORIES:                                        # epoch_mean_dice_history, ... (reference :26-38)
+            setattr(self, f"epoch_{name}_history", [])
+        for kind in ("iou", "dice", "acc"):
+            setattr(self, f"last_per_class_{kind}", None)
+        keep = torch.ones(num_classes, dtype=torch.bool)
+        if ignore_index is not None and 0 <= ignore_index < num_classes:
+            keep[ignore_index] = False                                      # the class left out of the macro averages
+        self.mask = keep
 
     # ---- device-resident accumulation ----------------------------------------------------------
     def _sync(self):
@@ -96,24 +91,19 @@ class MetricsHistory:
             L.argmax_confusion(pred, label, n, c, h, w, counts, None, status)
 
     def compute_epoch_metrics(self, epsilon: float = 1e-6):
-        """Macro-averaged (mean_dice, mean_iou, mean_acc) of the accumulated epoch; appended to the histories."""
-        tp, fp, fn, tn = self.total_tp, self.total_fp, self.total_fn, self.total_tn
-        per_class_iou = tp / (tp + fp + fn)
-        per_class_dice = (2 * tp) / (2 * tp + fp + fn)
-        per_class_acc = (tp + tn) / (tp + tn + fp + fn)
-        mean_iou = per_class_iou[self.mask].mean().item()
-        mean_dice = per_class_dice[self.mask].mean().item()
-        mean_acc = per_class_acc[self.mask].mean().item()
-        self.epoch_mean_iou_history.append(mean_iou)
-        self.epoch_mean_dice_history.append(mean_dice)
-        self.epoch_mean_acc_history.append(mean_acc)
-        self.epoch_per_class_iou_history.append(per_class_iou.numpy())
-        self.epoch_per_class_dice_history.append(per_class_dice.numpy())
-        self.epoch_per_class_acc_history.append(per_class_acc.numpy())
-        self.last_per_class_iou = per_class_iou
-        self.last_per_class_dice = per_class_dice
-        self.last_per_class_acc = per_class_acc
-        return mean_dice, mean_iou, mean_acc
+        """Macro-averaged (mean_dice, mean_iou, mean_acc) of the accumulated epoch; appended to the histories.
+        (`epsilon` is accepted and unused, as in the reference: an absent class yields NaN.)"""
+        self._sync()
+        tp, fp, fn, tn = self._host
+        union = tp + fp + fn
+        per_class = {"iou": tp / union, "dice": (2 * tp) / (tp + union), "acc": (tp + tn) / (union + tn)}
+        means = {}
+        for kind, values in per_class.items():
+            means[kind] = values[self.mask].mean().item()
+            getattr(self, f"epoch_mean_{kind}_history").append(means[kind])
+            getattr(self, f"epoch_per_class_{kind}_history").append(values.numpy())
+            setattr(self, f"last_per_class_{kind}", values)
+        return means["dice"], means["iou"], means["acc"]
 
     def to(self, device):
         """Kept for API parity; totals live on the host, counters follow the predictions' device."""
@@ -142,29 +132,14 @@ class MetricsHistory:
     def get_num_classes(self):
         return self.num_classes
 
-    def get_mean_dice_history(self):
-        return self.epoch_mean_dice_history
 
-    def get_mean_iou_history(self):
-        return self.epoch_mean_iou_history
+def _install_getters():
+    """get_mean_*_history / get_class_*_history / get_last_per_class_* of the reference (:152-182), generated."""
+    for kind in ("dice", "iou", "acc"):
+        for public, attr in ((f"get_mean_{kind}_history", f"epoch_mean_{kind}_history"),
+                             (f"get_class_{kind}_history", f"epoch_per_class_{kind}_history"),
+                             (f"get_last_per_class_{kind}", f"last_per_class_{kind}")):
+            setattr(MetricsHistory, public, (lambda a: lambda self: getattr(self, a))(attr))
 
-    def get_mean_acc_history(self):
-        return self.epoch_mean_acc_history
 
-    def get_class_dice_history(self):
-        return self.epoch_per_class_dice_history
-
-    def get_class_iou_history(self):
-        return self.epoch_per_class_iou_history
-
-    def get_class_acc_history(self):
-        return self.epoch_per_class_acc_history
-
-    def get_last_per_class_dice(self):
-        return self.last_per_class_dice
-
-    def get_last_per_class_iou(self):
-        return self.last_per_class_iou
-
-    def get_last_per_class_acc(self):
-        return self.last_per_class_acc
+_install_getters()
