@@ -324,6 +324,28 @@ def test_first_layer_pixel_pair_form_equals_k64_form(monkeypatch):
     assert rel_l2(c[0], ref) < 5e-2 and torch.isfinite(c[1]).all()
 
 
+def test_more_than_four_classes_takes_the_unfused_head_path():
+    """dout > 4: bn_relu_apply + head_fprop forward, head_bwd + stand-alone BatchNorm backward (the fused head kernels cover
+    1..4 classes).  fp32 tier against the CPU oracle, bf16 tier against the fp32 tier."""
+    x, y = make_batch(2, 32, 32, 3, 6, seed=41)
+    torch.manual_seed(0)
+    sd = unet_oracle.init_state_dict(3, 6)
+    ref_loss, ref_logits, ref_grads, _ = unet_oracle.loss_and_grads(
+        sd, x, y.squeeze(1), lambda lg, t: loss_oracle.dice_ce_loss(lg, t, smooth_dice=1.0), dtype=torch.float64)
+    out = {}
+    for precision in ("fp32", "bf16"):
+        m = build(3, 6, precision)
+        logits = m(x.to(DEV))
+        loss = WeightedDiceCELoss(smooth_dice=1)(logits, y.squeeze(1).to(DEV))
+        loss.backward()
+        out[precision] = (logits.detach(), loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()})
+    assert rel_max(out["fp32"][0], ref_logits) < 1e-4 and abs(out["fp32"][1] - ref_loss.item()) < 1e-4
+    for k in ("output.weight", "output.bias", "up4.doubleConv.doubleConvReLU.4.weight", "up4.doubleConv.doubleConvReLU.3.weight"):
+        assert rel_l2(out["fp32"][2][k], ref_grads[k]) < 5e-3, k
+    assert rel_l2(out["bf16"][0], ref_logits) < 5e-2
+    assert rel_l2(out["bf16"][2]["output.weight"], ref_grads["output.weight"]) < 0.2
+
+
 def test_batch_of_one_and_repeatability():
     x, y = make_batch(1, 64, 64, 3, 3, seed=4)
     m = build(3, 3, "bf16")
