@@ -346,6 +346,29 @@ def test_more_than_four_classes_takes_the_unfused_head_path():
     assert rel_l2(out["bf16"][2]["output.weight"], ref_grads["output.weight"]) < 0.2
 
 
+@pytest.mark.parametrize("n,h,w,din,dout", [(5, 64, 96, 3, 3), (7, 32, 32, 3, 3), (2, 16, 16, 3, 3), (3, 128, 64, 1, 2),
+                                             (2, 64, 64, 5, 3), (1, 512, 512, 3, 4)])
+def test_shape_sweep_train_and_eval(n, h, w, din, dout):
+    """Odd batch sizes, non-square images, 1 / 5 input channels, 16x16 (a 1x1 bottleneck) up to 512x512: a training step and
+    an eval forward run in both tiers, stay finite, and the bf16 loss tracks the fp32-tier loss."""
+    x, y = make_batch(n, h, w, din, max(dout, 2), seed=1)
+    losses = {}
+    for precision in ("bf16", "fp32"):
+        if precision == "fp32" and n * h * w > 70000:
+            continue                                  # the CUDA-core tier is a parity tool, not a throughput path
+        m = build(din, dout, precision)
+        logits = m(x.to(DEV))
+        loss = WeightedDiceCELoss(smooth_dice=1)(logits, y.squeeze(1).to(DEV))
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+        m.eval()
+        with torch.no_grad():
+            assert torch.isfinite(m(x.to(DEV))).all()
+        losses[precision] = loss.item()
+    if "fp32" in losses:
+        assert abs(losses["bf16"] - losses["fp32"]) < 1e-2
+
+
 def test_batch_of_one_and_repeatability():
     x, y = make_batch(1, 64, 64, 3, 3, seed=4)
     m = build(3, 3, "bf16")
