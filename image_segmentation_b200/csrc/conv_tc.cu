@@ -492,6 +492,39 @@ __global__ void __launch_bounds__(kConvThreads, 1) tc_conv_kernel(const __grid_c
   }
 }
 
+// Work distribution of the CTA-pair kernels.  Work item = (N tile, pair of pixel tiles).  When the pairs split evenly
+// over the N tiles, pair p keeps ONE N tile (weight rows, statistics channels) and the groups of pairs walk the pixel
+// tiles in step, so a pixel tile is fetched by all N tiles at about the same time and comes from DRAM once (the input
+// of a deep layer, 134 MB at batch 64, does not fit the L2: pixel-fastest order streamed it once per N tile).
+struct PairSched {
+  int iters, n_fixed, m0, mstep, m_pairs, pair_id, num_pairs;
+  bool grouped;
+  __device__ PairSched(int pair_id_, int num_pairs_, int m_pairs_, int num_n_tiles) {
+    pair_id = pair_id_; num_pairs = num_pairs_; m_pairs = m_pairs_;
+    grouped = num_n_tiles > 1 && num_pairs % num_n_tiles == 0;
+    if (grouped) {
+      mstep = num_pairs / num_n_tiles;
+      n_fixed = pair_id / mstep;
+      m0 = pair_id % mstep;
+      iters = m0 < m_pairs ? (m_pairs - m0 + mstep - 1) / mstep : 0;
+    } else {
+      mstep = n_fixed = m0 = 0;
+      const int total = m_pairs * num_n_tiles;
+      iters = pair_id < total ? (total - pair_id + num_pairs - 1) / num_pairs : 0;
+    }
+  }
+  __device__ __forceinline__ void get(int k, int& n_tile, int& m_pair) const {
+    if (grouped) {
+      n_tile = n_fixed;
+      m_pair = m0 + k * mstep;
+    } else {
+      const int pt = pair_id + k * num_pairs;
+      n_tile = pt / m_pairs;
+      m_pair = pt % m_pairs;
+    }
+  }
+};
+
 // -------------------------------------------------------------------------------------------------
 // CTA-pair variant of tc_conv_kernel (cta_group::2).  The in-kernel counters showed the single-CTA MMA bound by
 // shared-memory operand fetch (~80 B/cycle: (4096 + 32 N)/80 cycles per M=128 MMA).  A pair of CTAs on adjacent SMs
@@ -519,7 +552,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
-  const int num_ptiles = m_pairs * p.num_n_tiles;
+  const PairSched sched(pair_id, num_pairs, m_pairs, p.num_n_tiles);
   const int ksteps = p.taps * p.chunks_per_tap;
   const int stages = p.stages;
 
@@ -552,8 +585,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
-        const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+      for (int kk = 0; kk < sched.iters; ++kk) {
+        int n_tile, m_pair;
+        sched.get(kk, n_tile, m_pair);
+        const int m_tile = 2 * m_pair + (int)rank;
         const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;   // a tile past the end is all out-of-bounds: zero fill
         for (int s = 0; s < ksteps; ++s) {
@@ -589,7 +624,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
+      for (int kk = 0; kk < sched.iters; ++kk, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
@@ -627,8 +662,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     st.clear();
     st.n_tile = -1;
     int it = g;
-    for (int pt = pair_id + g * num_pairs; pt < num_ptiles; pt += 2 * num_pairs, it += 2) {
-      const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+    for (int kk = g; kk < sched.iters; kk += 2, it += 2) {
+      int n_tile, m_pair;
+      sched.get(kk, n_tile, m_pair);
+      const int m_tile = 2 * m_pair + (int)rank;
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.pw, h0 = th * p.ph, n0 = tn * p.nb;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && (n0 + nb_i) < p.n;
@@ -864,7 +901,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
   const bool leader = rank == 0;
   const int num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   const int m_pairs = (p.num_m_tiles + 1) >> 1;
-  const int num_ptiles = m_pairs * p.num_n_tiles;
+  const PairSched sched(pair_id, num_pairs, m_pairs, p.num_n_tiles);
   const int cpt = p.chunks_per_tap;
   const int a_stages = p.stages, b_slots = p.b_slots;
   const bool resident = p.resident_b != 0;
@@ -902,8 +939,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       bool first = true;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs) {
-        const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+      for (int kk = 0; kk < sched.iters; ++kk) {
+        int n_tile, m_pair;
+        sched.get(kk, n_tile, m_pair);
+        const int m_tile = 2 * m_pair + (int)rank;
         const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
         const int w0 = tw * 8, h0 = th * 16;
         const int brow = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
@@ -944,7 +983,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
       uint32_t pa = 0, pb = 0;
       bool first = true;
       int it = 0;
-      for (int pt = pair_id; pt < num_ptiles; pt += num_pairs, ++it) {
+      for (int kk = 0; kk < sched.iters; ++kk, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
@@ -1004,8 +1043,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
     st.clear();
     st.n_tile = -1;
     int it = g;
-    for (int pt = pair_id + g * num_pairs; pt < num_ptiles; pt += 2 * num_pairs, it += 2) {
-      const int n_tile = pt / m_pairs, m_tile = 2 * (pt % m_pairs) + (int)rank;
+    for (int kk = g; kk < sched.iters; kk += 2, it += 2) {
+      int n_tile, m_pair;
+      sched.get(kk, n_tile, m_pair);
+      const int m_tile = 2 * m_pair + (int)rank;
       const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
       const int w0 = tw * 8, h0 = th * 16;
       const bool valid = (w0 + pw_i) < p.w && (h0 + ph_i) < p.h && tn < p.n;
