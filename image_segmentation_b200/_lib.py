@@ -17,6 +17,13 @@ LIB_PATH = os.path.join(PKG_DIR, "libunetk.so")
 
 F32, BF16 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
+# experiment switches of the tcgen05 path (include/unetk.h UNETK_TC_*), OR-ed into `algo`; the shared library itself
+# reads no environment variables -- tools set TC_FLAGS (or UNETK_TC_FLAGS="no_pair,no_halo,...") on the Python side
+TC_FLAG_BITS = {"no_pair": 1 << 8, "no_halo": 1 << 9, "no_even_groups": 1 << 10, "no_halo_n256": 1 << 11,
+                "no_halo_pair": 1 << 12, "no_wgrad_c64": 1 << 13}
+TC_FLAGS = 0
+for _f in filter(None, os.environ.get("UNETK_TC_FLAGS", "").split(",")):
+    TC_FLAGS |= TC_FLAG_BITS[_f.strip()]
 MODE_1X1, MODE_3X3, MODE_CONVT, MODE_CONVT_GATHER = 0, 1, 2, 3
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
@@ -102,6 +109,8 @@ def lib():
                 "(python -m image_segmentation_b200._build, or __graft_entry__.build()). There is no fallback path.")
         l = C.CDLL(LIB_PATH)
         l.unetk_version.restype = C.c_int
+        l.unetk_query_workspace.restype = C.c_int64
+        l.unetk_query_workspace.argtypes = [C.c_int32] * 5
         l.unetk_last_error.restype = C.c_char_p
         vp = C.c_void_p
         P = C.POINTER
@@ -139,7 +148,7 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_im2col3x3_first", "unetk_permute3",
+    "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_query_workspace", "unetk_im2col3x3_first", "unetk_permute3",
     "unetk_weights_pack", "unetk_weights_unpack",
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
@@ -151,6 +160,18 @@ EXPORTED_SYMBOLS = (
 def check(rc: int):
     if rc != 0:
         raise RuntimeError("libunetk: " + lib().unetk_last_error().decode(errors="replace"))
+
+
+WS_BN_STATS, WS_BN_BWD_SUMS, WS_HEAD_BN_SUMS, WS_POOL_IDX, WS_WGRAD, WS_DICE_ACCUM, WS_DICE_COEF, WS_EVAL_ACCUM, \
+    WS_CONFUSION = range(9)
+
+
+def query_workspace(what: int, a: int, b: int = 0, c: int = 0, d: int = 0) -> int:
+    """Bytes of caller-provided scratch `what` (include/unetk.h UNETK_WS_*)."""
+    n = lib().unetk_query_workspace(what, a, b, c, d)
+    if n < 0:
+        check(int(n))
+    return int(n)
 
 
 def stream_ptr() -> int:
@@ -250,7 +271,7 @@ def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUT
     else:
         bnz = nhwc(bn_reduce[0])
         bsc, bsh, bmu, bis, bsum = (t.data_ptr() for t in bn_reduce[1:])
-    a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo, ptr(bias), ptr(stat_sum), ptr(stat_sumsq),
+    a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo | TC_FLAGS, ptr(bias), ptr(stat_sum), ptr(stat_sumsq),
                  bnz, bsc, bsh, bmu, bis, bsum)
     if algo_flops is None:
         if mode in (MODE_1X1, MODE_3X3):
@@ -264,7 +285,7 @@ def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUT
 
 
 def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
-    a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo)
+    a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo | TC_FLAGS)
     if algo_flops is None:
         taps = (1, 9, 4)[mode]
         algo_flops = 2 * u.shape[0] * u.shape[1] * u.shape[2] * taps * u.shape[3] * s.shape[3]

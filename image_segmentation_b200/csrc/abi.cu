@@ -41,6 +41,33 @@ int unetk_version(void) { return 100; }
 
 const char* unetk_last_error(void) { return unetk::g_err; }
 
+int64_t unetk_query_workspace(int32_t what, int32_t a, int32_t b, int32_t c, int32_t d) {
+  if (a <= 0) {
+    unetk::set_error("query_workspace: first size must be positive");
+    return UNETK_ERR_INVALID;
+  }
+  switch (what) {
+    case UNETK_WS_BN_STATS:
+    case UNETK_WS_BN_BWD_SUMS: return 2LL * a * (int64_t)sizeof(double);
+    case UNETK_WS_HEAD_BN_SUMS: return b > 0 ? (3LL + b) * a * (int64_t)sizeof(double) : UNETK_ERR_INVALID;
+    case UNETK_WS_POOL_IDX:
+      if (b <= 0 || c <= 0 || d <= 0 || (b & 1) || (c & 1) || (d % 8)) break;
+      return (int64_t)a * (b / 2) * (c / 2) * (d / 8) * 2;
+    case UNETK_WS_WGRAD: {
+      if (a > 2 || b <= 0 || c <= 0) break;
+      const int taps = a == 0 ? 1 : (a == 1 ? 9 : 4);
+      return (int64_t)b * taps * c * (int64_t)sizeof(float);
+    }
+    case UNETK_WS_DICE_ACCUM: return (3LL * a + 2) * (int64_t)sizeof(double);
+    case UNETK_WS_DICE_COEF: return (2LL * a + 1) * (int64_t)sizeof(float);
+    case UNETK_WS_EVAL_ACCUM: return b > 0 ? (int64_t)a * (3LL * b + 2) * (int64_t)sizeof(double) : UNETK_ERR_INVALID;
+    case UNETK_WS_CONFUSION: return 4LL * a * (int64_t)sizeof(int64_t);
+    default: break;
+  }
+  unetk::set_error("query_workspace: unknown buffer %d or bad sizes (%d,%d,%d,%d)", what, a, b, c, d);
+  return UNETK_ERR_INVALID;
+}
+
 int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;
   UNETK_CUDA(cudaGetDevice(&dev));

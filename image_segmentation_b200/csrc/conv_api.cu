@@ -73,7 +73,7 @@ int unetk_conv(const unetk_conv_args* a, void* stream) {
     UNETK_REQUIRE(a->bn_scale && a->bn_shift && a->bn_mean && a->bn_invstd && a->bn_sums, "conv: bn_* pointers missing");
   }
 
-  int algo = a->algo;
+  int algo = a->algo & UNETK_ALGO_MASK;
   if (algo == UNETK_ALGO_AUTO) algo = a->x.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
   if (algo == UNETK_ALGO_TC) {
     const char* why = "";
@@ -110,7 +110,7 @@ int unetk_wgrad(const unetk_wgrad_args* a, void* stream) {
     UNETK_REQUIRE(a->s.n == a->u.n && a->s.h == a->u.h && a->s.w == a->u.w, "wgrad: u and s must share a spatial shape");
   else
     UNETK_REQUIRE(a->s.n == a->u.n && a->s.h == 2 * a->u.h && a->s.w == 2 * a->u.w, "wgrad(mode 2): s must be [N,2h,2w,C]");
-  int algo = a->algo;
+  int algo = a->algo & UNETK_ALGO_MASK;
   if (algo == UNETK_ALGO_AUTO) algo = a->u.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
   if (algo == UNETK_ALGO_TC) {
     const char* why = "";

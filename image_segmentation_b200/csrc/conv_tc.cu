@@ -100,7 +100,7 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 // forward-family kernels: y[rows, N] = A[rows, K] * B[N, K]^T, both operands K-major in shared memory
 //   tc_conv_kernel       : one TMA box per (tap, 64-channel chunk) -- every mode; tc_conv2_kernel = its CTA-pair form
 //   tc_conv_halo2_kernel : the default for 3x3: halo reuse (below) + CTA pairs, every N tile
-//   tc_conv_halo_kernel  : single-CTA halo kernel (one pixel tile, or UNETK_HALO_PAIR=0); 3x3 only; ONE (18 x 10 pixel) halo box per 64-channel chunk feeds all 9 taps through
+//   tc_conv_halo_kernel  : single-CTA halo kernel (one pixel tile, or UNETK_TC_NO_HALO_PAIR); 3x3 only; ONE (18 x 10 pixel) halo box per 64-channel chunk feeds all 9 taps through
 //                          row-shifted UMMA descriptors (start + (r*10+s)*128 B, SBO = 10*128 B).  tools/umma_probe.cu
 //                          established on B200 that 128B swizzling is a function of the absolute shared-memory address,
 //                          so shifted starts and a 1280-byte group stride address the TMA-written tile consistently.
@@ -109,15 +109,16 @@ PixelTile choose_pixel_tile(int n, int h, int w) {
 // per-CTA cycle counters of the halo kernel (role idle times), read back with unetk_debug_counters(); 8 slots per CTA:
 // [0] producer wait(empty A) [1] mma wait(full A) [2] mma wait(full B) [3] mma wait(tmem empty) [4] mma total
 // [5] epilogue g0 wait(tmem full) [6] epilogue g0 inside epilogue_tile [7] epilogue g0 total
-__device__ long long g_dbg[160 * 8];
-// (compiled in only with -DUNETK_DEBUG_COUNTERS; the default build carries no clock reads in the role loops)
+// (compiled in only with -DUNETK_DEBUG_COUNTERS; the default build carries neither the array nor clock reads)
 #ifdef UNETK_DEBUG_COUNTERS
+__device__ long long g_dbg[160 * 8];
 constexpr bool kDbg = true;
 #define DBG_T0() const long long _t0 = clock64()
 #define DBG_ADD(var) var += clock64() - _t0
 #define DBG_NOW() clock64()
 #else
 constexpr bool kDbg = false;
+__device__ long long* const g_dbg = nullptr;   // never dereferenced: every use is behind `if (kDbg ...)`
 #define DBG_T0() do { } while (0)
 #define DBG_ADD(var) do { } while (0)
 #define DBG_NOW() 0LL
@@ -1607,7 +1608,7 @@ static int set_smem_attr(K kernel, int bytes) {
 constexpr int kMaxSmem = 227 * 1024;
 
 template <int BLOCK_N>
-static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, bool pair, cudaStream_t stream) {
+static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, bool pair, bool even_groups, cudaStream_t stream) {
   static int attr_rc = set_smem_attr(tc_conv_kernel<BLOCK_N, false>, kMaxSmem);
   static int attr_rc1 = set_smem_attr(tc_conv_kernel<BLOCK_N, true>, kMaxSmem);
   static int attr_rc2 = set_smem_attr(tc_conv_halo_kernel<BLOCK_N>, kMaxSmem);
@@ -1625,7 +1626,6 @@ static int launch_conv(const ConvParams& p, int smem_bytes, bool halo, bool pair
     const int ptiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     int pairs = ptiles < sm_count() / 2 ? ptiles : sm_count() / 2;
     // grouped schedule (PairSched) needs the pairs to split evenly over the N tiles: give up at most a few pairs for it
-    static const bool even_groups = !(getenv("UNETK_EVEN_GROUPS") && getenv("UNETK_EVEN_GROUPS")[0] == '0');
     // (3x3 halo kernels only: measured +5..16 % on the Cout = 1024 layers, -7 % on the short ConvT launches)
     if (even_groups && halo && p.num_n_tiles > 1 && pairs >= 4 * p.num_n_tiles && pairs % p.num_n_tiles != 0)
       pairs -= pairs % p.num_n_tiles;
@@ -1688,11 +1688,14 @@ static int launch_wgrad3x3_c64(const WgradParams& p, cudaStream_t stream) {
 
 }  // namespace unetk
 
-// internal debugging aid (not part of include/unetk.h): per-CTA idle-cycle counters of the last halo conv launch
-extern "C" int unetk_debug_counters(long long* host_out, int n) {
+#ifdef UNETK_DEBUG_COUNTERS
+// internal debugging aid of instrumented builds only (not part of include/unetk.h): per-CTA idle-cycle counters of the
+// last halo conv launch
+extern "C" __attribute__((visibility("default"))) int unetk_debug_counters(long long* host_out, int n) {
   if (n > 160 * 8) n = 160 * 8;
   return cudaMemcpyFromSymbol(host_out, unetk::tc::g_dbg, sizeof(long long) * n) == cudaSuccess ? 0 : -2;
 }
+#endif
 
 namespace unetk {
 
@@ -1718,23 +1721,8 @@ bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char**
   return true;
 }
 
-static bool pair_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("UNETK_NO_PAIR");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-static bool halo_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("UNETK_NO_HALO");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
+// Experiment switches travel in the upper bits of unetk_conv_args.algo / unetk_wgrad_args.algo (UNETK_TC_* in unetk.h):
+// the library reads no environment variables and keeps no mutable global state.
 
 int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   using namespace tc;
@@ -1752,8 +1740,9 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   // halo variant: 3x3, N tile <= 128 (the layers whose operand traffic is L2-bound), image at least one tile big
   // halo reuse also for N = 256 (CTA pairs): measured 5-9% faster on the deep layers once the MMA issue path was fixed
   // (the per-tap pair kernel is then bound by L2->SMEM operand traffic, which the halo tile cuts by ~40%)
-  static const bool halo_n256 = !(getenv("UNETK_HALO_N256") && getenv("UNETK_HALO_N256")[0] == '0');
-  const bool halo = a->mode == 1 && (block_n <= 128 || halo_n256) && g.rows_h >= 16 && g.rows_w >= 8 && !halo_disabled();
+  const int flags = a->algo & ~UNETK_ALGO_MASK;
+  const bool halo_n256 = !(flags & UNETK_TC_NO_HALO_N256);
+  const bool halo = a->mode == 1 && (block_n <= 128 || halo_n256) && g.rows_h >= 16 && g.rows_w >= 8 && !(flags & UNETK_TC_NO_HALO);
   PixelTile pt;
   if (halo) {
     pt.pw = 8; pt.ph = 16; pt.nb = 1;
@@ -1779,10 +1768,11 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   // CTA pairs (cta_group::2) whenever there are at least two pixel tiles: each CTA then loads only half of the weight rows
   // per K step.  Measured on B200 (batch 64) with the warp-uniform MMA issue: pairs gain 4-10% on the per-tap kernel and
   // 8-17% on the halo kernel (N <= 128).  (Before the issue path was fixed the halo kernel LOST 10-30% with pairs: the
-  // single-lane waterfall issue was the bottleneck and the leader CTA had to issue for both.)  UNETK_HALO_PAIR=0 and
-  // UNETK_NO_PAIR=1 keep the single-CTA kernels reachable for experiments.
-  static const bool halo_pair = !(getenv("UNETK_HALO_PAIR") && getenv("UNETK_HALO_PAIR")[0] == '0');
-  const bool pair = !pair_disabled() && pt.num_tiles() >= 2 && (!halo || halo_pair || (halo_n256 && block_n == 256));
+  // single-lane waterfall issue was the bottleneck and the leader CTA had to issue for both.)  UNETK_TC_NO_HALO_PAIR and
+  // UNETK_TC_NO_PAIR (algo flags) keep the single-CTA kernels reachable for experiments.
+  const bool halo_pair = !(flags & UNETK_TC_NO_HALO_PAIR);
+  const bool pair = !(flags & UNETK_TC_NO_PAIR) && pt.num_tiles() >= 2 && (!halo || halo_pair || (halo_n256 && block_n == 256));
+  const bool even_groups = !(flags & UNETK_TC_NO_EVEN_GROUPS);
   if ((rc = make_mat_map(&p.map_b, a->w, g.cout_total, ktotal, pair ? block_n / 2 : block_n))) return rc;
   p.mode = a->mode;
   p.taps = g.taps;
@@ -1836,9 +1826,9 @@ int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream) {
   p.off_bars = p.off_zbuf + (bnred ? 2 : 0) * kStagingBytes;
   const int smem_bytes = p.off_bars + kBarBytes + 1024;
   UNETK_REQUIRE(smem_bytes <= kMaxSmem && p.stages >= 2, "conv(tc): shared-memory plan failed (%d bytes, %d stages)", smem_bytes, p.stages);
-  if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, pair, stream);
-  if (block_n == 128) return launch_conv<128>(p, smem_bytes, halo, pair, stream);
-  return launch_conv<64>(p, smem_bytes, halo, pair, stream);
+  if (block_n == 256) return launch_conv<256>(p, smem_bytes, halo, pair, even_groups, stream);
+  if (block_n == 128) return launch_conv<128>(p, smem_bytes, halo, pair, even_groups, stream);
+  return launch_conv<64>(p, smem_bytes, halo, pair, even_groups, stream);
 }
 
 bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why) {
@@ -1888,8 +1878,7 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int rc;
-  static const bool no_c64 = getenv("UNETK_WGRAD_C64") && getenv("UNETK_WGRAD_C64")[0] == '0';
-  const bool c64 = a->u.c == 64 && !no_c64;   // nine taps per stage (tc_wgrad3x3_c64_kernel): U patch with a row of halo
+  const bool c64 = a->u.c == 64 && !(a->algo & UNETK_TC_NO_WGRAD_C64);   // nine taps per stage (tc_wgrad3x3_c64_kernel): U patch with a row of halo
   if ((rc = make_act_map(&p.map_u, a->u, 8, c64 ? 18 : 16, 1, 1, 0, 0))) return rc;
   if ((rc = make_act_map(&p.map_s[0], a->s, 10, 16, 1, 1, 0, 0))) return rc;
   const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1;
@@ -1914,7 +1903,7 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
 
 int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
   using namespace tc;
-  if (a->mode == 1 && a->u.h >= 16 && a->u.w >= 8 && !halo_disabled()) return tc_wgrad3x3_halo(a, stream);
+  if (a->mode == 1 && a->u.h >= 16 && a->u.w >= 8 && !(a->algo & UNETK_TC_NO_HALO)) return tc_wgrad3x3_halo(a, stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   const PixelTile pt = choose_pixel_tile(a->u.n, a->u.h, a->u.w);

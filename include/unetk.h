@@ -30,6 +30,13 @@
 extern "C" {
 #endif
 
+/* The shared library is built with -fvisibility=hidden: only the entry points declared here are exported. */
+#if defined(__GNUC__)
+#define UNETK_API __attribute__((visibility("default")))
+#else
+#define UNETK_API
+#endif
+
 #define UNETK_F32 0
 #define UNETK_BF16 1
 #define UNETK_U8 2   /* label buffers only */
@@ -44,6 +51,15 @@ extern "C" {
 #define UNETK_ALGO_AUTO 0   /* bf16 -> tcgen05, f32 -> SIMT */
 #define UNETK_ALGO_SIMT 1   /* CUDA-core FFMA kernels (any dtype; the fp32 parity tier) */
 #define UNETK_ALGO_TC 2     /* TMA + tcgen05.mma + TMEM (bf16 only) */
+#define UNETK_ALGO_MASK 0xff
+/* Experiment switches for the tcgen05 path, OR-ed into `algo` (the library reads no environment variables):
+ * each one turns OFF a default optimisation so that its effect can be measured (tools/run_layer.py). */
+#define UNETK_TC_NO_PAIR (1 << 8)        /* single-CTA kernels instead of cta_group::2 pairs */
+#define UNETK_TC_NO_HALO (1 << 9)        /* one TMA box per tap instead of one halo tile per 64-channel chunk */
+#define UNETK_TC_NO_EVEN_GROUPS (1 << 10) /* do not trim the pair count to a multiple of the N-tile count */
+#define UNETK_TC_NO_HALO_N256 (1 << 11)  /* halo reuse only for N tiles <= 128 */
+#define UNETK_TC_NO_HALO_PAIR (1 << 12)  /* halo kernel without CTA pairs */
+#define UNETK_TC_NO_WGRAD_C64 (1 << 13)  /* generic 3-tap weight-gradient kernel for 64-channel gradients */
 
 typedef struct unetk_tensor {
   void* ptr;
@@ -53,23 +69,46 @@ typedef struct unetk_tensor {
 } unetk_tensor;
 
 /* ---- library ---------------------------------------------------------------------------- */
-int unetk_version(void);
-const char* unetk_last_error(void);
+UNETK_API int unetk_version(void);
+UNETK_API const char* unetk_last_error(void);
 /* sm_count / compute capability of the current device */
-int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+UNETK_API int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* Caller-provided scratch sizes.  The library never allocates device memory; every accumulator / workspace the
+ * entry points below take is allocated (and, where stated, zeroed) by the caller.  unetk_query_workspace returns
+ * the size in BYTES of buffer `what` for a problem described by up to four integers, or a negative error code.
+ *   UNETK_WS_BN_STATS     (C)            stat_sum + stat_sumsq of unetk_conv / unetk_bn_stats        2*C doubles
+ *   UNETK_WS_BN_BWD_SUMS  (C)            unetk_bn_bwd_args.sums / unetk_conv_args.bn_sums            2*C doubles
+ *   UNETK_WS_HEAD_BN_SUMS (C, dout)      unetk_head_bn_bwd_args.sums                                 (3+dout)*C doubles
+ *   UNETK_WS_POOL_IDX     (N, H, W, C)   pool_idx of unetk_bn_relu_apply for a [N,H,W,C] input       N*(H/2)*(W/2)*(C/8) uint16
+ *   UNETK_WS_WGRAD        (mode, Cu, Cs) dw of unetk_wgrad                                           Cu*taps*Cs floats
+ *   UNETK_WS_DICE_ACCUM   (C)            unetk_dice_ce_args.accum                                    3C+2 doubles
+ *   UNETK_WS_DICE_COEF    (C)            unetk_dice_ce_args.coef                                     2C+1 floats
+ *   UNETK_WS_EVAL_ACCUM   (N, C)         unetk_eval_args.accum                                       N*(3C+2) doubles
+ *   UNETK_WS_CONFUSION    (C)            counts of unetk_argmax_confusion / unetk_eval_loss_metrics  4*C int64      */
+#define UNETK_WS_BN_STATS 0
+#define UNETK_WS_BN_BWD_SUMS 1
+#define UNETK_WS_HEAD_BN_SUMS 2
+#define UNETK_WS_POOL_IDX 3
+#define UNETK_WS_WGRAD 4
+#define UNETK_WS_DICE_ACCUM 5
+#define UNETK_WS_DICE_COEF 6
+#define UNETK_WS_EVAL_ACCUM 7
+#define UNETK_WS_CONFUSION 8
+UNETK_API int64_t unetk_query_workspace(int32_t what, int32_t a, int32_t b, int32_t c, int32_t d);
 
 /* ---- layout --------------------------------------------------------------------------------
  * unetk_im2col3x3_first: X.to(device) + first conv's implicit im2col (utils/training.py:45,
  * unet/unet.py:16 for down1).  x is NCHW fp32 [N,Cin,H,W]; out is NHWC [N,H,W,out.c] with
  * out[.., (r*3+s)*Cin + ci] = x[n, ci, h+r-1, w+s-1] (zero outside / for k >= 9*Cin).
  * The first conv then runs as a 1x1 contraction over out.c channels.                          */
-int unetk_im2col3x3_first(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w,
+UNETK_API int unetk_im2col3x3_first(const float* x_nchw, int32_t n, int32_t cin, int32_t h, int32_t w,
                           const unetk_tensor* out, void* stream);
 
 /* unetk_permute3: dst[i0*ds0+i1*ds1+i2*ds2] = (dst_dtype) src[i0*ss0+i1*ss1+i2*ss2], fp32 source.
  * Packs nn.Conv2d / nn.ConvTranspose2d weights (OIHW / IOHW fp32, unet/unet.py:16,19,59) into the
  * K-major operand layouts of the contraction kernels and unpacks weight gradients back.       */
-int unetk_permute3(const float* src, void* dst, int32_t dst_dtype, int32_t d0, int32_t d1, int32_t d2,
+UNETK_API int unetk_permute3(const float* src, void* dst, int32_t dst_dtype, int32_t d0, int32_t d1, int32_t d2,
                    int64_t ss0, int64_t ss1, int64_t ss2, int64_t ds0, int64_t ds1, int64_t ds2,
                    void* stream);
 
@@ -90,8 +129,8 @@ typedef struct unetk_wjob {
   void* dst1;
   int32_t kind, cout, cin, kpad;
 } unetk_wjob;
-int unetk_weights_pack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, int32_t dtype, void* stream);
-int unetk_weights_unpack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, void* dst_base, void* stream);
+UNETK_API int unetk_weights_pack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, int32_t dtype, void* stream);
+UNETK_API int unetk_weights_unpack(const unetk_wjob* jobs, const int32_t* tiles, int32_t ntiles, void* dst_base, void* stream);
 
 /* ---- contractions --------------------------------------------------------------------------
  * One implicit-GEMM entry for every "activation x weight" product of the path:
@@ -127,7 +166,7 @@ typedef struct unetk_conv_args {
   const float* bn_invstd;
   double* bn_sums;
 } unetk_conv_args;
-int unetk_conv(const unetk_conv_args* a, void* stream);
+UNETK_API int unetk_conv(const unetk_conv_args* a, void* stream);
 
 /* Weight gradient: dw[cu][t][cs] += sum_p u[p, cu] * s[gather(p, t), cs]   (fp32, accumulated)
  *   mode 0: 1 tap; mode 1: 3x3 pad 1 (u = dY, s = X); mode 2: 2x2 stride 2 (u = X low-res, s = dY hi-res)
@@ -139,13 +178,13 @@ typedef struct unetk_wgrad_args {
   int32_t mode;
   int32_t algo;
 } unetk_wgrad_args;
-int unetk_wgrad(const unetk_wgrad_args* a, void* stream);
+UNETK_API int unetk_wgrad(const unetk_wgrad_args* a, void* stream);
 
 /* per-channel sum over all pixels: out[c] += sum_p t[p, c]  (bias gradients of ConvTranspose2d) */
-int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream);
+UNETK_API int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream);
 
 /* ---- BatchNorm + ReLU + MaxPool (unet/unet.py:17-18,20-21,40) ------------------------------- */
-int unetk_bn_stats(const unetk_tensor* z, double* sum, double* sumsq, void* stream);
+UNETK_API int unetk_bn_stats(const unetk_tensor* z, double* sum, double* sumsq, void* stream);
 
 typedef struct unetk_bn_finalize_args {
   const double* sum;
@@ -165,12 +204,12 @@ typedef struct unetk_bn_finalize_args {
   float* mean;   /* batch mean of the bias-free conv output */
   float* invstd;
 } unetk_bn_finalize_args;
-int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream);
+UNETK_API int unetk_bn_finalize(const unetk_bn_finalize_args* a, void* stream);
 
 /* a = relu(z*scale+shift); optionally pooled = maxpool2x2(a) in the same pass (pooled->ptr may be NULL).
  * pool_idx (optional, [N,H/2,W/2,C/8] uint16): 2 bits per channel = window position (2*dy+dx) of the FIRST maximum in
  * scan order -- what torch's max_pool2d backward routes the gradient to; consumed by unetk_bn_relu_bwd_*.            */
-int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift,
+UNETK_API int unetk_bn_relu_apply(const unetk_tensor* z, const float* scale, const float* shift,
                         const unetk_tensor* a, const unetk_tensor* pooled, uint16_t* pool_idx, void* stream);
 
 /* Backward of (BN train -> ReLU [-> MaxPool]):
@@ -191,15 +230,15 @@ typedef struct unetk_bn_bwd_args {
   float* dbeta;
   const void* pool_idx; /* uint16 [N,H/2,W/2,C/8] from unetk_bn_relu_apply; required when dpool is given */
 } unetk_bn_bwd_args;
-int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream);
-int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream);
+UNETK_API int unetk_bn_relu_bwd_reduce(const unetk_bn_bwd_args* a, void* stream);
+UNETK_API int unetk_bn_relu_bwd_apply(const unetk_bn_bwd_args* a, void* stream);
 
 /* ---- 1x1 classifier head (unet/unet.py:91) -------------------------------------------------- */
 /* logits NCHW fp32 [N,dout,H,W] = a[N,H,W,64] . w[dout][cin] + b */
-int unetk_head_fprop(const unetk_tensor* a, const float* w, const float* b, int32_t dout,
+UNETK_API int unetk_head_fprop(const unetk_tensor* a, const float* w, const float* b, int32_t dout,
                      float* logits_nchw, void* stream);
 /* da = dlogits . w ; dw[dout][cin] += ; db[dout] += */
-int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float* w, int32_t dout,
+UNETK_API int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float* w, int32_t dout,
                    const unetk_tensor* da, float* dw, float* db, void* stream);
 
 /* ---- weighted Dice + CE loss (utils/weighted_loss.py:31-98,140-166) --------------------------- */
@@ -218,19 +257,19 @@ typedef struct unetk_dice_ce_args {
   const float* grad_out; /* [1] device scalar (bwd) */
   float* dlogits;        /* NCHW fp32 (bwd) */
 } unetk_dice_ce_args;
-int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream);
-int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
+UNETK_API int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream);
+UNETK_API int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
 
 /* ---- confusion-count metrics (utils/MetricsHistory.py:65-86) ---------------------------------- */
 /* pred NCHW fp32 [N,C,H,W] (N images at once), label [N,H,W] int64.
  * counts[4][C] (tp, fp, fn, tn; int64) are ACCUMULATED; argmax_out (optional) receives the hard mask. */
-int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
+UNETK_API int unetk_argmax_confusion(const float* pred, const int64_t* label, int32_t n, int32_t c, int32_t h,
                            int32_t w, int64_t* counts, uint8_t* argmax_out, int32_t* status, void* stream);
 
 /* BatchNorm apply + ReLU of the last block fused with the head forward (unet/unet.py:20-21 -> :91).  `a` may be NULL
  * (or a->ptr NULL): the activation is then not stored at all -- with unetk_head_bn_bwd_* nothing reads it again.
  * dout 1..4 and C == 64 (the U-Net head), else UNETK_ERR_UNSUPPORTED (use unetk_bn_relu_apply + unetk_head_fprop). */
-int unetk_bn_relu_head_fprop(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
+UNETK_API int unetk_bn_relu_head_fprop(const unetk_tensor* z, const float* scale, const float* shift, const unetk_tensor* a,
                              const float* w_head, const float* b_head, int32_t dout, float* logits_nchw, void* stream);
 
 /* ---- head backward fused with the BatchNorm backward of the last block (unet/unet.py:91 <- :21-25) ----------- */
@@ -255,8 +294,8 @@ typedef struct unetk_head_bn_bwd_args {
   float* dw_head;  /* apply only, [dout][C] */
   float* db_head;  /* apply only, [dout] (may be NULL) */
 } unetk_head_bn_bwd_args;
-int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream);
-int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream);
+UNETK_API int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream);
+UNETK_API int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream);
 
 /* ---- evaluation tail (utils/utils.py:51-75,101-115; utils/training.py:93-101) ------------------- */
 /* One entry per image of a batch (device array).  The network output [N,C,TH,TW] holds image i in the window
@@ -272,7 +311,7 @@ typedef struct unetk_eval_image {
 
 /* process_batch_reverse (utils/utils.py:101-115): crop + F.interpolate(mode 0 'bilinear', align_corners=False |
  * mode 1 'nearest') of every image of the batch in one launch.  max_out_pixels = max_i out_h*out_w. */
-int unetk_crop_resize(const float* src_nchw, int32_t n, int32_t c, int32_t th, int32_t tw,
+UNETK_API int unetk_crop_resize(const float* src_nchw, int32_t n, int32_t c, int32_t th, int32_t tw,
                       const unetk_eval_image* images, int32_t max_out_pixels, int32_t mode, float* out_packed,
                       void* stream);
 
@@ -296,7 +335,7 @@ typedef struct unetk_eval_args {
   int64_t* counts;       /* [4][C] tp, fp, fn, tn ACCUMULATED (MetricsHistory.accumulate) */
   int32_t* status;       /* |= 1 if a label is outside [0,C) */
 } unetk_eval_args;
-int unetk_eval_loss_metrics(const unetk_eval_args* a, void* stream);
+UNETK_API int unetk_eval_loss_metrics(const unetk_eval_args* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,10 +71,10 @@ print(f"{a.op} cin={a.cin} cout={a.cout} hw={a.hw} batch={a.batch}: {ms:.3f} ms 
 if os.environ.get("UNETK_DBG") == "1":
     import ctypes
     buf = (ctypes.c_longlong * (148 * 8))()
-    L.lib().unetk_debug_counters(buf, 148 * 8)
+    L.lib().unetk_debug_counters(buf, 148 * 8)     # only in builds with UNETK_NVCC_EXTRA=-DUNETK_DEBUG_COUNTERS
     import numpy as np
     d = np.array(buf[:]).reshape(148, 8)
-    if os.environ.get("UNETK_HALO_PAIR") == "1":
+    if not (L.TC_FLAGS & (L.TC_FLAG_BITS["no_halo_pair"] | L.TC_FLAG_BITS["no_pair"])):
         d = d[::2]     # leader CTAs hold the MMA counters
     names = ["prod wait emptyA", "mma wait fullA", "mma wait fullB", "mma wait tmem_empty", "mma total",
              "epi0 wait tmem_full", "epi0 in epilogue", "epi0 total"]
