@@ -99,9 +99,11 @@ class ClockSampler:
 # CPU leg: the oracle port (the only place besides tests/ and smoke() that executes oracle/)
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_steps(steps, warmup, batch=4):
+    """Config[0] of BASELINE.json on the host cores.  Uses the UNMODIFIED reference modules staged under oracle/_ref/
+    (oracle/build_ref.py; kind "reference") and falls back to the oracle port (kind "port") when they did not travel."""
     import torch
     from image_segmentation_b200.utils.synthetic import make_batch
-    from oracle import loss_oracle, metrics_oracle, unet_oracle
+    from oracle import ref_shim
     # every host core: torchrun exports OMP_NUM_THREADS=1 for its workers, which would time the CPU path on one thread
     try:
         cores = len(os.sched_getaffinity(0))
@@ -109,31 +111,53 @@ def cpu_reference_steps(steps, warmup, batch=4):
         cores = os.cpu_count() or 1
     torch.set_num_threads(max(1, cores))
     torch.manual_seed(0)
-    m = unet_oracle.OracleUNet(3, 3, native_ops=True).train()   # the reference's own ATen operators (F.batch_norm, ...)
-    opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
     w = torch.tensor(CLASS_W3)
     x, y = make_batch(batch, H, W, 3, 3, seed=1234)
+    if ref_shim.available():
+        ref = ref_shim.load()
+        kind = "reference"
+        m = ref.unet(3, 3).train()                                   # unet/unet.py:67
+        loss_fn = ref.WeightedDiceCELoss(smooth_dice=1, class_weights=w)   # utils/weighted_loss.py:102
+        agg = ref.MetricsHistory(3)                                  # utils/MetricsHistory.py:9
+
+        def loss_of(pred):
+            return loss_fn(pred, y.squeeze(1))
+
+        def metrics_of(pred):
+            for j in range(batch):
+                agg.accumulate(pred[j].detach(), y[j])
+    else:
+        from oracle import loss_oracle, metrics_oracle, unet_oracle
+        kind = "port"
+        m = unet_oracle.OracleUNet(3, 3, native_ops=True).train()   # the reference's own ATen operators (F.batch_norm, ...)
+
+        def loss_of(pred):
+            return loss_oracle.dice_ce_loss(pred, y, smooth_dice=1.0, class_weights=w, dtype=torch.float32)
+
+        def metrics_of(pred):
+            for j in range(batch):
+                metrics_oracle.confusion_counts(pred[j].detach().numpy(), y[j].numpy(), 3)
+    opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         pred = m(x)
-        loss = loss_oracle.dice_ce_loss(pred, y, smooth_dice=1.0, class_weights=w, dtype=torch.float32)   # fp32 like the reference
+        loss = loss_of(pred)
         loss.backward()
         opt.step()
         opt.zero_grad()
-        for j in range(batch):
-            metrics_oracle.confusion_counts(pred[j].detach().numpy(), y[j].numpy(), 3)
+        metrics_of(pred)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return batch, times, torch.get_num_threads()
+    return batch, times, torch.get_num_threads(), kind
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch, times, threads = cpu_reference_steps(args.steps, args.warmup)
+    batch, times, threads, kind = cpu_reference_steps(args.steps, args.warmup)
     total = sum(times)
     value = batch * len(times) / total
     line = {
@@ -142,7 +166,7 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "unet(3,3) 256x256 training step (fwd+loss+bwd+AdamW+metrics), CPU fp32, "
                                f"bounded sample: batch {batch} per step instead of 64"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"{len(times)} steps of batch {batch} at 256x256 on {threads} threads "
                                    f"(os.cpu_count()={os.cpu_count()})"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -287,53 +311,86 @@ def run_gpu_arm(args):
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
 
     # ---- per-launch instrumentation of the contraction kernels (extra steps, not part of `value`; every rank runs
-    #      them -- they contain collectives -- but only rank 0 records events) ----
+    #      them -- they contain collectives -- but only rank 0 records events).
+    #      The instrumented steps are EAGER (one CUDA event pair per launch), so the host is slower than the GPU.  To time
+    #      the kernels the way they run inside the graphed step -- back to back, at sustained clocks -- every
+    #      instrumented step is enqueued behind a spin kernel (torch.cuda._sleep) long enough for the host to finish
+    #      enqueueing the whole step; `share_of_step` (contraction time / GPU time of the step, spin excluded) shows
+    #      whether that worked, and no roofline figure is printed when it is below 0.5. ----
     roof = None
     records = []
-    prof_steps = 2
-    if rank == 0:
-        L.PROFILE_HOOK = records
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_steps = 3
+    spin_cycles = int(args.spin_ms * 1e-3 * 1.9e9)
+    marks = []
     torch.cuda.synchronize()
-    e0.record()
-    for _ in range(prof_steps):
+    for i in range(prof_steps):
+        if rank == 0:
+            L.PROFILE_HOOK = records
+        if spin_cycles > 0:
+            torch.cuda._sleep(spin_cycles)
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
         step_resident()
-    e1.record()
-    torch.cuda.synchronize()
-    L.PROFILE_HOOK = None
+        m1.record()
+        marks.append((m0, m1))
+        L.PROFILE_HOOK = None
+        torch.cuda.synchronize()
     if rank == 0:
-        step_ms = e0.elapsed_time(e1) / prof_steps
-        flops = sum(r[1] for r in records if r[0] in ("conv", "wgrad"))
-        kms = sum(r[2].elapsed_time(r[3]) for r in records if r[0] in ("conv", "wgrad"))
+        step_ms = sum(m0.elapsed_time(m1) for m0, m1 in marks) / prof_steps
+        fam = {}
+
+        def family(r):
+            if r[0] == "wgrad":
+                return "wgrad"
+            return "conv3x3" if r[5] == L.MODE_3X3 else ("convT" if r[5] in (L.MODE_CONVT, L.MODE_CONVT_GATHER) else "conv1x1")
+        for r in records:
+            if r[0] in ("conv", "wgrad"):
+                f = fam.setdefault(family(r), [0.0, 0.0, 0])
+                f[0] += r[1]
+                f[1] += r[2].elapsed_time(r[3])
+                f[2] += 1
+        flops = sum(f[0] for f in fam.values())
+        kms = sum(f[1] for f in fam.values())
         by_kind = {}
         for r in records:
             by_kind.setdefault(r[0], [0.0, 0.0])
             by_kind[r[0]][0] += r[2].elapsed_time(r[3]) / prof_steps
             by_kind[r[0]][1] += r[1] / prof_steps
+        share = kms / prof_steps / step_ms if step_ms > 0 else 0.0
         achieved = flops / (kms * 1e-3) / 1e12 if kms > 0 else 0.0
+        valid = share >= 0.5
         dominant = None
         dpath = os.path.join(ROOT, "profiles", "dominant_launch.json")
         if os.path.isfile(dpath):
             dominant = json.load(open(dpath))
-        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["sustained"], "frac_of_burst": achieved / peaks["burst"],
+        step_tflops = (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved if valid else None, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["sustained"] if valid else None,
+                "frac_of_burst": achieved / peaks["burst"] if valid else None,
                 "traffic": dominant["traffic_bytes"] if dominant else None,
-                "peak_source": peaks["source"] + ", sustained figure (kernels timed inside a long step)",
-                "kernel": "tc::tc_conv_halo2_kernel / tc_conv2_kernel / tc_wgrad3x3_kernel (tcgen05 implicit GEMM family)",
-                "how": f"sum of algorithmic FLOPs / sum of CUDA-event durations over every unetk_conv and unetk_wgrad launch "
-                       f"of {prof_steps} instrumented steps; `traffic` is the ncu DRAM byte count of the dominant launch "
-                       "described in `dominant_launch` (profiles/dominant_launch.json)",
+                "peak_source": peaks["source"] + ", sustained figure (kernels timed back to back inside a full step); "
+                               "frac_of_burst uses the burst figure",
+                "kernel": "tc::tc_conv_halo2_kernel / tc_conv2_kernel / tc_wgrad3x3*_kernel (tcgen05 implicit-GEMM family)",
+                "how": f"sum of algorithmic FLOPs / sum of CUDA-event durations over every unetk_conv and unetk_wgrad launch of "
+                       f"{prof_steps} instrumented eager steps, each enqueued behind a {args.spin_ms:.0f} ms spin kernel so that "
+                       "the launches run back to back; refused (null) when share_of_step < 0.5; `traffic` = ncu DRAM bytes of "
+                       "the dominant launch (profiles/dominant_launch.json)",
+                "valid": valid,
+                "share_of_step": share,
+                "instrumented_step_ms": step_ms,
+                "families": {k: {"tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None, "ms_per_step": v[1] / prof_steps,
+                                 "launches_per_step": v[2] // prof_steps} for k, v in sorted(fam.items())},
                 "dominant_launch": dominant,
-                "share_of_step": kms / prof_steps / step_ms,
                 "ms_per_step_by_kernel": {k: round(v[0], 3) for k, v in sorted(by_kind.items())},
-                "step_tflops": (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12,
-                "step_frac_of_sustained_peak": (B * FLOP_PER_IMAGE_TRAIN / (ms_per_step * 1e-3)) / 1e12 / peaks["sustained"]}
+                "step_tflops": step_tflops,
+                "step_frac": step_tflops / peaks["sustained"],
+                "step_frac_of_burst": step_tflops / peaks["burst"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        b, times, threads = cpu_reference_steps(steps=3, warmup=1)
+        b, times, threads, kind = cpu_reference_steps(steps=3, warmup=1)
         v = b * len(times) / sum(times)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
                "sample": f"3 steps of batch {b} at 256x256 (fp32, {threads} threads, os.cpu_count()={os.cpu_count()})"}
 
     if rank == 0:
@@ -376,6 +433,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
+    ap.add_argument("--spin-ms", type=float, default=120.0,
+                    help="length of the spin kernel in front of each instrumented (roofline) step; 0 disables it")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -205,11 +205,11 @@ def nhwc(t: Optional[torch.Tensor]) -> Tensor:
 
 # ---- instrumentation (bench.py): launch counter and optional per-call CUDA-event records ----------
 COUNTERS = {"launches": 0}
-PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start_event, end_event, label)
+PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start_event, end_event, label, tag)
 LABEL = ""            # free-form tag of the layer being launched (set by the engine, read by the hook)
 
 
-def _run(kind, nlaunch, flops, fn, *args):
+def _run(kind, nlaunch, flops, fn, *args, tag=None):
     COUNTERS["launches"] += nlaunch
     hook = PROFILE_HOOK
     if hook is None:
@@ -219,7 +219,7 @@ def _run(kind, nlaunch, flops, fn, *args):
     e0.record()
     check(fn(*args))
     e1.record()
-    hook.append((kind, flops, e0, e1, LABEL))
+    hook.append((kind, flops, e0, e1, LABEL, tag))
 
 
 # ---- thin wrappers ------------------------------------------------------------------------------
@@ -281,7 +281,7 @@ def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUT
         else:
             algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * 4 * x.shape[3] * y.shape[3]
     simt = algo == ALGO_SIMT or (algo == ALGO_AUTO and x.dtype != torch.bfloat16)
-    _run("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, C.byref(a), stream_ptr())
+    _run("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, C.byref(a), stream_ptr(), tag=mode)
 
 
 def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
@@ -289,7 +289,7 @@ def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
     if algo_flops is None:
         taps = (1, 9, 4)[mode]
         algo_flops = 2 * u.shape[0] * u.shape[1] * u.shape[2] * taps * u.shape[3] * s.shape[3]
-    _run("wgrad", 1, algo_flops, lib().unetk_wgrad, C.byref(a), stream_ptr())
+    _run("wgrad", 1, algo_flops, lib().unetk_wgrad, C.byref(a), stream_ptr(), tag=mode)
 
 
 def channel_sum(t, out):

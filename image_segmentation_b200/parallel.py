@@ -8,8 +8,12 @@ completion order (head, up4 .. up1, down5 .. down1); as soon as a bucket of that
 all-reduce is enqueued (``async_op=True``: NCCL's stream waits for the kernels enqueued so far and
 then runs next to the dgrad/wgrad kernels that follow).  Averaging is folded into the upstream
 gradient (``d logits / world``; every backward kernel is linear in it), so no extra pass over the
-gradients exists.  BatchNorm statistics and Dice sums stay per rank, exactly as the reference would
-behave under stock DistributedDataParallel (it has no SyncBN).
+gradients exists.  BatchNorm batch statistics and Dice sums stay per rank (the reference has no SyncBN).
+
+Difference from stock DistributedDataParallel: DDP's default ``broadcast_buffers=True`` re-broadcasts rank 0's
+BatchNorm running statistics at every forward pass; here the buffers are broadcast once at construction and then
+evolve per rank.  Call ``sync_buffers()`` before evaluating or checkpointing (``eval_loop`` followed by
+``MetricsHistory.all_reduce`` must see the same running statistics on every rank).
 """
 from __future__ import annotations
 
@@ -44,6 +48,11 @@ class DataParallelUNet:
     def _on_bucket(self, plan, end_offset: int):
         if not self._enabled or self.world == 1:
             return
+        if getattr(self, "_plan_generation", None) != (id(plan), getattr(plan, "generation", 0)):
+            # first bucket of a new backward pass: a previous pass that raised midway must not leave stale offsets / works
+            self._plan_generation = (id(plan), getattr(plan, "generation", 0))
+            self._works = []
+            self._sent = 0
         if end_offset - self._sent >= self.bucket_elems:
             self._launch(plan, end_offset)
 
@@ -60,6 +69,12 @@ class DataParallelUNet:
                 w.wait()          # current stream waits for NCCL; the host does not block
         self._works = []
         self._sent = 0
+        self._plan_generation = None
+
+    def sync_buffers(self, src: int = 0):
+        """Broadcast rank ``src``'s BatchNorm running statistics (what DDP's broadcast_buffers does every forward)."""
+        for t in self.model.buffers():
+            dist.broadcast(t.data, src=src, group=self.group)
 
     # Gradient accumulation (utils/training.py:49-56): every micro-batch is reduced.  The flat buffer holds only
     # the CURRENT backward's gradients (autograd adds them to .grad afterwards), so skipping the reduction for all

@@ -361,7 +361,12 @@ class UNetPlan:
                        stat_sum=l.stat_sum if training else None, stat_sumsq=l.stat_sumsq if training else None,
                        algo=self.algo, algo_flops=(2 * count * 9 * l.cin * l.cout) if l.first else None)
             bn = l.bn
-            momentum = bn.momentum if bn.momentum is not None else 0.1
+            if bn.momentum is None:
+                # nn.BatchNorm2d(momentum=None) means a cumulative moving average whose factor 1/num_batches_tracked lives
+                # on the device; reading it would stall the stream (and break graph capture), so it is refused loudly
+                raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not supported by the fused "
+                                          "engine; the reference always uses the default momentum 0.1 (unet/unet.py:17,20)")
+            momentum = bn.momentum
             track = bn.track_running_stats and bn.running_mean is not None
             L.bn_finalize(l.stat_sum, l.stat_sumsq, count, l.cout, training, bn.weight, bn.bias, l.conv.bias,
                           bn.running_mean if track else None, bn.running_var if track else None,

@@ -80,6 +80,7 @@ class unet(nn.Module):
         self.precision = "bf16"
         self.conv_algo = "auto"
         self._engine = None
+        self._train_graph = None
 
     def forward(self, x):
         if self._engine is None:
@@ -89,9 +90,14 @@ class unet(nn.Module):
     def _apply(self, fn, *args, **kwargs):
         # .to()/.cuda()/.double() move or retype parameters: cached device buffers are then stale
         self._engine = None
+        self._train_graph = None      # a captured step replays into the dropped engine's buffers (utils/training.py)
         return super()._apply(fn, *args, **kwargs)
 
     def __getstate__(self):
+        # device-side caches and process-group hooks never travel with a pickled / deep-copied model
         state = self.__dict__.copy()
         state["_engine"] = None
+        state["_train_graph"] = None
+        for name in ("_bucket_hook", "_backward_done_hook", "_grad_scale"):
+            state.pop(name, None)
         return state

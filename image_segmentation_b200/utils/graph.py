@@ -32,6 +32,7 @@ class GraphedTrainStep:
             y = y[:, 0]
         self.y = y.long().contiguous().clone()
         self.loss = None
+        self._engine = None
         model.train()
         # warm-up on a side stream (allocator pools, cudaFuncSetAttribute, optimizer state) as torch recommends
         optimizer.zero_grad(set_to_none=True)      # stale .grad tensors would be accumulated into by the warm-up step
@@ -47,6 +48,10 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._eager_step()
         torch.cuda.synchronize(dev)
+        # the graph replays into the buffers of THIS engine (activations, operand packs, scratch): keep it alive and refuse
+        # to replay once the model has dropped it (model.to(...) / .float() re-create the engine)
+        self._engine = getattr(model, "_engine", None)
+        self._param_ptrs = tuple(p.data_ptr() for p in params)
 
     def _eager_step(self):
         pred = self.model(self.x)
@@ -59,6 +64,10 @@ class GraphedTrainStep:
         return loss.detach()
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if getattr(self.model, "_engine", None) is not self._engine or \
+                tuple(p.data_ptr() for p in self.model.parameters()) != self._param_ptrs:
+            raise RuntimeError("this GraphedTrainStep was captured for buffers the model no longer owns (the model was "
+                               "moved / re-typed after the capture); capture a new one")
         self.x.copy_(x, non_blocking=True)
         if y.dim() == 4:
             y = y[:, 0]

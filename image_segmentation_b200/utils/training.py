@@ -9,6 +9,7 @@ Changes that do not alter results:
   * the loss value is read back once per optimiser step (as the reference does) -- no other syncs.
 """
 import os
+import sys
 
 import torch
 
@@ -25,7 +26,12 @@ except Exception:  # pragma: no cover
 
 
 def _progress(iterable, **kw):
-    if _tqdm is None or os.environ.get("UNETK_NO_TQDM", "1") == "1":
+    # the reference always shows tqdm bars; they are shown here as well unless stdout is not a terminal (logs, tests)
+    # or UNETK_NO_TQDM=1
+    quiet = os.environ.get("UNETK_NO_TQDM")
+    if quiet is None:
+        quiet = "0" if sys.stderr.isatty() else "1"
+    if _tqdm is None or quiet == "1":
         class _P:
             def __init__(self, it):
                 self._it = it
@@ -64,13 +70,43 @@ def _invalidate_weight_packs(model):
                 plan._pack_versions = None
 
 
+def _graph_signature(model, loss_fn, optimizer, X, y):
+    """Everything a captured step bakes in: batch shape, the addresses of parameters and optimizer state, the optimizer's
+    hyper-parameters (python floats are frozen into the capture; tensors are read at replay time, so only their address
+    counts), the loss configuration and the model's precision / kernel selection.  Any difference => re-capture."""
+    def norm(v):
+        if torch.is_tensor(v):
+            return ("tensor", v.data_ptr())
+        if isinstance(v, (list, tuple)):
+            return tuple(norm(e) for e in v)
+        return v
+    params = [p for g in optimizer.param_groups for p in g["params"]]
+    state = tuple(t.data_ptr() for p in params for _, t in sorted(optimizer.state.get(p, {}).items()) if torch.is_tensor(t))
+    hyper = tuple(tuple((k, norm(v)) for k, v in sorted(g.items()) if k != "params") for g in optimizer.param_groups)
+    cw = getattr(loss_fn, "class_weights", None)
+    loss_cfg = (getattr(loss_fn, "dice_weight", None), getattr(loss_fn, "ce_weight", None),
+                getattr(loss_fn, "ignore_index", None), getattr(loss_fn, "smooth_dice", None),
+                None if cw is None else (cw.data_ptr(), cw._version))
+    return (tuple(X.shape), tuple(y.shape), tuple(p.data_ptr() for p in model.parameters()),
+            tuple(p.data_ptr() for p in params), state, hyper, loss_cfg, model.precision, model.conv_algo, model.training)
+
+
 def _graph_for(model, loss_fn, optimizer, X, y):
-    """Captured step for this (model, loss, optimizer, batch shape); cached on the model across epochs."""
+    """Captured step for this (model, loss, optimizer, batch shape); cached on the model across epochs.
+
+    The cache entry holds STRONG references to the loss, the optimizer and the engine whose buffers the graph replays
+    into, and is compared by identity (``is``) plus ``_graph_signature``: a moved model (``unet._apply`` drops the engine
+    and this cache), a restored optimizer state (``load_state_dict`` replaces the state tensors), a changed learning
+    rate / weight decay, or a different loss object all lead to a fresh capture instead of a replay into stale memory."""
     from .graph import GraphedTrainStep
-    key = (id(loss_fn), id(optimizer), tuple(X.shape), tuple(y.shape))
+    sig = _graph_signature(model, loss_fn, optimizer, X, y)
     cached = getattr(model, "_train_graph", None)
-    if cached is not None and cached[0] == key:
-        return cached[1]
+    if cached is not None:
+        c_loss, c_opt, c_engine, c_sig, g = cached
+        if c_loss is loss_fn and c_opt is optimizer and c_engine is model._engine and c_sig == sig:
+            return g
+        model._train_graph = None        # stale: release the old graph (and its private memory pool) before re-capturing
+        del cached, g
     try:
         g = GraphedTrainStep(model, loss_fn, optimizer, X, y, metrics=None, warmup=0)
     except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
@@ -78,7 +114,8 @@ def _graph_for(model, loss_fn, optimizer, X, y):
         _invalidate_weight_packs(model)
         optimizer.zero_grad(set_to_none=True)
         return None
-    model._train_graph = (key, g)
+    # the signature is taken AFTER the capture: its warm-up may have created optimizer state
+    model._train_graph = (loss_fn, optimizer, model._engine, _graph_signature(model, loss_fn, optimizer, X, y), g)
     return g
 
 
@@ -142,6 +179,12 @@ def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device
         for value in reader.drain():
             total_loss += value
             processed_batches += 1
+    # out-of-range labels (the reference raises from scatter_, utils/weighted_loss.py:58): graph replays never run the
+    # Python side of the loss again, so the device flag is read here, once per epoch, after the queue has drained
+    status = getattr(loss_fn, "_status", None)
+    if status is not None and torch.device(device).type == "cuda":
+        status.publish()
+        status.check(True, type(loss_fn).__name__)
     avg_loss = total_loss / processed_batches if processed_batches > 0 else 0
     print(f"Training Avg loss (per effective batch): {avg_loss:>8f}")
     return avg_loss
@@ -251,29 +294,47 @@ def eval_loop(dataloader, model, loss_fn, device, target_size, agg):
 def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, val_dataloader, accumulation_steps,
           device, train_loss_fn, val_loss_fn, target_size, scheduler=None, agg=None, load=True, save=True,
           num_classes=4, ignore_index=3, epochs=100):
-    """Train/evaluate for ``epochs`` epochs with best-mIoU checkpointing and resume (reference :453-617)."""
-    model.to(device)
+    """Train/evaluate for ``epochs`` epochs with best-mIoU checkpointing and resume (reference :453-617).
+
+    Same printed lines, files and checkpoint keys as the reference.  Deliberate differences: the model is moved to
+    ``device`` if it is not there yet (the reference expects the caller to have done it), and a missing ``agg`` is
+    created instead of failing in ``eval_loop``."""
+    dev = torch.device(device)
+    p0 = next(model.parameters(), None)
+    if p0 is not None and (p0.device.type != dev.type or (dev.index is not None and p0.device.index != dev.index)):
+        model.to(device)
     if agg is None:
         agg = MetricsHistory(num_classes, ignore_index)
-    best = {"best_dev_dice": -1.0, "best_dev_miou": -1.0, "best_dev_loss": float("inf")}
+    best = {"best_dev_dice": -float("inf"), "best_dev_miou": -float("inf"), "best_dev_loss": float("inf")}
     start_epoch = 0
     path = os.path.join(model_save_dir, model_save_name)
-    if save:
-        os.makedirs(os.path.join(model_save_dir, "metrics"), exist_ok=True)
+    os.makedirs(model_save_dir, exist_ok=True)
+    os.makedirs(os.path.join(model_save_dir, "metrics"), exist_ok=True)
     if load and os.path.isfile(path):
-        print(f"Loading checkpoint from {path}")
+        print(f"Loading checkpoint from: {path}")
         ckpt = torch.load(path, map_location=device, weights_only=True)
         model.load_state_dict(ckpt["model_state_dict"])
-        for key, obj in (("optimizer_state_dict", optimizer), ("scheduler_state_dict", scheduler)):
-            if obj is not None and key in ckpt:
-                try:
-                    obj.load_state_dict(ckpt[key])
-                except Exception as e:  # same tolerance as the reference
-                    print(f" -> could not restore {key}: {e}")
+        print(" -> Model state loaded.")
+        for key, obj, what in (("optimizer_state_dict", optimizer, "Optimizer"), ("scheduler_state_dict", scheduler, "Scheduler")):
+            try:
+                obj.load_state_dict(ckpt[key])
+                print(f" -> {what} state loaded.")
+            except Exception as e:  # same tolerance (and wording) as the reference: a missing scheduler lands here too
+                print(f" -> Warning: Could not load {what.lower()} state: {e}. {what} will start from scratch.")
+        # the reference replaces the caller's history object on resume (checkpoints never contain one, :530-536)
+        try:
+            agg = ckpt.get("history")
+            agg.to(device)
+            print(" -> Metrics History loaded.")
+        except Exception:
+            print(" -> No metric history saved")
+            agg = MetricsHistory(num_classes, ignore_index)
         start_epoch = ckpt.get("epoch", 0)
         for k in best:
             best[k] = ckpt.get(k, best[k])
         print(f" -> Resuming training from epoch {start_epoch + 1}")
+        print(f" -> Loaded best metrics: Dice={best['best_dev_dice']:.6f}, mIoU={best['best_dev_miou']:.6f}, "
+              f"Loss={best['best_dev_loss']:.6f}")
         print(f" -> Notes from checkpoint: {ckpt.get('notes', 'N/A')}")
     else:
         print(f"Checkpoint file not found at {path}. Starting training from scratch.")
@@ -303,4 +364,5 @@ def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, v
     print(f"Best validation IoU score achieved: {best['best_dev_miou']:.6f}")
     print(f"Corresponding validation dice: {best['best_dev_dice']:.6f}")
     print(f"Corresponding validation loss: {best['best_dev_loss']:.6f}")
+    print(f"Best model saved to: {os.path.join(model_save_dir, model_save_name)}")
     return best

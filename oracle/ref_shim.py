@@ -17,7 +17,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("UNET_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/build_ref.py (git-ignored copies)
+
+
+def _default_root() -> str:
+    for cand in (os.environ.get("UNET_REFERENCE_ROOT"), "/root/reference", _STAGED):
+        if cand and os.path.isfile(os.path.join(cand, "unet", "unet.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def available() -> bool:
