@@ -209,23 +209,58 @@ PROFILE_HOOK = None   # set to a list to collect (kind, algorithmic_flops, start
 LABEL = ""            # free-form tag of the layer being launched (set by the engine, read by the hook)
 
 
+class Call:
+    """One prepared C-ABI call: the ctypes argument structs are built ONCE (device pointers inside a plan are stable)
+    and the call is then replayed every step with only the stream changing -- the host cost of a launch drops from a
+    struct build + stride checks to one foreign-function call.  `keep` pins the tensors the structs point into.
+    Pointer fields that change per step (gradients living in a per-backward flat buffer) are re-pointed with ``patch``."""
+    __slots__ = ("kind", "nlaunch", "flops", "fn", "args", "tag", "label", "keep", "patches")
+
+    def __init__(self, kind, nlaunch, flops, fn, args, tag=None, keep=None, label=None):
+        self.kind, self.nlaunch, self.flops, self.fn, self.args = kind, nlaunch, flops or 0, fn, tuple(args)
+        self.tag, self.keep, self.label, self.patches = tag, keep, label, None
+
+    def patch_ptr(self, struct, field: str, byte_offset: int):
+        """Before every call, ``struct.field = base_ptr + byte_offset`` (base_ptr is passed to __call__)."""
+        if self.patches is None:
+            self.patches = []
+        self.patches.append((struct, field, byte_offset))
+        return self
+
+    def __call__(self, stream: int, base_ptr: int = 0):
+        COUNTERS["launches"] += self.nlaunch
+        if self.patches:
+            for struct, field, off in self.patches:
+                setattr(struct, field, base_ptr + off)
+        hook = PROFILE_HOOK
+        if hook is None:
+            rc = self.fn(*self.args, stream)
+            if rc:
+                check(rc)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = self.fn(*self.args, stream)
+        e1.record()
+        if rc:
+            check(rc)
+        hook.append((self.kind, self.flops, e0, e1, self.label if self.label is not None else LABEL, self.tag))
+
+
 def _run(kind, nlaunch, flops, fn, *args, tag=None):
-    COUNTERS["launches"] += nlaunch
-    hook = PROFILE_HOOK
-    if hook is None:
-        check(fn(*args))
-        return
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    check(fn(*args))
-    e1.record()
-    hook.append((kind, flops, e0, e1, LABEL, tag))
+    """Immediate call (tests, tools): `args` includes the stream as its last element."""
+    Call(kind, nlaunch, flops, fn, args[:-1], tag=tag)(args[-1])
 
 
-# ---- thin wrappers ------------------------------------------------------------------------------
+# ---- thin wrappers: prep_*() builds a Call, the plain name runs it on the current stream ---------------------------
 def im2col3x3_first(x_nchw: torch.Tensor, out: torch.Tensor):
+    prep_im2col3x3_first(x_nchw, out)(stream_ptr())
+
+
+def prep_im2col3x3_first(x_nchw: torch.Tensor, out: torch.Tensor) -> Call:
     n, cin, h, w = x_nchw.shape
-    _run("layout", 1, 0, lib().unetk_im2col3x3_first, x_nchw.data_ptr(), n, cin, h, w, C.byref(nhwc(out)), stream_ptr())
+    t = nhwc(out)
+    return Call("layout", 1, 0, lib().unetk_im2col3x3_first, (x_nchw.data_ptr(), n, cin, h, w, C.byref(t)), keep=(t, x_nchw, out))
 
 
 def permute3(src: torch.Tensor, dst: torch.Tensor, dims, src_strides, dst_strides, dst_offset_elems: int = 0):
@@ -263,7 +298,16 @@ def weights_unpack(wj: "WeightJobs", dst_base: torch.Tensor):
          stream_ptr())
 
 
-def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None, bn_reduce=None):
+def conv_flops(x, y, mode):
+    if mode in (MODE_1X1, MODE_3X3):
+        return 2 * y.shape[0] * y.shape[1] * y.shape[2] * (9 if mode == MODE_3X3 else 1) * x.shape[3] * y.shape[3]
+    if mode == MODE_CONVT:
+        return 2 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * 4 * y.shape[3]
+    return 2 * y.shape[0] * y.shape[1] * y.shape[2] * 4 * x.shape[3] * y.shape[3]
+
+
+def prep_conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None, bn_reduce=None,
+              label=None) -> Call:
     """bn_reduce = (z, scale, shift, mean, invstd, sums): fuse the BatchNorm-backward reduction of the layer whose
     activated-output gradient this launch produces (see unetk.h)."""
     if bn_reduce is None:
@@ -274,57 +318,113 @@ def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUT
     a = ConvArgs(nhwc(x), w.data_ptr(), nhwc(y), mode, algo | TC_FLAGS, ptr(bias), ptr(stat_sum), ptr(stat_sumsq),
                  bnz, bsc, bsh, bmu, bis, bsum)
     if algo_flops is None:
-        if mode in (MODE_1X1, MODE_3X3):
-            algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * (9 if mode == MODE_3X3 else 1) * x.shape[3] * y.shape[3]
-        elif mode == MODE_CONVT:
-            algo_flops = 2 * x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] * 4 * y.shape[3]
-        else:
-            algo_flops = 2 * y.shape[0] * y.shape[1] * y.shape[2] * 4 * x.shape[3] * y.shape[3]
-    simt = algo == ALGO_SIMT or (algo == ALGO_AUTO and x.dtype != torch.bfloat16)
-    _run("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, C.byref(a), stream_ptr(), tag=mode)
+        algo_flops = conv_flops(x, y, mode)
+    simt = (algo & 0xff) == ALGO_SIMT or ((algo & 0xff) == ALGO_AUTO and x.dtype != torch.bfloat16)
+    return Call("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, (C.byref(a),), tag=mode,
+                keep=(a, x, w, y, bias, stat_sum, stat_sumsq, bn_reduce), label=label)
 
 
-def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
+def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUTO, algo_flops=None, bn_reduce=None):
+    prep_conv(x, w, y, mode, bias, stat_sum, stat_sumsq, algo, algo_flops, bn_reduce)(stream_ptr())
+
+
+def prep_wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None, label=None) -> Call:
     a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo | TC_FLAGS)
     if algo_flops is None:
         taps = (1, 9, 4)[mode]
         algo_flops = 2 * u.shape[0] * u.shape[1] * u.shape[2] * taps * u.shape[3] * s.shape[3]
-    _run("wgrad", 1, algo_flops, lib().unetk_wgrad, C.byref(a), stream_ptr(), tag=mode)
+    return Call("wgrad", 1, algo_flops, lib().unetk_wgrad, (C.byref(a),), tag=mode, keep=(a, u, s, dw), label=label)
+
+
+def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
+    prep_wgrad(u, s, dw, mode, algo, algo_flops)(stream_ptr())
+
+
+def prep_channel_sum(t, out=None, label=None) -> Call:
+    """out=None: the destination pointer is patched per call (``call.patch_ptr(...)`` is done by the caller)."""
+    tt = nhwc(t)
+    return Call("reduce", 1, 0, lib().unetk_channel_sum, (C.byref(tt), ptr(out)), keep=(tt, t, out), label=label)
 
 
 def channel_sum(t, out):
-    _run("reduce", 1, 0, lib().unetk_channel_sum, C.byref(nhwc(t)), out.data_ptr(), stream_ptr())
+    prep_channel_sum(t, out)(stream_ptr())
 
 
 def bn_stats(z, s, ss):
     _run("bn_stats", 1, 0, lib().unetk_bn_stats, C.byref(nhwc(z)), s.data_ptr(), ss.data_ptr(), stream_ptr())
 
 
-def bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
-                scale, shift, mean, invstd):
+def prep_bn_finalize(s, ss, count, c, training, gamma, beta, conv_bias, running_mean, running_var, nbt, momentum, eps,
+                     scale, shift, mean, invstd, label=None) -> Call:
     a = BnFinalizeArgs(ptr(s), ptr(ss), count, c, 1 if training else 0, ptr(gamma), ptr(beta), ptr(conv_bias),
                        ptr(running_mean), ptr(running_var), ptr(nbt), momentum, eps, ptr(scale), ptr(shift),
                        ptr(mean), ptr(invstd))
-    _run("bn_finalize", 1, 0, lib().unetk_bn_finalize, C.byref(a), stream_ptr())
+    return Call("bn_finalize", 1, 0, lib().unetk_bn_finalize, (C.byref(a),), label=label,
+                keep=(a, s, ss, gamma, beta, conv_bias, running_mean, running_var, nbt, scale, shift, mean, invstd))
+
+
+def bn_finalize(*args):
+    prep_bn_finalize(*args)(stream_ptr())
+
+
+def prep_bn_relu_apply(z, scale, shift, a, pooled=None, pool_idx=None, label=None) -> Call:
+    tz, ta, tp = nhwc(z), nhwc(a), nhwc(pooled)
+    return Call("bn_apply", 1, 0, lib().unetk_bn_relu_apply,
+                (C.byref(tz), scale.data_ptr(), shift.data_ptr(), C.byref(ta), C.byref(tp), ptr(pool_idx)), label=label,
+                keep=(tz, ta, tp, z, scale, shift, a, pooled, pool_idx))
 
 
 def bn_relu_apply(z, scale, shift, a, pooled=None, pool_idx=None):
-    _run("bn_apply", 1, 0, lib().unetk_bn_relu_apply, C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(),
-         C.byref(nhwc(a)), C.byref(nhwc(pooled)), ptr(pool_idx), stream_ptr())
+    prep_bn_relu_apply(z, scale, shift, a, pooled, pool_idx)(stream_ptr())
+
+
+def prep_bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma=None, dbeta=None, pool_idx=None, reduced=False,
+                     label=None):
+    """Returns (args struct, [Call, ...]): the reduce pass (unless `reduced`: the sums were already accumulated by the
+    producing unetk_conv launch) and the apply pass.  dgamma / dbeta may be None and patched per call."""
+    a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
+                  ptr(dgamma), ptr(dbeta), ptr(pool_idx))
+    keep = (a, z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx)
+    calls = []
+    if not reduced:
+        calls.append(Call("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, (C.byref(a),), keep=keep, label=label))
+    calls.append(Call("bn_bwd_apply", 1, 0, lib().unetk_bn_relu_bwd_apply, (C.byref(a),), keep=keep, label=label))
+    return a, calls
 
 
 def bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx=None, reduced=False):
     """reduced=True: `sums` were already accumulated by the producing unetk_conv launch (bn_reduce=...)."""
-    a = BnBwdArgs(nhwc(z), nhwc(dy), nhwc(dpool), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(sums), nhwc(dz),
-                  ptr(dgamma), ptr(dbeta), ptr(pool_idx))
     s = stream_ptr()
-    if not reduced:
-        _run("bn_bwd_reduce", 1, 0, lib().unetk_bn_relu_bwd_reduce, C.byref(a), s)
-    _run("bn_bwd_apply", 1, 0, lib().unetk_bn_relu_bwd_apply, C.byref(a), s)
+    for c in prep_bn_relu_bwd(z, dy, dpool, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, pool_idx, reduced)[1]:
+        c(s)
+
+
+def prep_head_fprop(a, w, b, dout, logits, label=None) -> Call:
+    ta = nhwc(a)
+    return Call("head", 1, 0, lib().unetk_head_fprop, (C.byref(ta), w.data_ptr(), ptr(b), dout, logits.data_ptr()),
+                keep=(ta, a, w, b, logits), label=label)
 
 
 def head_fprop(a, w, b, dout, logits):
-    _run("head", 1, 0, lib().unetk_head_fprop, C.byref(nhwc(a)), w.data_ptr(), ptr(b), dout, logits.data_ptr(), stream_ptr())
+    prep_head_fprop(a, w, b, dout, logits)(stream_ptr())
+
+
+def prep_head_bwd(dlogits, a, w, dout, da, dw=None, db=None, label=None) -> Call:
+    """dw / db None: patched per call (arguments 5 and 6 are plain pointers, so the Call carries a tiny struct)."""
+    ta, tda = nhwc(a), nhwc(da)
+    box = HeadBwdPtrs(ptr(dw), ptr(db))
+    call = Call("head", 1, 0, _head_bwd_boxed, (dlogits.data_ptr(), C.byref(ta), w.data_ptr(), dout, C.byref(tda), box),
+                keep=(ta, tda, box, dlogits, a, w, da, dw, db), label=label)
+    call.box = None
+    return call, box
+
+
+class HeadBwdPtrs(C.Structure):
+    _fields_ = [("dw", C.c_void_p), ("db", C.c_void_p)]
+
+
+def _head_bwd_boxed(dlogits, ta, w, dout, tda, box, stream):
+    return lib().unetk_head_bwd(dlogits, ta, w, dout, tda, box.dw, box.db, stream)
 
 
 def head_bwd(dlogits, a, w, dout, da, dw, db):
@@ -332,19 +432,34 @@ def head_bwd(dlogits, a, w, dout, da, dw, db):
          dw.data_ptr(), ptr(db), stream_ptr())
 
 
+def prep_bn_relu_head_fprop(z, scale, shift, a, w_head, b_head, dout, logits, label=None) -> Call:
+    tz, ta = nhwc(z), nhwc(a)
+    return Call("bn_apply", 1, 0, lib().unetk_bn_relu_head_fprop,
+                (C.byref(tz), scale.data_ptr(), shift.data_ptr(), C.byref(ta), w_head.data_ptr(), ptr(b_head), dout,
+                 logits.data_ptr()), keep=(tz, ta, z, scale, shift, a, w_head, b_head, logits), label=label)
+
+
 def bn_relu_head_fprop(z, scale, shift, a, w_head, b_head, dout, logits):
     """BatchNorm apply + ReLU of the last block fused with the head forward; ``a=None`` skips storing the activation."""
-    _run("bn_apply", 1, 0, lib().unetk_bn_relu_head_fprop, C.byref(nhwc(z)), scale.data_ptr(), shift.data_ptr(),
-         C.byref(nhwc(a)), w_head.data_ptr(), ptr(b_head), dout, logits.data_ptr(), stream_ptr())
+    prep_bn_relu_head_fprop(z, scale, shift, a, w_head, b_head, dout, logits)(stream_ptr())
+
+
+def prep_head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma=None, dbeta=None, dw_head=None,
+                     db_head=None, label=None):
+    """Head backward fused with the BatchNorm backward of the block that feeds the head (two launches).
+    Returns (args struct, [reduce Call, apply Call]); the four gradient pointers may be None and patched per call."""
+    a = HeadBnBwdArgs(nhwc(z), dlogits.data_ptr(), w_head.data_ptr(), dout, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                      ptr(sums), nhwc(dz), ptr(dgamma), ptr(dbeta), ptr(dw_head), ptr(db_head))
+    keep = (a, dlogits, z, w_head, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head, db_head)
+    return a, [Call("bn_bwd_reduce", 1, 0, lib().unetk_head_bn_bwd_reduce, (C.byref(a),), keep=keep, label=label),
+               Call("bn_bwd_apply", 1, 0, lib().unetk_head_bn_bwd_apply, (C.byref(a),), keep=keep, label=label)]
 
 
 def head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head, db_head):
-    """Head backward fused with the BatchNorm backward of the block that feeds the head (two launches)."""
-    a = HeadBnBwdArgs(nhwc(z), dlogits.data_ptr(), w_head.data_ptr(), dout, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
-                      ptr(sums), nhwc(dz), ptr(dgamma), ptr(dbeta), ptr(dw_head), ptr(db_head))
     s = stream_ptr()
-    _run("bn_bwd_reduce", 1, 0, lib().unetk_head_bn_bwd_reduce, C.byref(a), s)
-    _run("bn_bwd_apply", 1, 0, lib().unetk_head_bn_bwd_apply, C.byref(a), s)
+    for c in prep_head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head,
+                              db_head)[1]:
+        c(s)
 
 
 def dice_ce_fwd(args):

@@ -248,7 +248,8 @@ def test_fused_head_passes_at_batch_64(dout):
     logits = torch.empty((N, dout, H, W), dtype=torch.float32, device=DEV)
     L.bn_relu_head_fprop(z, scale, shift, None, wh, bh, dout, logits)
     pre = z.double() * scale.double() + shift.double()                 # exact value of the kernel's fp32 fma
-    a = pre.clamp_min(0)
+    # the fused kernels reproduce the unfused pipeline, in which the activation is STORED as bf16 before the head reads it
+    a = pre.clamp_min(0).float().to(BF).double()
     ref = torch.einsum("nhwc,kc->nkhw", a, wh.double()) + bh.double()[None, :, None, None]
     rel = ((logits.double() - ref).abs().max() / ref.abs().max()).item()
     assert rel < 1e-5, f"fused head forward rel {rel:.3e}"               # fp32 arithmetic: north-star fp32 budget 1e-4
@@ -269,7 +270,8 @@ def test_fused_head_passes_at_batch_64(dout):
     ref_dz = scale.double() * (dyv - s1 / M - xhat * (s2 / M))
     err = (dz.double() - ref_dz).abs()
     assert int((err > ref_dz.abs() * 2.0 ** -8 + 2e-5 * ref_dz.abs().max()).sum()) == 0
-    ref_dwh = torch.einsum("nkhw,nhwc->kc", dl.double(), a)
+    # (the backward pass recomputes a = relu(z*scale+shift) without the bf16 rounding of the stored activation)
+    ref_dwh = torch.einsum("nkhw,nhwc->kc", dl.double(), pre.clamp_min(0))
     assert ((dwh.double() - ref_dwh).abs().max() / ref_dwh.abs().max()).item() < 1e-5
     assert ((dbh.double() - dl.double().sum(dim=(0, 2, 3))).abs().max() / dl.double().abs().sum(dim=(0, 2, 3)).max()).item() < 1e-5
     assert ((dgamma.double() - s2).abs().max() / (dyv * xhat).abs().sum(dim=(0, 1, 2)).max()).item() < 1e-5

@@ -255,6 +255,54 @@ def test_train_loop_graph_replay_equals_eager(monkeypatch, capsys):
     assert int(res["1"][1]["down1.doubleConvReLU.1.num_batches_tracked"]) == 15
 
 
+def test_train_graph_cache_never_replays_into_stale_state(monkeypatch):
+    """the captured step cached on the model must be dropped / re-captured when (a) the model is moved
+    (model.to() at the top of every start() re-creates the engine whose buffers the graph replays into), (b) the
+    optimizer state is restored (load_state_dict replaces the state tensors), (c) a python-float learning rate changes.
+    Oracle: the same schedule through the eager loop (UNETK_TRAIN_GRAPH=0) -- per-epoch losses must agree."""
+    import copy
+    hw, n = 32, 2
+    loader = [(x, y.to(torch.uint8)) for x, y in (make_batch(n, hw, hw, 3, 3, seed=400 + i, labels="learnable") for i in range(4))]
+    dev = torch.device(DEV)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("UNETK_TRAIN_GRAPH", mode)
+        m = build(3, 3, "fp32")
+        opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=0.01, capturable=True)
+        fn = loss_for(3)
+        losses = [train_loop(loader, m, fn, opt, 1, dev, None, hw)]
+        g0 = m._train_graph
+        assert (g0 is not None) == (mode == "1")
+        # (a) model moved: engine and cached graph are gone
+        m.to(dev)
+        assert m._engine is None and m._train_graph is None
+        losses.append(train_loop(loader, m, fn, opt, 1, dev, None, hw))
+        # (b) optimizer state restored from a checkpoint: new state tensors => the old capture must not be replayed
+        saved = copy.deepcopy(opt.state_dict())
+        g1 = m._train_graph
+        opt.load_state_dict(saved)
+        losses.append(train_loop(loader, m, fn, opt, 1, dev, None, hw))
+        if mode == "1":
+            assert m._train_graph is not None and m._train_graph[4] is not g1[4], "graph was not re-captured after load_state_dict"
+            # the restored state advanced: 3 epochs x 4 steps
+            assert int(opt.state[next(iter(m.parameters()))]["step"]) == 12
+        # (c) learning-rate change between epochs (python float baked into the capture)
+        g2 = m._train_graph
+        for grp in opt.param_groups:
+            grp["lr"] = 1e-5
+        before = {k: v.detach().clone() for k, v in m.named_parameters()}
+        losses.append(train_loop(loader, m, fn, opt, 1, dev, None, hw))
+        if mode == "1":
+            assert m._train_graph[4] is not g2[4], "graph was not re-captured after the lr change"
+        step = max((v.detach() - before[k]).abs().max().item() for k, v in m.named_parameters())
+        assert step < 4 * 1e-5 * 1.5, f"parameters moved by {step:.2e}: the old learning rate is still in effect"
+        out[mode] = np.array(losses)
+    np.testing.assert_allclose(out["1"], out["0"], rtol=0, atol=5e-3)
+    # pickling / deep-copying a model that holds a captured graph must work (caches are stripped)
+    m2 = copy.deepcopy(m)
+    assert m2._train_graph is None and m2._engine is None
+
+
 def test_forward_metrics_pipeline_matches_oracle():
     """argmax masks and confusion counts are bit-exact given identical logits."""
     x, y = make_batch(2, 32, 32, 3, 4, seed=9)
