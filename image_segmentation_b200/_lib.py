@@ -69,7 +69,10 @@ class DiceCeArgs(C.Structure):
                 ("w", C.c_int32), ("class_weights", C.c_void_p), ("has_ignore", C.c_int32), ("ignore_index", C.c_int64),
                 ("dice_weight", C.c_float), ("ce_weight", C.c_float), ("smooth", C.c_float), ("accum", C.c_void_p),
                 ("coef", C.c_void_p), ("loss", C.c_void_p), ("status", C.c_void_p), ("grad_out", C.c_void_p),
-                ("dlogits", C.c_void_p)]
+                ("dlogits", C.c_void_p), ("input_kind", C.c_int32), ("nll_eps", C.c_float)]
+
+
+LOSS_LOGITS, LOSS_PROBS_LOG, LOSS_PROBS_RAW = 0, 1, 2
 
 
 UNETK_U8, UNETK_I64 = 2, 3      # label dtypes (include/unetk.h)
@@ -138,6 +141,14 @@ def lib():
             "unetk_head_bn_bwd_apply": [P(HeadBnBwdArgs), vp],
             "unetk_crop_resize": [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_int32, vp, vp],
             "unetk_eval_loss_metrics": [P(EvalArgs), vp],
+            "unetk_bias_sigmoid_fwd": [P(Tensor), vp, C.c_int32, vp, vp],
+            "unetk_bias_sigmoid_bwd": [vp, vp, C.c_int32, P(Tensor), vp, vp],
+            "unetk_bilinear_up_fwd": [P(Tensor), P(Tensor), vp],
+            "unetk_bilinear_up_bwd": [P(Tensor), P(Tensor), vp],
+            "unetk_prompt_compose_fwd": [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp],
+            "unetk_prompt_compose_bwd": [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp],
+            "unetk_nchw_to_nhwc": [vp, P(Tensor), vp],
+            "unetk_nhwc_to_nchw": [P(Tensor), vp, vp],
         }
         for name, argtypes in sigs.items():
             fn = getattr(l, name)
@@ -148,12 +159,14 @@ def lib():
 
 
 EXPORTED_SYMBOLS = (
-    "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_query_workspace", "unetk_im2col3x3_first", "unetk_permute3",
+    "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_query_workspace", "unetk_struct_size", "unetk_im2col3x3_first", "unetk_permute3",
     "unetk_weights_pack", "unetk_weights_unpack",
     "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
     "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply", "unetk_bn_relu_head_fprop",
+    "unetk_bias_sigmoid_fwd", "unetk_bias_sigmoid_bwd", "unetk_bilinear_up_fwd", "unetk_bilinear_up_bwd",
+    "unetk_prompt_compose_fwd", "unetk_prompt_compose_bwd", "unetk_nchw_to_nhwc", "unetk_nhwc_to_nchw",
 )
 
 
@@ -460,6 +473,52 @@ def head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, 
     for c in prep_head_bn_bwd(dlogits, z, w_head, dout, scale, shift, mean, invstd, sums, dz, dgamma, dbeta, dw_head,
                               db_head)[1]:
         c(s)
+
+
+def prep_bias_sigmoid_fwd(z, bias, dout, out, label=None) -> Call:
+    tz = nhwc(z)
+    return Call("recon", 1, 0, lib().unetk_bias_sigmoid_fwd, (C.byref(tz), ptr(bias), dout, out.data_ptr()),
+                keep=(tz, z, bias, out), label=label)
+
+
+def prep_bias_sigmoid_bwd(dy, out, dout, dz, dbias, label=None) -> Call:
+    tz = nhwc(dz)
+    return Call("recon", 1, 0, lib().unetk_bias_sigmoid_bwd, (dy.data_ptr(), out.data_ptr(), dout, C.byref(tz), ptr(dbias)),
+                keep=(tz, dy, out, dz, dbias), label=label)
+
+
+def prep_bilinear_up(src, dst, backward=False, label=None) -> Call:
+    """forward: dst = interpolate(src); backward: `src` receives the gradient gathered from `dst` (= d dst)."""
+    ts, td = nhwc(src), nhwc(dst)
+    if backward:
+        return Call("bilinear", 1, 0, lib().unetk_bilinear_up_bwd, (C.byref(td), C.byref(ts)), keep=(ts, td, src, dst), label=label)
+    return Call("bilinear", 1, 0, lib().unetk_bilinear_up_fwd, (C.byref(ts), C.byref(td)), keep=(ts, td, src, dst), label=label)
+
+
+def bilinear_up(src, dst, backward=False):
+    prep_bilinear_up(src, dst, backward)(stream_ptr())
+
+
+def prompt_compose_fwd(clip_logits, mask_logits, out):
+    n, _, h, w = clip_logits.shape
+    _run("prompt", 1, 0, lib().unetk_prompt_compose_fwd, clip_logits.data_ptr(), mask_logits.data_ptr(), n, h, w, out.data_ptr(),
+         stream_ptr())
+
+
+def prompt_compose_bwd(clip_logits, mask_logits, dfinal, dmask):
+    n, _, h, w = clip_logits.shape
+    _run("prompt", 1, 0, lib().unetk_prompt_compose_bwd, clip_logits.data_ptr(), mask_logits.data_ptr(), dfinal.data_ptr(), n, h, w,
+         dmask.data_ptr(), stream_ptr())
+
+
+def prep_nchw_to_nhwc(src, dst, label=None) -> Call:
+    td = nhwc(dst)
+    return Call("layout", 1, 0, lib().unetk_nchw_to_nhwc, (src.data_ptr(), C.byref(td)), keep=(td, src, dst), label=label)
+
+
+def prep_nhwc_to_nchw(src, dst, label=None) -> Call:
+    ts = nhwc(src)
+    return Call("layout", 1, 0, lib().unetk_nhwc_to_nchw, (C.byref(ts), dst.data_ptr()), keep=(ts, src, dst), label=label)
 
 
 def dice_ce_fwd(args):

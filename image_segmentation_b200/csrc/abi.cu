@@ -68,6 +68,22 @@ int64_t unetk_query_workspace(int32_t what, int32_t a, int32_t b, int32_t c, int
   return UNETK_ERR_INVALID;
 }
 
+int32_t unetk_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return (int32_t)sizeof(unetk_tensor);
+    case 1: return (int32_t)sizeof(unetk_conv_args);
+    case 2: return (int32_t)sizeof(unetk_wgrad_args);
+    case 3: return (int32_t)sizeof(unetk_bn_finalize_args);
+    case 4: return (int32_t)sizeof(unetk_bn_bwd_args);
+    case 5: return (int32_t)sizeof(unetk_wjob);
+    case 6: return (int32_t)sizeof(unetk_dice_ce_args);
+    case 7: return (int32_t)sizeof(unetk_head_bn_bwd_args);
+    case 8: return (int32_t)sizeof(unetk_eval_image);
+    case 9: return (int32_t)sizeof(unetk_eval_args);
+    default: return -1;
+  }
+}
+
 int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
   int dev = 0;
   UNETK_CUDA(cudaGetDevice(&dev));

@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(256) dice_ce_reduce_kernel(unetk_dice_ce_args 
     const int y = (int)yl;
     const int64_t img = p / hw, off = p % hw;
     SoftmaxT<CM> s;
-    pixel_softmax<CM>(a.logits, img * c * hw + off, hw, c, y, s);
+    if (a.input_kind == UNETK_LOSS_LOGITS)
+      pixel_softmax<CM>(a.logits, img * c * hw + off, hw, c, y, s);
+    else
+      pixel_probs<CM>(a.logits, img * c * hw + off, hw, c, y, a.input_kind, a.nll_eps, s);
 #pragma unroll
     for (int k = 0; k < CM; ++k) {
       // utils/weighted_loss.py:50-58: with C == 1 the reference uses y.float() itself as the "one-hot"
@@ -243,6 +246,23 @@ __global__ void __launch_bounds__(256) dice_ce_bwd_kernel(unetk_dice_ce_args a) 
     }
     const int y = (int)yl;
     SoftmaxT<CM> s;
+    if (a.input_kind != UNETK_LOSS_LOGITS) {
+      // probability inputs (utils/weighted_loss.py:207-210,338-340): no softmax Jacobian;
+      //   d Dice / d p_k = -coef_k (2 oh_k - dc_k),   d NLL / d p_y = -w_y / (p_y + eps)   (or -w_y for raw inputs)
+      pixel_probs<CM>(a.logits, base, hw, c, y, a.input_kind, a.nll_eps, s);
+      const bool valid = !(a.has_ignore && yl == a.ignore_index);
+      const float wy = valid ? (a.class_weights ? a.class_weights[y] : 1.f) * ce_scale : 0.f;
+#pragma unroll
+      for (int k = 0; k < CM; ++k) {
+        if (k < c) {
+          const float oh = c == 1 ? (float)y : (k == y ? 1.f : 0.f);
+          float gx = -coef[k] * (2.f * oh - coef[c + k]);
+          if (k == y) gx -= a.input_kind == UNETK_LOSS_PROBS_LOG ? wy / (s.p[k] + a.nll_eps) : wy;
+          a.dlogits[base + k * hw] = gx * go;
+        }
+      }
+      continue;
+    }
     pixel_softmax<CM>(a.logits, base, hw, c, y, s);
     float g[CM], dot = 0.f;
 #pragma unroll

@@ -46,6 +46,21 @@ __device__ __forceinline__ void pixel_softmax(const float* __restrict__ logits, 
   softmax_of<CM>(x, c, y, s);
 }
 
+// Probability inputs (the prompt model's losses, utils/weighted_loss.py:207-210,338-340): p = x as given, and the
+// "log-probability" of the label is nll_nonlin(x)[y] = log(x[y] + eps) (UNETK_LOSS_PROBS_LOG) or x[y] itself
+// (UNETK_LOSS_PROBS_RAW: nll_nonlin=None feeds NLLLoss with the raw input).
+template <int CM>
+__device__ __forceinline__ void pixel_probs(const float* __restrict__ x, int64_t base, int64_t hw, int c, int y, int kind,
+                                            float eps, SoftmaxT<CM>& s) {
+  float py = 0.f;
+#pragma unroll
+  for (int k = 0; k < CM; ++k) {
+    s.p[k] = k < c ? x[base + k * hw] : 0.f;
+    if (k == y) py = s.p[k];
+  }
+  s.logp_y = kind == UNETK_LOSS_PROBS_LOG ? logf(py + eps) : py;
+}
+
 // torch.argmax over x[0..c): first maximum wins, NaN counts as the largest value (utils/MetricsHistory.py:65)
 __device__ __forceinline__ int argmax_first(const float (&x)[kMaxClasses], int c) {
   float best = x[0];

@@ -1,5 +1,6 @@
-"""Drop-in for the hot-path classes of the reference's ``utils/weighted_loss.py``:
-``WeightedMemoryEfficientDiceLoss`` (:6-98) and ``WeightedDiceCELoss`` (:102-166).
+"""Drop-in for the reference's ``utils/weighted_loss.py``: ``WeightedMemoryEfficientDiceLoss`` (:6-98),
+``WeightedDiceCELoss`` (:102-166) and the prompt-model variants ``WeightedMemoryEfficientDiceLossPrompt`` (:170-273)
+and ``WeightedDiceNLLLoss`` (:276-343: Dice on PROBABILITIES + ``NLLLoss(log(p + 1e-9))``).
 
 Same constructor arguments, same ``forward(outputs, targets)`` contract and error behaviour, but the
 ~12 ATen ops of the reference (softmax, zeros_like + scatter_, three [N,C,H,W] products/sums, clip,
@@ -61,7 +62,8 @@ class _DiceCEFunction(torch.autograd.Function):
                             1 if cfg["ignore_index"] is not None else 0,
                             cfg["ignore_index"] if cfg["ignore_index"] is not None else 0,
                             cfg["dice_weight"], cfg["ce_weight"], cfg["smooth"], accum.data_ptr(), coef.data_ptr(),
-                            loss.data_ptr(), cfg["status"].dev.data_ptr(), None, None)
+                            loss.data_ptr(), cfg["status"].dev.data_ptr(), None, None, cfg.get("input_kind", 0),
+                            cfg.get("nll_eps", 0.0))
         L.dice_ce_fwd(args)
         ctx.save_for_backward(logits, target, coef)
         ctx.cfg = cfg
@@ -80,13 +82,15 @@ class _DiceCEFunction(torch.autograd.Function):
                             1 if cfg["ignore_index"] is not None else 0,
                             cfg["ignore_index"] if cfg["ignore_index"] is not None else 0,
                             cfg["dice_weight"], cfg["ce_weight"], cfg["smooth"], None, coef.data_ptr(), None,
-                            cfg["status"].dev.data_ptr(), go.data_ptr(), dlogits.data_ptr())
+                            cfg["status"].dev.data_ptr(), go.data_ptr(), dlogits.data_ptr(), cfg.get("input_kind", 0),
+                            cfg.get("nll_eps", 0.0))
         L.dice_ce_bwd(args)
         return dlogits, None, None
 
 
 class _FusedLossBase(nn.Module):
-    def _run(self, logits, target, dice_weight, ce_weight, smooth, ignore_index, class_weights):
+    def _run(self, logits, target, dice_weight, ce_weight, smooth, ignore_index, class_weights, input_kind=L.LOSS_LOGITS,
+             nll_eps=0.0):
         L.require_cuda(logits, target)
         if logits.dim() != 4:
             raise ValueError(f"expected logits [N,C,H,W], got {tuple(logits.shape)}")
@@ -116,7 +120,7 @@ class _FusedLossBase(nn.Module):
             raise ValueError("ignore_index out of range")
         cfg = dict(class_weights=cw, ignore_index=None if ignore_index is None else int(ignore_index),
                    dice_weight=float(dice_weight), ce_weight=float(ce_weight), smooth=float(smooth),
-                   status=self._status)
+                   status=self._status, input_kind=int(input_kind), nll_eps=float(nll_eps))
         lg = logits if (logits.dtype == torch.float32 and logits.is_contiguous()) else logits.float().contiguous()
         tg = target if (target.dtype == torch.int64 and target.is_contiguous()) else target.long().contiguous()
         with torch.cuda.device(dev):
@@ -207,3 +211,103 @@ class WeightedDiceCELoss(_FusedLossBase):
             raise ValueError(f"Unsupported target shape {targets.shape} for CE. Expected [N, H, W] or [N, 1, H, W].")
         return self._run(outputs, t3, self.dice_weight, self.ce_weight, self.smooth_dice, self.ignore_index,
                          self.class_weights)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# prompt-model losses (probability inputs)
+# ---------------------------------------------------------------------------------------------------------------------
+def _classify_nonlin(fn):
+    """The reference takes arbitrary callables (``nll_nonlin``, ``dice_nonlin``).  The fused kernel knows two:
+    ``None`` (identity) and the prompt notebook's ``lambda x: torch.log(x + eps)`` (prompt_based/prompt.ipynb:68).
+    The callable is probed on three values; anything else is refused loudly.  Returns ("identity"|"log", eps)."""
+    if fn is None:
+        return "identity", 0.0
+    probe = torch.tensor([0.0, 0.25, 1.0], dtype=torch.float64)
+    try:
+        out = fn(probe)
+    except Exception as e:
+        raise NotImplementedError(f"nonlinearity {fn!r} cannot be evaluated on a CPU probe tensor: {e}")
+    if torch.equal(out, probe):
+        return "identity", 0.0
+    eps = float(torch.exp(out[0]))
+    if eps > 0 and torch.allclose(out, torch.log(probe + eps), rtol=1e-9, atol=1e-12):
+        return "log", eps
+    raise NotImplementedError("only nll_nonlin=None or x -> log(x + eps) is supported by the fused Dice+NLL kernel")
+
+
+class WeightedMemoryEfficientDiceLossPrompt(_FusedLossBase):
+    """Soft Dice over the batch on logits (``apply_softmax=True``) or probabilities (``False``); returns ``-dice``
+    (reference: utils/weighted_loss.py:170-273).  ``dice_nonlin`` must be None (the reference's own wrapper never
+    forwards it, :299-304)."""
+
+    def __init__(self, dice_nonlin=None, apply_softmax: bool = True, ignore_index: Optional[int] = None,
+                 class_weights: Optional[torch.Tensor] = None, smooth: float = 1e-5):
+        super().__init__()
+        if dice_nonlin is not None and _classify_nonlin(dice_nonlin)[0] != "identity":
+            raise NotImplementedError("dice_nonlin is not supported by the fused kernel")
+        self.apply_softmax = apply_softmax
+        self.ignore_index = ignore_index
+        self.smooth = smooth
+        self.dice_nonlin = dice_nonlin
+        if class_weights is not None:
+            assert isinstance(class_weights, torch.Tensor), "class_weights must be a torch.Tensor"
+        self.class_weights = class_weights
+
+    def forward(self, x, y):
+        if y.dim() == x.dim() - 1 and y.shape == x.shape[:1] + x.shape[2:]:
+            y3 = y
+        elif y.dim() == x.dim() and y.shape[1] == 1:
+            y3 = y[:, 0]
+        elif y.dim() == x.dim() and y.shape == x.shape:
+            raise NotImplementedError("soft / one-hot float targets are not supported by the fused kernel")
+        else:
+            raise ValueError(f"Shape mismatch: probs {x.shape}, y {y.shape}")
+        kind = L.LOSS_LOGITS if self.apply_softmax else L.LOSS_PROBS_RAW
+        return self._run(x, y3, 1.0, 0.0, self.smooth, self.ignore_index, self.class_weights, kind, 0.0)
+
+
+class WeightedDiceNLLLoss(_FusedLossBase):
+    """``dice_weight * SoftDice(p) + nll_weight * NLLLoss(nll_nonlin(p))`` (reference: utils/weighted_loss.py:276-343).
+
+    Supported configurations (anything else raises NotImplementedError):
+      * ``apply_softmax=False`` with ``nll_nonlin = lambda x: torch.log(x + eps)`` -- the prompt model's loss
+        (prompt_based/prompt.ipynb:68-70): inputs are probabilities;
+      * ``apply_softmax=False`` with ``nll_nonlin=None``: NLLLoss on the raw probabilities.
+    ``dice_nonlin`` is stored but -- exactly as in the reference (:299-304) -- never applied."""
+
+    def __init__(self, dice_weight: float = 1.0, nll_weight: float = 1.0, ignore_index: Optional[int] = None,
+                 class_weights: Optional[torch.Tensor] = None, smooth_dice: float = 1e-5, apply_softmax: bool = True,
+                 dice_nonlin=None, nll_nonlin=None, nll_kwargs={}):
+        super().__init__()
+        self.dice_weight = dice_weight
+        self.nll_weight = nll_weight
+        self.ignore_index = ignore_index
+        self.dice_nonlin = dice_nonlin
+        self.nll_nonlin = nll_nonlin
+        self.class_weights = class_weights
+        self.smooth_dice = smooth_dice
+        self.apply_softmax = apply_softmax
+        extra = {k: v for k, v in dict(nll_kwargs).items() if not (k == "reduction" and v == "mean")}
+        if extra:
+            raise NotImplementedError(f"nll_kwargs {sorted(extra)} are not supported by the fused Dice+NLL kernel")
+        if apply_softmax:
+            raise NotImplementedError("WeightedDiceNLLLoss(apply_softmax=True) feeds NLLLoss with raw logits in the reference; "
+                                      "only the probability-input form (apply_softmax=False) is on the accelerated path")
+        kind, eps = _classify_nonlin(nll_nonlin)
+        self._kind = L.LOSS_PROBS_LOG if kind == "log" else L.LOSS_PROBS_RAW
+        self._eps = eps
+        self.dice = WeightedMemoryEfficientDiceLossPrompt(apply_softmax=apply_softmax, ignore_index=ignore_index,
+                                                          class_weights=class_weights, smooth=smooth_dice)
+
+    def forward(self, outputs, targets):
+        if targets.ndim == 3:
+            t3 = targets
+        elif targets.ndim == 4 and targets.shape[1] == 1:
+            t3 = targets[:, 0]
+        elif targets.ndim == outputs.ndim and targets.shape[1] != 1:
+            raise ValueError(f"Target shape {targets.shape} has multiple channels but expected class indices "
+                             "[N, H, W] or [N, 1, H, W] for CE.")
+        else:
+            raise ValueError(f"Unsupported target shape {targets.shape} for CE. Expected [N, H, W] or [N, 1, H, W].")
+        return self._run(outputs, t3, self.dice_weight, self.nll_weight, self.smooth_dice, self.ignore_index,
+                         self.class_weights, self._kind, self._eps)

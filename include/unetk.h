@@ -96,6 +96,10 @@ UNETK_API int unetk_device_query(int32_t* sm_count, int32_t* cc_major, int32_t* 
 #define UNETK_WS_EVAL_ACCUM 7
 #define UNETK_WS_CONFUSION 8
 UNETK_API int64_t unetk_query_workspace(int32_t what, int32_t a, int32_t b, int32_t c, int32_t d);
+/* sizeof() of the argument structs as compiled into the library, for bindings that mirror them by hand (ctypes, cgo, JNI):
+ * 0 unetk_tensor, 1 unetk_conv_args, 2 unetk_wgrad_args, 3 unetk_bn_finalize_args, 4 unetk_bn_bwd_args, 5 unetk_wjob,
+ * 6 unetk_dice_ce_args, 7 unetk_head_bn_bwd_args, 8 unetk_eval_image, 9 unetk_eval_args; -1 for an unknown id.   */
+UNETK_API int32_t unetk_struct_size(int32_t which);
 
 /* ---- layout --------------------------------------------------------------------------------
  * unetk_im2col3x3_first: X.to(device) + first conv's implicit im2col (utils/training.py:45,
@@ -241,7 +245,17 @@ UNETK_API int unetk_head_fprop(const unetk_tensor* a, const float* w, const floa
 UNETK_API int unetk_head_bwd(const float* dlogits_nchw, const unetk_tensor* a, const float* w, int32_t dout,
                    const unetk_tensor* da, float* dw, float* db, void* stream);
 
-/* ---- weighted Dice + CE loss (utils/weighted_loss.py:31-98,140-166) --------------------------- */
+/* ---- weighted Dice + CE loss (utils/weighted_loss.py:31-98,140-166) ---------------------------
+ * input_kind selects what `logits` holds:
+ *   UNETK_LOSS_LOGITS     class scores; softmax inside (WeightedDiceCELoss, utils/weighted_loss.py:102-166)
+ *   UNETK_LOSS_PROBS_LOG  probabilities (apply_softmax=False); the likelihood term is NLLLoss(log(p + nll_eps))
+ *                         (WeightedDiceNLLLoss with nll_nonlin = log(x + 1e-9), utils/weighted_loss.py:276-343,
+ *                         prompt_based/prompt.ipynb:68-70)
+ *   UNETK_LOSS_PROBS_RAW  probabilities; NLLLoss on the raw input (nll_nonlin=None)
+ * The backward pass then returns d loss / d input for that kind of input. */
+#define UNETK_LOSS_LOGITS 0
+#define UNETK_LOSS_PROBS_LOG 1
+#define UNETK_LOSS_PROBS_RAW 2
 typedef struct unetk_dice_ce_args {
   const float* logits;   /* NCHW fp32 */
   const int64_t* target; /* [N,H,W] */
@@ -256,6 +270,8 @@ typedef struct unetk_dice_ce_args {
   int32_t* status; /* |= 1 if a label is outside [0,C) (the reference raises from scatter_) */
   const float* grad_out; /* [1] device scalar (bwd) */
   float* dlogits;        /* NCHW fp32 (bwd) */
+  int32_t input_kind;    /* UNETK_LOSS_* */
+  float nll_eps;         /* UNETK_LOSS_PROBS_LOG only */
 } unetk_dice_ce_args;
 UNETK_API int unetk_dice_ce_fwd(const unetk_dice_ce_args* a, void* stream);
 UNETK_API int unetk_dice_ce_bwd(const unetk_dice_ce_args* a, void* stream);
@@ -336,6 +352,33 @@ typedef struct unetk_eval_args {
   int32_t* status;       /* |= 1 if a label is outside [0,C) */
 } unetk_eval_args;
 UNETK_API int unetk_eval_loss_metrics(const unetk_eval_args* a, void* stream);
+
+/* ---- other model families on the same blocks ------------------------------------ */
+/* Reconstruction output (autoencoder/autoencoder.py:188-191): out[n,k,h,w] = sigmoid(z[n,h,w,k] + bias[k]) for k < dout
+ * (z is the NHWC output of the 3x3 convolution whose Cout is zero-padded; only its first dout channels are read).
+ * Backward: dz[p,k] = dy[p,k] * out (1 - out) for k < dout and 0 for k in [dout, 8); channels >= 8 of dz are NOT written
+ * (the caller zeroes dz once); dbias[k] += sum_p dz[p,k] (may be NULL).  dout 1..8.                                  */
+UNETK_API int unetk_bias_sigmoid_fwd(const unetk_tensor* z, const float* bias, int32_t dout, float* out_nchw, void* stream);
+UNETK_API int unetk_bias_sigmoid_bwd(const float* dy_nchw, const float* out_nchw, int32_t dout, const unetk_tensor* dz,
+                                     float* dbias, void* stream);
+
+/* F.interpolate(src, size=(dst.h, dst.w), mode='bilinear', align_corners=False) in NHWC (clip/clipunet.py:99-100); dst may
+ * be a channel slice of a concat buffer.  _bwd computes d src from d dst (gather over the interpolation footprints). */
+UNETK_API int unetk_bilinear_up_fwd(const unetk_tensor* src, const unetk_tensor* dst, void* stream);
+UNETK_API int unetk_bilinear_up_bwd(const unetk_tensor* ddst, const unetk_tensor* dsrc, void* stream);
+
+/* PromptModel.forward tail (prompt_based/prompt.py:36-56), NCHW fp32: p = softmax(clip_logits [N,4,H,W]),
+ * m = sigmoid(mask_logits [N,1,H,W]); final = [1 - m, m p0 + m p3, m p1, m p2].  The CLIP branch is frozen in the
+ * reference (prompt.py:30-31), so the backward returns d mask_logits only.                                         */
+UNETK_API int unetk_prompt_compose_fwd(const float* clip_logits, const float* mask_logits, int32_t n, int32_t h, int32_t w,
+                                       float* final_probs, void* stream);
+UNETK_API int unetk_prompt_compose_bwd(const float* clip_logits, const float* mask_logits, const float* dfinal, int32_t n,
+                                       int32_t h, int32_t w, float* dmask_logits, void* stream);
+
+/* Layout converters of the block-level API (DoubleConvReLU / Down / Up called on their own, unet/unet.py:24,44,62):
+ * NCHW fp32 [N,C,H,W] <-> NHWC dst/src (dtype of the tensor descriptor; any C). */
+UNETK_API int unetk_nchw_to_nhwc(const float* src_nchw, const unetk_tensor* dst, void* stream);
+UNETK_API int unetk_nhwc_to_nchw(const unetk_tensor* src, float* dst_nchw, void* stream);
 
 #ifdef __cplusplus
 }

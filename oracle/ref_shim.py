@@ -65,6 +65,46 @@ def _install_shims():
     tn.tqdm = _PassThroughTqdm
 
 
+_REF_PACKAGES = ("utils", "unet", "autoencoder", "clip", "prompt_based")
+
+
+def _is_reference_module(name: str) -> bool:
+    return any(name == p or name.startswith(p + ".") for p in _REF_PACKAGES)
+
+
+def random_init_clip_vit(seed: int = 0):
+    """The reference builds its encoder with ``CLIPVisionModel.from_pretrained("openai/clip-vit-base-patch16")``
+    (clip/clipunet.py:25-26), which needs the network.  BASELINE.json config 4 asks for RANDOM-INIT weights of that
+    architecture: patch ``from_pretrained`` of both classes to build ViT-B/16 (hidden 768, 12 layers, 224 px, patch 16)
+    from a default config.  Returns a context manager; nothing in the reference is edited."""
+    import contextlib
+
+    import torch
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+
+    @contextlib.contextmanager
+    def patched():
+        cfg_fp, model_fp = CLIPVisionConfig.from_pretrained, CLIPVisionModel.from_pretrained
+
+        def cfg_from(*a, **k):
+            return CLIPVisionConfig(patch_size=16)
+
+        def model_from(*a, **k):
+            state = torch.random.get_rng_state()
+            torch.manual_seed(seed)
+            try:
+                return CLIPVisionModel(CLIPVisionConfig(patch_size=16))
+            finally:
+                torch.random.set_rng_state(state)
+        CLIPVisionConfig.from_pretrained = staticmethod(cfg_from)
+        CLIPVisionModel.from_pretrained = staticmethod(model_from)
+        try:
+            yield
+        finally:
+            CLIPVisionConfig.from_pretrained, CLIPVisionModel.from_pretrained = cfg_fp, model_fp
+    return patched()
+
+
 def load():
     """Returns a namespace with the reference's hot-path symbols (raises if unavailable)."""
     if not available():
@@ -72,8 +112,7 @@ def load():
     _install_shims()
     # the reference's top-level packages are called `unet` and `utils`; import them under the
     # reference root without leaving it on sys.path for the rest of the process
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")
-             or k == "unet" or k.startswith("unet.")}
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_reference_module(k)}
     sys.path.insert(0, REFERENCE_ROOT)
     try:
         import importlib
@@ -90,10 +129,18 @@ def load():
         ns.WeightedDiceCELoss = ns.loss_mod.WeightedDiceCELoss
         ns.WeightedMemoryEfficientDiceLoss = ns.loss_mod.WeightedMemoryEfficientDiceLoss
         ns.MetricsHistory = ns.metrics_mod.MetricsHistory
+        # the other model families; each is optional
+        for attr, modname in (("autoencoder_mod", "autoencoder.autoencoder"), ("clip_mod", "clip.clipunet"),
+                              ("prompt_mod", "prompt_based.prompt")):
+            try:
+                setattr(ns, attr, importlib.import_module(modname))
+            except Exception as e:  # e.g. transformers missing
+                setattr(ns, attr, None)
+                setattr(ns, attr + "_error", e)
         return ns
     finally:
         sys.path.remove(REFERENCE_ROOT)
-        for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.") or k == "unet" or k.startswith("unet.")]:
+        for k in [k for k in sys.modules if _is_reference_module(k)]:
             # keep reference modules reachable only through `ns`
             sys.modules.pop(k)
         sys.modules.update(saved)

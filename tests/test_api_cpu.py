@@ -58,10 +58,19 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(L.WgradArgs) == 32 + 32 + 8 + 8
     assert ctypes.sizeof(L.BnBwdArgs) == 3 * 32 + 5 * 8 + 32 + 24
     assert ctypes.sizeof(L.BnFinalizeArgs) == 8 * 2 + 8 + 4 + 4 + 6 * 8 + 8 + 4 * 8
-    assert ctypes.sizeof(L.DiceCeArgs) == 8 * 2 + 16 + 8 + 8 + 8 + 16 + 8 * 6
+    assert ctypes.sizeof(L.DiceCeArgs) == 8 * 2 + 16 + 8 + 8 + 8 + 16 + 8 * 6 + 8
     assert ctypes.sizeof(L.HeadBnBwdArgs) == 32 + 8 + 8 + 8 + 4 * 8 + 8 + 32 + 4 * 8
     assert ctypes.sizeof(L.EvalImage) == 32
     assert ctypes.sizeof(L.EvalArgs) == 136      # static_assert'ed on the C side (csrc/eval.cu)
+    # ... and against what the compiled library itself reports
+    lib = L.lib()
+    lib.unetk_struct_size.restype = ctypes.c_int32
+    for which, cls in enumerate((L.Tensor, L.ConvArgs, L.WgradArgs, L.BnFinalizeArgs, L.BnBwdArgs, L.WJob, L.DiceCeArgs,
+                                 L.HeadBnBwdArgs, L.EvalImage, L.EvalArgs)):
+        assert lib.unetk_struct_size(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.unetk_struct_size(99) == -1
+    assert L.query_workspace(L.WS_DICE_ACCUM, 3) == 11 * 8 and L.query_workspace(L.WS_WGRAD, 1, 64, 128) == 64 * 9 * 128 * 4
+    assert L.query_workspace(L.WS_POOL_IDX, 2, 8, 8, 64) == 2 * 4 * 4 * 8 * 2
 
 
 def test_no_cpu_fallback():
