@@ -1,5 +1,6 @@
-"""Drop-in for the U-Net part of the reference's ``utils/training.py``: ``train_loop`` (:18-64),
-``eval_loop`` (:67-121) and ``start`` (:453-617) with the same signatures, printed lines and
+"""Drop-in for the reference's ``utils/training.py``: ``train_loop`` (:18-64), ``eval_loop`` (:67-121),
+``trainReconstruction`` (:123-151), ``train_loop_prompt`` (:153-199), ``evalReconstruction`` (:202-239),
+``eval_loop_prompt`` (:242-296) and ``start`` (:453-617) with the same signatures, printed lines and
 checkpoint dictionary keys.  Model, loss and metrics objects are passed in, exactly as in the
 reference; with this package's ``unet`` / ``WeightedDiceCELoss`` / ``MetricsHistory`` every step runs on
 the CUDA kernels, and the loops themselves only sequence work (host code stays Python).
@@ -286,6 +287,138 @@ def eval_loop(dataloader, model, loss_fn, device, target_size, agg):
     print(f"  Mean IoU (mIoU): {mean_iou:>8f}")
     print(f"  --- Per-Class IoU ---")
     for c in range(agg.get_num_classes()):
+        print(f"    Class {c}: {per_class_iou[c].item():>8f}")
+    print("-" * 25)
+    return avg_loss, mean_dice, mean_iou
+
+
+def trainReconstruction(dataloader, model, loss_fn, optimizer, accumulation_steps, device=None):
+    """One epoch of reconstruction pre-training (reference utils/training.py:123-151): ``loss_fn(model(X), X)`` with
+    gradient accumulation; returns the mean of the per-batch losses.  The reference reads a module-global ``device``;
+    here it defaults to the device of the model's parameters.  Per-batch losses are read back one step late
+    (``AsyncScalarReader``): same values, same order, no pipeline stall."""
+    import numpy as np
+    device = torch.device(device) if device is not None else next(model.parameters()).device
+    losses = []
+    model.train()
+    num_batches = len(dataloader)
+    cuda = device.type == "cuda"
+    reader = AsyncScalarReader(device, depth=2) if cuda else None
+    for batch_idx, (X, _) in enumerate(_progress(dataloader, total=num_batches, desc="Training")):
+        X = X.to(device, non_blocking=True)
+        pred = model(X)
+        loss = loss_fn(pred, X)
+        if reader is not None:
+            reader.push(loss)
+            losses += reader.ready()
+        else:
+            losses.append(loss.item())
+        (loss / accumulation_steps).backward()
+        if (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches:
+            optimizer.step()
+            optimizer.zero_grad()
+    if reader is not None:
+        losses += reader.drain()
+    return np.mean(losses)
+
+
+def evalReconstruction(dataloader, model, loss_fn, target_size, interpolation='bilinear', device=None):
+    """Evaluation of a reconstruction model at each image's original size (reference utils/training.py:202-239);
+    returns (total_loss / num_batches, mean per-image loss)."""
+    import numpy as np
+    device = torch.device(device) if device is not None else next(model.parameters()).device
+    model.eval()
+    num_batches = len(dataloader)
+    per_image = []
+    with torch.no_grad():
+        for original_X, _ in _progress(dataloader, total=num_batches, desc="Evaluation"):
+            resized_X, meta_list = process_batch_forward(original_X, target_size=target_size)
+            pred = model(resized_X.to(device, non_blocking=True))
+            pred = process_batch_reverse(pred, meta_list, interpolation=interpolation)
+            for p, label in zip(pred, original_X):
+                p = p.to(device).unsqueeze(0)
+                label = label.to(device).unsqueeze(0)
+                if label.shape[1] == 4 and label.ndim == 4:
+                    label = label[:, :3, :, :]          # RGBA to RGB
+                per_image.append(loss_fn(p, label.squeeze(1)).detach().double().reshape(()))
+    vals = torch.stack(per_image).cpu().numpy() if per_image else np.zeros(0)     # one read-back for the whole epoch
+    total_loss = float(vals.sum())
+    return total_loss / num_batches, np.mean(vals)
+
+
+def train_loop_prompt(dataloader, model, loss_fn, optimizer, accumulation_steps, device, scheduler=None, target_size=None):
+    """One epoch of training of a prompt-based model, batches of (image, point-prompt heat-map, label)
+    (reference utils/training.py:153-199)."""
+    model.train()
+    total_loss, processed_batches = 0.0, 0
+    optimizer.zero_grad()
+    num_batches = len(dataloader)
+    cuda = torch.device(device).type == "cuda"
+    reader = AsyncScalarReader(device) if cuda else None
+    pbar = _progress(enumerate(dataloader), total=num_batches, desc="Training")
+    for batch_idx, (X, p, y) in pbar:
+        if target_size is not None:
+            X, _ = process_batch_forward(X, target_size=target_size)
+            p, _ = process_batch_forward(p, target_size=target_size)
+            y, _ = process_batch_forward(y, target_size=target_size, interpolation="nearest")
+        X, p, y = X.to(device, non_blocking=True), p.to(device, non_blocking=True), y.to(device, non_blocking=True).long()
+        pred = model(X, p)
+        loss = loss_fn(pred, y.squeeze(1))
+        (loss / accumulation_steps).backward()
+        loss = loss.detach()
+        if (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches:
+            optimizer.step()
+            if scheduler:
+                scheduler.step()
+            optimizer.zero_grad()
+            if reader is not None:
+                reader.push(loss)
+                values = reader.ready()
+            else:
+                values = [loss.item()]
+            for value in values:
+                total_loss += value
+                processed_batches += 1
+                pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
+    if reader is not None:
+        for value in reader.drain():
+            total_loss += value
+            processed_batches += 1
+    avg_loss = total_loss / processed_batches if processed_batches > 0 else 0
+    print(f"Training Avg loss (per effective batch): {avg_loss:>8f}")
+    return avg_loss
+
+
+def eval_loop_prompt(dataloader, model, loss_fn, device, target_size, agg):
+    """Evaluation of a prompt-based model at each image's original resolution (reference utils/training.py:242-296).
+    Like the reference, ``agg`` is NOT reset here."""
+    model.eval()
+    num_images_processed = 0
+    losses = []
+    with torch.no_grad():
+        for X, p, y in _progress(dataloader, desc="Eval"):
+            X, meta_list = process_batch_forward(X, target_size=target_size)
+            p, _ = process_batch_forward(p, target_size=target_size)
+            preds = model(X.to(device, non_blocking=True), p.to(device, non_blocking=True))
+            preds = process_batch_reverse(preds, meta_list, interpolation='bilinear')
+            for pred, label in zip(preds, y):
+                label = label.to(device).long()
+                losses.append(loss_fn(pred.unsqueeze(0), label.unsqueeze(0).squeeze(1)).detach().double().reshape(()))
+                agg.accumulate(pred, label)
+                num_images_processed += 1
+    total_loss = float(torch.stack(losses).sum().item()) if losses else 0.0
+    avg_loss = total_loss / num_images_processed
+    mean_dice, mean_iou, mean_acc = agg.compute_epoch_metrics()
+    per_class_iou = agg.get_last_per_class_iou()
+    print(f"\n--- Evaluation Complete ---")
+    print(f"  Images Processed: {num_images_processed}")
+    print(f"  Average Loss (Original Size): {avg_loss:>8f}")
+    print(f"  Ignored Class : {agg.get_ignore_index()}")
+    print(f"  Macro Avg Acc score: {mean_acc:>8f}")
+    print(f"  Macro Avg Dice Score: {mean_dice:>8f}")
+    print(f"  Mean IoU (mIoU): {mean_iou:>8f}")
+    print(f"  --- Per-Class IoU ---")
+    for c in range(4):
         print(f"    Class {c}: {per_class_iou[c].item():>8f}")
     print("-" * 25)
     return avg_loss, mean_dice, mean_iou
