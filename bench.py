@@ -424,6 +424,232 @@ def run_gpu_arm(args):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------
+# other model families on the same kernels (BASELINE.json configs[2..4]); single GPU
+# ------------------------------------------------------------------------------------------------
+def build_family(workload, B, dev, reference=False):
+    """Returns (model, inputs on `dev` (list), step(*inputs) -> loss, description).  ``reference=True`` builds the
+    UNMODIFIED reference modules (oracle/_ref) instead of this package's."""
+    import torch
+    CW4 = torch.tensor([0.2046795970925636, 1.0271954434416883, 1.2293222812780409, 1.5388026781877073])
+    g = torch.Generator().manual_seed(1234)
+    if reference:
+        from oracle import ref_shim
+        ref = ref_shim.load()
+    torch.manual_seed(0)
+    if workload in ("autoencoder_recon", "autoencoder_seg"):
+        hw = 256
+        x = torch.rand(B, 3, hw, hw, generator=g)
+        if reference:
+            ae = ref.autoencoder_mod
+            Dice = ref.WeightedDiceCELoss
+        else:
+            from image_segmentation_b200.autoencoder import autoencoder as ae
+            from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss as Dice
+        if workload == "autoencoder_recon":
+            model = ae.ReconstructionAutoencoder(3)
+            mse = torch.nn.MSELoss()
+            inputs = [x]
+            fwd = lambda m, x: mse(m(x), x)  # noqa: E731
+            desc = "ReconstructionAutoencoder(3) 256x256 reconstruction pre-training step (MSE)"
+        else:
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                model = ae.SegmentationAutoencoder(3, 64, 4, freeze_encoder=True)
+            y = torch.randint(0, 4, (B, hw, hw), generator=g)
+            loss_fn = Dice(smooth_dice=1, class_weights=CW4.to(dev) if reference else CW4)
+            inputs = [x, y]
+            fwd = lambda m, x, y: loss_fn(m(x), y)  # noqa: E731
+            desc = "SegmentationAutoencoder(3, 64, 4, freeze_encoder=True) 256x256 training step (Dice+CE)"
+    elif workload in ("clip", "prompt"):
+        from oracle import ref_shim
+        hw = 224
+        x = torch.rand(B, 3, hw, hw, generator=g)
+        y = torch.randint(0, 4, (B, hw, hw), generator=g)
+        with ref_shim.random_init_clip_vit(seed=0):
+            if reference:
+                clip = ref.clip_mod.ClipUNet()
+            else:
+                from image_segmentation_b200.clip.clipunet import ClipUNet
+                clip = ClipUNet()
+            if workload == "clip":
+                model = clip
+                Dice = ref.WeightedDiceCELoss if reference else __import__(
+                    "image_segmentation_b200.utils.weighted_loss", fromlist=["WeightedDiceCELoss"]).WeightedDiceCELoss
+                loss_fn = Dice(smooth_dice=1, class_weights=CW4.to(dev) if reference else CW4)
+                inputs = [x, y]
+                fwd = lambda m, x, y: loss_fn(m(x), y)  # noqa: E731
+                desc = "ClipUNet (frozen random-init CLIP ViT-B/16 + U-Net decoder) 224x224 training step (Dice+CE)"
+            else:
+                heat = torch.rand(B, 1, hw, hw, generator=g)
+                stable_log = lambda t: torch.log(t + 1e-9)  # noqa: E731
+                if reference:
+                    model = ref.prompt_mod.PromptModel()
+                    NLL = ref.loss_mod.WeightedDiceNLLLoss
+                else:
+                    from image_segmentation_b200.prompt_based.prompt import PromptModel
+                    from image_segmentation_b200.utils.weighted_loss import WeightedDiceNLLLoss as NLL
+                    model = PromptModel(clip=clip)
+                loss_fn = NLL(smooth_dice=1, class_weights=CW4.to(dev) if reference else CW4, apply_softmax=False, nll_nonlin=stable_log)
+                inputs = [x, heat, y]
+                fwd = lambda m, x, h, y: loss_fn(m(x, h), y)  # noqa: E731
+                desc = "PromptModel (frozen ClipUNet + unet(4,1) + probability composition) 224x224 training step (Dice+NLL)"
+    else:
+        raise SystemExit(f"unknown workload {workload}")
+    model = model.to(dev).train()
+    return model, [t.to(dev) for t in inputs], fwd, desc
+
+
+def run_family_arm(args):
+    import torch
+    from image_segmentation_b200 import _lib as L
+    from image_segmentation_b200.utils.graph import GraphedStep
+    from image_segmentation_b200.utils.prefetch import AsyncScalarReader
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("--workload other than unet is a single-GPU measurement")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    L.lib()
+    peaks = load_peaks()
+    B = args.batch
+    model, inputs, fwd, desc = build_family(args.workload, B, dev)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+
+    def step(*inp):
+        loss = fwd(model, *inp)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    for _ in range(max(args.warmup, 3)):
+        step(*inputs)
+    graphed = None
+    if not args.no_graph:
+        try:
+            graphed = GraphedStep(step, inputs, models=[m for m in model.modules() if hasattr(m, "_engine")], optimizer=opt, warmup=1)
+        except Exception as e:
+            print(f"[bench] CUDA graph capture failed, timing the eager path: {e!r}", file=sys.stderr)
+    run = (lambda: graphed(*inputs)) if graphed is not None else (lambda: step(*inputs))
+    for _ in range(3):
+        run()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.COUNTERS["launches"] = 0
+    e0.record()
+    for _ in range(args.steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    value = B * args.steps / (ms / 1e3)
+    # end to end: the step's inputs come from pinned host memory every step, the loss is read back on the host
+    pinned = [t.cpu().pin_memory() for t in inputs]
+    slots = [[torch.empty_like(t) for t in inputs] for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def run_e2e(steps):
+        reader, total, evs = AsyncScalarReader(dev), 0.0, [None, None]
+        for i in range(steps):
+            k = i % 2
+            with torch.cuda.stream(copy_stream):
+                if evs[k] is not None:
+                    copy_stream.wait_event(evs[k])
+                for d, s in zip(slots[k], pinned):
+                    d.copy_(s, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            torch.cuda.current_stream().wait_event(ready)
+            loss = graphed(*slots[k]) if graphed is not None else step(*slots[k])
+            evs[k] = torch.cuda.Event()
+            evs[k].record()
+            reader.push(loss)
+            total += sum(reader.ready())
+        return total + sum(reader.drain())
+    run_e2e(2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    # contraction roofline from instrumented eager steps behind a spin kernel (see run_gpu_arm)
+    records, marks = [], []
+    for _ in range(3):
+        L.PROFILE_HOOK = records
+        torch.cuda._sleep(int(args.spin_ms * 1e-3 * 1.9e9))
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        step(*inputs)
+        m1.record()
+        L.PROFILE_HOOK = None
+        torch.cuda.synchronize()
+        marks.append((m0, m1))
+    step_ms = sum(a.elapsed_time(b) for a, b in marks) / 3
+    conv = [r for r in records if r[0] in ("conv", "wgrad")]
+    flops = sum(r[1] for r in conv)
+    kms = sum(r[2].elapsed_time(r[3]) for r in conv)
+    by_kind = {}
+    for r in records:
+        by_kind[r[0]] = by_kind.get(r[0], 0.0) + r[2].elapsed_time(r[3]) / 3
+    share = kms / 3 / step_ms
+    achieved = flops / (kms * 1e-3) / 1e12 if kms else 0.0
+    flop_per_image = flops / 3 / B
+    roof = {"bound": "tensor", "achieved": achieved if share >= 0.3 else None, "peak": peaks["sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["sustained"] if share >= 0.3 else None, "frac_of_burst": achieved / peaks["burst"],
+            "traffic": None, "share_of_step": share, "instrumented_step_ms": step_ms,
+            "ms_per_step_by_kernel": {k: round(v, 3) for k, v in sorted(by_kind.items())},
+            "algorithmic_gflop_per_image": flop_per_image / 1e9,
+            "step_tflops": B * flop_per_image / (ms / args.steps * 1e-3) / 1e12,
+            "note": "contraction kernels of this package only; time spent in torch's frozen ViT (clip / prompt workloads) is part "
+                    "of the step but not of `achieved`"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            cpu = family_cpu_baseline(args.workload)
+        except Exception as e:
+            cpu = {"unavailable": repr(e)[:200]}
+    line = {"metric": f"{args.workload}_train_images_per_sec", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc + f", batch {B}, bf16 activations + fp32 master weights, AdamW",
+                       "launch": "one CUDA graph per step" if graphed is not None else "eager launches"},
+            "clocks": clocks,
+            "e2e": {"value": B * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in pinned),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": L.COUNTERS["launches"] if graphed is None else None,
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+
+
+def family_cpu_baseline(workload, batch=2, steps=2):
+    """The UNMODIFIED reference model of the same family on the host cores (bounded sample: batch 2)."""
+    import torch
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores))
+    model, inputs, fwd, _ = build_family(workload, batch, torch.device("cpu"), reference=True)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.01)
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        loss = fwd(model, *inputs)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    return {"value": batch * len(times) / sum(times), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{len(times)} steps of batch {batch} ({torch.get_num_threads()} threads, fp32)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,6 +657,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=64, help="images per GPU")
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="unet", choices=["unet", "autoencoder_recon", "autoencoder_seg", "clip", "prompt"],
+                    help="unet = the headline (BASELINE.json configs[1]); the others are the model families of configs[2..4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph step")
     ap.add_argument("--spin-ms", type=float, default=120.0,
@@ -438,6 +666,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload != "unet":
+        run_family_arm(args)
     else:
         run_gpu_arm(args)
 

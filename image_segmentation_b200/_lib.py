@@ -428,7 +428,6 @@ def prep_head_bwd(dlogits, a, w, dout, da, dw=None, db=None, label=None) -> Call
     box = HeadBwdPtrs(ptr(dw), ptr(db))
     call = Call("head", 1, 0, _head_bwd_boxed, (dlogits.data_ptr(), C.byref(ta), w.data_ptr(), dout, C.byref(tda), box),
                 keep=(ta, tda, box, dlogits, a, w, da, dw, db), label=label)
-    call.box = None
     return call, box
 
 

@@ -20,27 +20,12 @@ unchanged and any optimizer works); sub-blocks are not callable on their own.
 import torch
 import torch.nn as nn
 
-from ..engine import Engine, NetPlan
+from ..engine import Engine, EngineModule as _EngineModule, NetPlan
 
 
 def _holder_forward(self, *a, **k):
     raise RuntimeError("sub-blocks of the autoencoder family are parameter holders; call the enclosing "
                        "ReconstructionAutoencoder / SegmentationAutoencoder (the whole network runs as one fused CUDA pass)")
-
-
-class _EngineModule(nn.Module):
-    """Top-level models: one launch-plan engine per instance, dropped whenever parameters move or are re-typed."""
-    _engine = None
-
-    def _apply(self, fn, *args, **kwargs):
-        # .to()/.cuda()/.double() move or retype parameters: cached device buffers are then stale
-        self._engine = None
-        return super()._apply(fn, *args, **kwargs)
-
-    def __getstate__(self):
-        state = self.__dict__.copy()
-        state["_engine"] = None
-        return state
 
 
 class EncoderBlock(nn.Module):

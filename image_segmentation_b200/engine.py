@@ -938,7 +938,10 @@ class _NetFunction(torch.autograd.Function):
         ctx.n_inputs = n_inputs
         ctx.params = tensors[n_inputs:]
         ctx.generation = plan.generation + 1
-        return plan.forward(tensors[:n_inputs], training=model.training)
+        # the result leaves the plan as a COPY: the plan-owned buffer is overwritten by the next forward pass (and returning
+        # the same tensor object every step would keep the previous step's autograd graph alive, which breaks CUDA-graph
+        # capture); 4 bytes x N x C x H x W once per step
+        return plan.forward(tensors[:n_inputs], training=model.training).clone()
 
     @staticmethod
     def backward(ctx, dout):
@@ -957,6 +960,22 @@ class _NetFunction(torch.autograd.Function):
         out = [grads.get(p) if p.requires_grad else None for p in ctx.params]
         gin = [plan.input_grads.get(i) if ctx.needs_input_grad[3 + i] else None for i in range(ctx.n_inputs)]
         return (None, None, None, *gin, *out)
+
+
+class EngineModule(torch.nn.Module):
+    """Base of every engine-backed module: one launch-plan engine per instance, dropped whenever parameters move or are
+    re-typed, never pickled."""
+    _engine = None
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to()/.cuda()/.double() move or retype parameters: cached device buffers are then stale
+        self._engine = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engine"] = None
+        return state
 
 
 class Engine:
@@ -978,7 +997,7 @@ class Engine:
                 raise RuntimeError("parameters must stay fp32 (master weights); precision is selected with model.precision")
         if self.check_inputs is not None:
             self.check_inputs(*inputs)
-        precision = os.environ.get("UNETK_PRECISION", m.precision)
+        precision = os.environ.get("UNETK_PRECISION", getattr(m, "precision", "bf16"))
         inputs = tuple(x.contiguous() if x.dtype == torch.float32 else x.float().contiguous() for x in inputs)
         dev = inputs[0].device
         key = (tuple(tuple(x.shape) for x in inputs), tuple(bool(x.requires_grad) for x in inputs), precision, dev.index)
@@ -1006,4 +1025,4 @@ class Engine:
                 plan.busy = True
                 return _NetFunction.apply(m, plan, len(inputs), *inputs, *params)
             with torch.no_grad():
-                return plan.forward(inputs, training=m.training)
+                return plan.forward(inputs, training=m.training).clone()

@@ -4,7 +4,8 @@ but ``unet.forward`` runs the B200-native engine (``engine.py``) instead of chai
 
 The nn.Conv2d / nn.BatchNorm2d / nn.ConvTranspose2d objects are kept purely as *parameter holders*
 (so ``torch.manual_seed(s); unet(3, 3)`` is bit-identical to the reference, checkpoints load unchanged
-and any optimizer works); their own ``forward`` methods are never called on the hot path.
+and any optimizer works); their own ``forward`` methods are never called on the hot path.  The blocks
+(``DoubleConvReLU``, ``Down``, ``Up``) stay callable on their own, as in the reference (unet/unet.py:24,44,62).
 
 Reference: unet/unet.py:4-25 (DoubleConvReLU), :28-45 (Down), :47-64 (Up), :67-105 (unet).
 
@@ -15,6 +16,7 @@ Extra, non-reference attributes of ``unet``:
 import torch
 from torch import nn
 
+from ..engine import Engine, EngineModule, NhwcOutput
 from .engine import UNetEngine
 
 
@@ -25,38 +27,69 @@ def _conv_bn_relu_pair(din, dout):
     return nn.Sequential(*layers)
 
 
-class DoubleConvReLU(nn.Module):
-    """(conv3x3 -> BatchNorm -> ReLU) x 2; parameter holder, see module docstring."""
+class DoubleConvReLU(EngineModule):
+    """(conv3x3 -> BatchNorm -> ReLU) x 2 (unet/unet.py:4-25).
+
+    Inside ``unet`` the block is a parameter holder (the whole network runs as ONE fused pass); called on its own it runs
+    as a small launch plan of its own: NCHW fp32 in -> NHWC -> the same fused kernels -> NCHW fp32 out, differentiable
+    w.r.t. parameters and input.  Channel counts on the tensor-core tier: multiples of 64 (or an image-like input with
+    at most 7 channels, which takes the first-layer im2col path and receives no input gradient)."""
 
     def __init__(self, din, dout):
         super().__init__()
         self.doubleConvReLU = _conv_bn_relu_pair(din, dout)
 
+    def _build(self, plan, x):
+        from .engine import double_conv
+        n, c, h, w = x.shape
+        src = plan.image_input(c, h, w) if 9 * c <= 64 else plan.nchw_input(0, x)
+        _, l2 = double_conv(plan, "block", self, src)
+        plan.add(NhwcOutput(plan, "block.out", l2.out))
+
     def forward(self, x):
-        raise RuntimeError("sub-blocks are parameter holders; call the enclosing unet(...) module "
-                           "(the whole network runs as one fused CUDA pass)")
+        if self._engine is None:
+            self._engine = Engine(self, self._build)
+        return self._engine.run(x)
 
 
 class Down(nn.Module):
-    """MaxPool2d(2,2) then DoubleConvReLU; parameter holder."""
+    """MaxPool2d(2,2) then DoubleConvReLU (unet/unet.py:28-45).  Called on its own: torch's MaxPool2d, then the block's
+    own launch plan (inside ``unet`` the pooling is fused into the producing BatchNorm-apply pass instead)."""
 
     def __init__(self, din, dout):
         super().__init__()
         self.maxpool_doubleConv = nn.Sequential(nn.MaxPool2d(kernel_size=2, stride=2), DoubleConvReLU(din, dout))
 
-    forward = DoubleConvReLU.forward
+    def forward(self, x):
+        return self.maxpool_doubleConv(x)
 
 
-class Up(nn.Module):
-    """ConvTranspose2d(k2,s2) + skip concatenation + DoubleConvReLU; parameter holder."""
+class Up(EngineModule):
+    """ConvTranspose2d(k2,s2) on x2 + cat([x1, up(x2)], 1) + DoubleConvReLU (unet/unet.py:47-64).  Called on its own it is
+    one launch plan: x1 lands in the first half of the concat buffer, the ConvTranspose epilogue writes the second."""
 
     def __init__(self, din, dout):
         super().__init__()
         self.upsample = nn.ConvTranspose2d(din, dout, kernel_size=2, stride=2)
         self.doubleConv = DoubleConvReLU(din, dout)
 
+    def _build(self, plan, x1, x2):
+        from .engine import double_conv
+        n, c1, h, w = x1.shape
+        if x2.shape[2] * 2 != h or x2.shape[3] * 2 != w:
+            # the reference fails in torch.cat (unet/unet.py:63) for such sizes
+            raise RuntimeError(f"Sizes of tensors must match: x1 {tuple(x1.shape)}, up(x2) from {tuple(x2.shape)}")
+        cat = plan.cat(h, w, [c1, self.upsample.out_channels], name="cat")
+        plan.nchw_input(0, x1, out=cat.parts[0])
+        a2 = plan.nchw_input(1, x2)
+        plan.conv_transpose("upsample", self.upsample, a2, out=cat.parts[1])
+        _, l2 = double_conv(plan, "doubleConv", self.doubleConv, cat)
+        plan.add(NhwcOutput(plan, "out", l2.out))
+
     def forward(self, x1, x2):
-        return DoubleConvReLU.forward(self, x1)
+        if self._engine is None:
+            self._engine = Engine(self, self._build)
+        return self._engine.run(x1, x2)
 
 
 class unet(nn.Module):

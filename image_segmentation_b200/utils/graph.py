@@ -18,6 +18,52 @@ from __future__ import annotations
 import torch
 
 
+class GraphedStep:
+    """Generic form: ``step_fn(*static_inputs) -> device scalar`` captured once; ``__call__(*inputs)`` copies the new inputs
+    into the static tensors and replays.  Used for the other model families (reconstruction: loss(model(x), x); prompt
+    model: model(x, heatmap)), where the step is not ``loss_fn(model(x), y)``.
+
+        step = GraphedStep(lambda x: train_step(x), [x_example], models=[model], warmup=2)
+    """
+
+    def __init__(self, step_fn, example_inputs, models=(), optimizer=None, warmup: int = 2):
+        dev = example_inputs[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedStep needs CUDA inputs")
+        self.step_fn, self.models = step_fn, list(models)
+        self.static = [t.contiguous().clone() for t in example_inputs]
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                step_fn(*self.static)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        if optimizer is not None:
+            optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = step_fn(*self.static)
+        torch.cuda.synchronize(dev)
+        self._engines = [getattr(m, "_engine", None) for m in self.models]
+
+    def __call__(self, *inputs):
+        if any(getattr(m, "_engine", None) is not e for m, e in zip(self.models, self._engines)):
+            raise RuntimeError("this GraphedStep was captured for buffers a model no longer owns; capture a new one")
+        for dst, src in zip(self.static, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for m in self.models:           # parameters changed inside the graph without bumping their version counters
+            eng = getattr(m, "_engine", None)
+            if eng is not None:
+                for pool in eng.plans.values():
+                    for plan in pool:
+                        plan._pack_versions = None
+        return self.out
+
+
 class GraphedTrainStep:
     def __init__(self, model, loss_fn, optimizer, example_x: torch.Tensor, example_y: torch.Tensor, metrics=None,
                  warmup: int = 3):

@@ -303,6 +303,53 @@ def test_train_graph_cache_never_replays_into_stale_state(monkeypatch):
     assert m2._train_graph is None and m2._engine is None
 
 
+def test_blocks_are_callable_on_their_own_like_the_reference():
+    """DoubleConvReLU / Down / Up forward (unet/unet.py:24,44,62): each block runs as its own launch plan.  Reference =
+    the same parameter holders run by torch's own modules (nn.Sequential of Conv2d/BatchNorm2d/ReLU, F.conv_transpose2d,
+    torch.cat) on the GPU in fp32."""
+    import copy
+    import torch.nn.functional as F
+    from image_segmentation_b200.unet.unet import DoubleConvReLU, Down, Up
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(6)
+    cases = []
+    dc = DoubleConvReLU(64, 128).to(DEV).train()
+    cases.append(("DoubleConvReLU", dc, [torch.randn(2, 64, 16, 24, generator=g)], lambda m, x: m.doubleConvReLU(x)))
+    dn = Down(64, 128).to(DEV).train()
+    cases.append(("Down", dn, [torch.randn(2, 64, 32, 16, generator=g)],
+                  lambda m, x: m.maxpool_doubleConv[1].doubleConvReLU(F.max_pool2d(x, 2, 2))))
+    up = Up(128, 64).to(DEV).train()
+    cases.append(("Up", up, [torch.randn(2, 64, 16, 16, generator=g), torch.randn(2, 128, 8, 8, generator=g)],
+                  lambda m, x1, x2: m.doubleConv.doubleConvReLU(torch.cat([x1, m.upsample(x2)], dim=1))))
+    first = DoubleConvReLU(3, 64).to(DEV).train()
+    cases.append(("DoubleConvReLU(3,64)", first, [torch.rand(2, 3, 32, 32, generator=g)], lambda m, x: m.doubleConvReLU(x)))
+    for name, mod, xs, ref_fn in cases:
+        ref_mod = copy.deepcopy(mod)
+        for sub in [mod] + list(mod.modules()):
+            sub.precision = "fp32"
+        xs_a = [x.to(DEV).requires_grad_(x.shape[1] > 7) for x in xs]
+        xs_b = [x.to(DEV).requires_grad_(x.shape[1] > 7) for x in xs]
+        out = mod(*xs_a)
+        ref = ref_fn(ref_mod, *xs_b)
+        assert out.shape == ref.shape, name
+        assert rel_max(out, ref) < 1e-4, (name, rel_max(out, ref))
+        up_grad = torch.randn(ref.shape, generator=g).to(DEV)
+        out.backward(up_grad)
+        ref.backward(up_grad)
+        for xa, xb in zip(xs_a, xs_b):
+            if xa.requires_grad:
+                assert rel_max(xa.grad, xb.grad) < 2e-3, (name, "input grad", rel_max(xa.grad, xb.grad))
+        for (k, p), (_, q) in zip(mod.named_parameters(), ref_mod.named_parameters()):
+            if k.endswith(".bias") and k.split(".")[-2] in ("0", "3"):
+                continue                   # conv bias in front of train-mode BatchNorm: exactly zero here, rounding noise in torch
+            assert rel_max(p.grad, q.grad) < 2e-3, (name, k, rel_max(p.grad, q.grad))
+        # bf16 tensor-core tier runs as well
+        for sub in [mod] + list(mod.modules()):
+            sub.precision = "bf16"
+        out16 = mod(*[x.to(DEV) for x in xs])
+        assert rel_l2(out16, ref) < 3e-2, (name, rel_l2(out16, ref))
+
+
 def test_forward_metrics_pipeline_matches_oracle():
     """argmax masks and confusion counts are bit-exact given identical logits."""
     x, y = make_batch(2, 32, 32, 3, 4, seed=9)
