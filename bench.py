@@ -497,6 +497,10 @@ def build_family(workload, B, dev, reference=False):
     else:
         raise SystemExit(f"unknown workload {workload}")
     model = model.to(dev).train()
+    if not reference and workload in ("clip", "prompt") and os.environ.get("UNETK_VIT_FP32", "0") != "1":
+        # the frozen third-party ViT under bf16 autocast (this package's tier is bf16); UNETK_VIT_FP32=1 keeps the reference's fp32
+        (model if workload == "clip" else model.clip).vit_autocast_dtype = torch.bfloat16
+        desc += "; frozen ViT under torch.autocast(bf16)"
     return model, [t.to(dev) for t in inputs], fwd, desc
 
 

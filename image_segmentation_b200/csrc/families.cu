@@ -109,41 +109,57 @@ __global__ void __launch_bounds__(256) bilinear_up_fwd_kernel(const T* __restric
   }
 }
 
-// gather form of the transpose: one thread per (source pixel, 8-channel group) sums the destination gradients whose
-// interpolation footprint contains that source pixel (window of ~2/scale destination rows / columns)
+// gather form of the transpose (no atomics): a warp owns one source pixel and `cgl` = min(C/8, 32) consecutive 8-channel
+// groups; its 32 / cgl lane rows walk the destination window whose interpolation footprint contains that source pixel
+// ((2/scale + 2)^2 positions: 34 x 34 for the 16x up-sampling of the last decoder block, where C/8 = 8 and four lane rows
+// share the walk) and are summed with shuffles.  Lanes of one row read consecutive 16-byte pieces of one pixel.
 template <typename T>
-__global__ void __launch_bounds__(128) bilinear_up_bwd_kernel(const T* __restrict__ dd, int dld, int n, int oh, int ow, int c,
-                                                              T* __restrict__ ds, int sld, int ih, int iw, float sh, float sw) {
+__global__ void __launch_bounds__(256) bilinear_up_bwd_kernel(const T* __restrict__ dd, int dld, int n, int oh, int ow, int c,
+                                                              T* __restrict__ ds, int sld, int ih, int iw, float sh, float sw,
+                                                              int cgl) {
   const int cg = c / 8;
-  const int64_t total = (int64_t)n * ih * iw * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const int64_t p = i / cg;
+  const int chunks = cg / cgl;                       // cgl divides cg (both powers-of-two multiples; checked by the host)
+  const int rows = 32 / cgl;                         // lane rows sharing the window walk
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % cgl, pr = lane / cgl;
+  const int64_t warps_total = (int64_t)n * ih * iw * chunks;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t wstride = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t wi = warp0; wi < warps_total; wi += wstride) {
+    const int chunk = (int)(wi % chunks);
+    const int64_t p = wi / chunks;
     const int sx = (int)(p % iw), sy = (int)((p / iw) % ih);
     const int64_t img = p / ((int64_t)iw * ih);
-    // destination rows y with i0 == sy or i1 == sy lie in ((sy - 1 + 0.5)/sh - 0.5, (sy + 1 + 0.5)/sh - 0.5); generous bounds
-    int y0 = (int)floorf(((float)sy - 1.f) / sh) - 1, y1 = (int)ceilf(((float)sy + 2.f) / sh) + 1;
-    int x0 = (int)floorf(((float)sx - 1.f) / sw) - 1, x1 = (int)ceilf(((float)sx + 2.f) / sw) + 1;
+    const int g = chunk * cgl + gl;
+    // rows y whose source coordinate lies in (sy - 1, sy + 1): y in ((sy - 0.5)/sh - 0.5, (sy + 1.5)/sh - 0.5); one row of
+    // slack on either side (border clamping is handled by lerp_of itself: weights are evaluated, never assumed)
+    int y0 = (int)floorf(((float)sy - 0.5f) / sh - 0.5f) - 1, y1 = (int)ceilf(((float)sy + 1.5f) / sh - 0.5f) + 1;
+    int x0 = (int)floorf(((float)sx - 0.5f) / sw - 0.5f) - 1, x1 = (int)ceilf(((float)sx + 1.5f) / sw - 0.5f) + 1;
     y0 = y0 < 0 ? 0 : y0; x0 = x0 < 0 ? 0 : x0;
     y1 = y1 > oh - 1 ? oh - 1 : y1; x1 = x1 > ow - 1 ? ow - 1 : x1;
+    if (sy == 0) y0 = 0;                              // negative source coordinates clamp to row / column 0
+    if (sx == 0) x0 = 0;
+    const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const T* base = dd + img * oh * ow * (int64_t)dld + g * 8;
-    for (int y = y0; y <= y1; ++y) {
-      const Lerp ly = lerp_of(y, sh, ih);
+    for (int q = pr; q < cnt; q += rows) {
+      const int y = y0 + q / nx, x = x0 + q % nx;
+      const Lerp ly = lerp_of(y, sh, ih), lx = lerp_of(x, sw, iw);
       const float wy = (ly.i0 == sy ? ly.l0 : 0.f) + (ly.i1 == sy ? ly.l1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int x = x0; x <= x1; ++x) {
-        const Lerp lx = lerp_of(x, sw, iw);
-        const float wx = (lx.i0 == sx ? lx.l0 : 0.f) + (lx.i1 == sx ? lx.l1 : 0.f);
-        if (wx == 0.f) continue;
+      const float wx = (lx.i0 == sx ? lx.l0 : 0.f) + (lx.i1 == sx ? lx.l1 : 0.f);
+      const float wgt = wy * wx;
+      if (wgt != 0.f) {
         float v[8];
         load8(base + ((int64_t)y * ow + x) * dld, v);
-        const float wgt = wy * wx;
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
       }
     }
-    store8(ds + p * sld + g * 8, acc);
+    for (int o = cgl; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (pr == 0) store8(ds + p * sld + g * 8, acc);
   }
 }
 
@@ -303,10 +319,13 @@ int unetk_bilinear_up_bwd(const unetk_tensor* ddst, const unetk_tensor* dsrc, vo
   int rc = check_bilinear(dsrc, ddst, "bilinear_up_bwd");
   if (rc) return rc;
   const float sh = (float)dsrc->h / (float)ddst->h, sw = (float)dsrc->w / (float)ddst->w;
-  const int64_t items = pixels(*dsrc) * (dsrc->c / 8);
+  const int cg = dsrc->c / 8;
+  int cgl = 1;
+  while (cgl < 32 && cg % (cgl * 2) == 0) cgl *= 2;   // largest power of two <= 32 dividing the number of channel groups
+  const int64_t warps = pixels(*dsrc) * (cg / cgl);
   UNETK_DISPATCH_DTYPE(dsrc->dtype, T, {
-    bilinear_up_bwd_kernel<T><<<grid_1d(items, 128, 16), 128, 0, (cudaStream_t)stream>>>(
-        (const T*)ddst->ptr, ddst->ld, ddst->n, ddst->h, ddst->w, ddst->c, (T*)dsrc->ptr, dsrc->ld, dsrc->h, dsrc->w, sh, sw);
+    bilinear_up_bwd_kernel<T><<<grid_1d(warps * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const T*)ddst->ptr, ddst->ld, ddst->n, ddst->h, ddst->w, ddst->c, (T*)dsrc->ptr, dsrc->ld, dsrc->h, dsrc->w, sh, sw, cgl);
   });
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;

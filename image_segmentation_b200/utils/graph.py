@@ -127,3 +127,89 @@ class GraphedTrainStep:
                 for plan in pool:
                     plan._pack_versions = None
         return self.loss
+
+
+class GraphedAccumulation:
+    """Gradient accumulation (utils/training.py:49-56; the reference trains with micro-batch 2 x 32 accumulation steps,
+    unet/unet.ipynb:41-42,64) as two CUDA graphs:
+
+      micro graph   forward + loss + backward of ONE micro-batch; its gradients (views of the engine's flat buffer, taken
+                    with ``torch.autograd.grad`` so that no per-parameter AccumulateGrad kernels run) are added to a
+                    persistent flat accumulator with one multi-tensor add;
+      step graph    optimizer.step() on ``p.grad`` (= views of the accumulator) and zeroing of the accumulator.
+
+    ``micro(x, y)`` returns the micro-batch loss (device scalar); ``step()`` applies the update."""
+
+    def __init__(self, model, loss_fn, optimizer, example_x, example_y, accumulation_steps: int):
+        self.model, self.loss_fn, self.optimizer, self.k = model, loss_fn, optimizer, accumulation_steps
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.x = example_x.to(dev, dtype=torch.float32).contiguous().clone()
+        y = example_y.to(dev)
+        if y.dim() == 4:
+            y = y[:, 0]
+        self.y = y.long().contiguous().clone()
+        total = sum(p.numel() for p in self.params)
+        self.accum = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.accum[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        self.link()
+        model.train()
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            self._micro()                       # warm-up (allocator pools, lazily built backward plan)
+            self.accum.zero_()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.micro_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.micro_graph):
+            self.loss = self._micro()
+        self.step_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.step_graph, pool=self.micro_graph.pool()):
+            optimizer.step()
+            self.accum.zero_()
+        self.accum.zero_()
+        torch.cuda.synchronize(dev)
+        self._engine = getattr(model, "_engine", None)
+        self._param_ptrs = tuple(p.data_ptr() for p in self.params)
+
+    def link(self):
+        """``p.grad`` = views of the accumulator (what the optimizer reads; eager fall-back steps accumulate into them too)."""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def unlink(self):
+        for p in self.params:
+            p.grad = None
+
+    def _micro(self):
+        pred = self.model(self.x)
+        loss = self.loss_fn(pred, self.y)
+        grads = torch.autograd.grad(loss / self.k, self.params)
+        torch._foreach_add_(self.views, list(grads))
+        return loss.detach()
+
+    def _check(self):
+        if getattr(self.model, "_engine", None) is not self._engine or \
+                tuple(p.data_ptr() for p in self.params) != self._param_ptrs:
+            raise RuntimeError("this GraphedAccumulation was captured for buffers the model no longer owns; capture a new one")
+
+    def micro(self, x, y):
+        self._check()
+        self.x.copy_(x, non_blocking=True)
+        if y.dim() == 4:
+            y = y[:, 0]
+        self.y.copy_(y, non_blocking=True)
+        self.micro_graph.replay()
+        return self.loss
+
+    def step(self):
+        self.step_graph.replay()
+        eng = getattr(self.model, "_engine", None)
+        if eng is not None:
+            for pool in eng.plans.values():
+                for plan in pool:
+                    plan._pack_versions = None

@@ -47,14 +47,19 @@ def _progress(iterable, **kw):
 
 
 def _graph_eligible(model, loss_fn, optimizer, accumulation_steps, scheduler, device) -> bool:
-    """Whole-step CUDA-graph replay inside train_loop needs: this package's unet + fused loss on a CUDA device, one
-    micro-batch per optimiser step, no LR scheduler, and an optimizer whose step is capturable
-    (``torch.optim.AdamW(..., capturable=True)`` / ``fused=True``).  ``UNETK_TRAIN_GRAPH=0`` turns it off."""
+    """Whole-step CUDA-graph replay inside train_loop needs: this package's unet + fused loss on a CUDA device and an
+    optimizer whose step is capturable (``torch.optim.AdamW(..., capturable=True)``).  Gradient accumulation
+    (``accumulation_steps > 1``, the reference's own configuration: micro-batch 2 x 32) replays a micro-batch graph and an
+    optimizer graph (``GraphedAccumulation``).  A learning-rate scheduler is fine when every ``lr`` is a DEVICE tensor
+    (``AdamW(lr=torch.tensor(1e-3, device=...))``: schedulers then update it in place and the captured step reads the new
+    value); with python-float learning rates a scheduler keeps the loop eager.  ``UNETK_TRAIN_GRAPH=0`` turns it off."""
     from ..unet.unet import unet as _unet
     from .weighted_loss import WeightedDiceCELoss as _Loss
     if os.environ.get("UNETK_TRAIN_GRAPH", "1") != "1" or torch.device(device).type != "cuda":
         return False
-    if accumulation_steps != 1 or scheduler is not None or not isinstance(model, _unet) or not isinstance(loss_fn, _Loss):
+    if not isinstance(model, _unet) or not isinstance(loss_fn, _Loss):
+        return False
+    if scheduler is not None and not all(torch.is_tensor(g["lr"]) and g["lr"].is_cuda for g in optimizer.param_groups):
         return False
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         return False
@@ -92,15 +97,15 @@ def _graph_signature(model, loss_fn, optimizer, X, y):
             tuple(p.data_ptr() for p in params), state, hyper, loss_cfg, model.precision, model.conv_algo, model.training)
 
 
-def _graph_for(model, loss_fn, optimizer, X, y):
+def _graph_for(model, loss_fn, optimizer, X, y, accumulation_steps=1):
     """Captured step for this (model, loss, optimizer, batch shape); cached on the model across epochs.
 
     The cache entry holds STRONG references to the loss, the optimizer and the engine whose buffers the graph replays
     into, and is compared by identity (``is``) plus ``_graph_signature``: a moved model (``unet._apply`` drops the engine
     and this cache), a restored optimizer state (``load_state_dict`` replaces the state tensors), a changed learning
     rate / weight decay, or a different loss object all lead to a fresh capture instead of a replay into stale memory."""
-    from .graph import GraphedTrainStep
-    sig = _graph_signature(model, loss_fn, optimizer, X, y)
+    from .graph import GraphedAccumulation, GraphedTrainStep
+    sig = _graph_signature(model, loss_fn, optimizer, X, y) + (accumulation_steps,)
     cached = getattr(model, "_train_graph", None)
     if cached is not None:
         c_loss, c_opt, c_engine, c_sig, g = cached
@@ -109,14 +114,18 @@ def _graph_for(model, loss_fn, optimizer, X, y):
         model._train_graph = None        # stale: release the old graph (and its private memory pool) before re-capturing
         del cached, g
     try:
-        g = GraphedTrainStep(model, loss_fn, optimizer, X, y, metrics=None, warmup=0)
+        if accumulation_steps > 1:
+            g = GraphedAccumulation(model, loss_fn, optimizer, X, y, accumulation_steps)
+        else:
+            g = GraphedTrainStep(model, loss_fn, optimizer, X, y, metrics=None, warmup=0)
     except Exception as e:  # pragma: no cover - capture is an optimisation, never a requirement
         print(f"[train_loop] CUDA graph capture unavailable, staying eager: {e!r}")
         _invalidate_weight_packs(model)
         optimizer.zero_grad(set_to_none=True)
         return None
     # the signature is taken AFTER the capture: its warm-up may have created optimizer state
-    model._train_graph = (loss_fn, optimizer, model._engine, _graph_signature(model, loss_fn, optimizer, X, y), g)
+    model._train_graph = (loss_fn, optimizer, model._engine,
+                          _graph_signature(model, loss_fn, optimizer, X, y) + (accumulation_steps,), g)
     return g
 
 
@@ -143,39 +152,55 @@ def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device
     reader = AsyncScalarReader(device) if torch.device(device).type == "cuda" else None
     graph_ok = _graph_eligible(model, loss_fn, optimizer, accumulation_steps, scheduler, device)
     graphed = None
-    for batch_idx, (X, y) in pbar:
-        if graph_ok and batch_idx >= 1 and graphed is None:
-            # the first (eager) step of the epoch doubled as warm-up; from the second batch on the whole step
-            # (forward + loss + backward + optimizer) replays as one CUDA graph -- same kernels, no launch gaps
-            graphed = _graph_for(model, loss_fn, optimizer, X, y)
-            graph_ok = graphed is not None
-        use_graph = graphed is not None and tuple(X.shape) == tuple(graphed.x.shape)
-        step_now = (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches
-        if use_graph:
-            loss = graphed(X, y)                         # optimizer.step() and zero_grad() are part of the graph
-        else:
-            pred = model(X)
-            loss = loss_fn(pred, y.squeeze(1))
-            (loss / accumulation_steps).backward()
-            # drop the autograd graph now: a graph kept alive by `loss` would pin its AccumulateGrad nodes to this
-            # stream and invalidate the CUDA-graph capture of the next step
-            loss = loss.detach()
-            del pred
-            if step_now:
-                optimizer.step()
+    accum = accumulation_steps > 1
+    try:
+        for batch_idx, (X, y) in pbar:
+            step_now = (batch_idx + 1) % accumulation_steps == 0 or (batch_idx + 1) == num_batches
+            # the first optimiser step of the epoch runs eagerly and doubles as warm-up; from then on the whole step
+            # (forward + loss + backward [+ optimizer]) replays as CUDA graphs -- same kernels, no launch gaps
+            if graph_ok and graphed is None and batch_idx >= accumulation_steps and batch_idx % accumulation_steps == 0:
+                graphed = _graph_for(model, loss_fn, optimizer, X, y, accumulation_steps)
+                graph_ok = graphed is not None
+                if graphed is not None and accum:
+                    graphed.link()
+            use_graph = graphed is not None and tuple(X.shape) == tuple(graphed.x.shape)
+            if use_graph and not accum:
+                loss = graphed(X, y)                     # optimizer.step() and zero_grad() are part of the graph
                 if scheduler:
                     scheduler.step()
-                optimizer.zero_grad()
-        if step_now:
-            if reader is not None:
-                reader.push(loss)
-                values = reader.ready()
+            elif use_graph:
+                loss = graphed.micro(X, y)
+                if step_now:
+                    graphed.step()
+                    if scheduler:
+                        scheduler.step()
             else:
-                values = [loss.item()]
-            for value in values:
-                total_loss += value
-                processed_batches += 1
-                pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
+                pred = model(X)
+                loss = loss_fn(pred, y.squeeze(1))
+                (loss / accumulation_steps).backward()
+                # drop the autograd graph now: a graph kept alive by `loss` would pin its AccumulateGrad nodes to this
+                # stream and invalidate the CUDA-graph capture of the next step
+                loss = loss.detach()
+                del pred
+                if step_now:
+                    optimizer.step()
+                    if scheduler:
+                        scheduler.step()
+                    # with a live accumulation graph p.grad are views of its accumulator: zero them in place
+                    optimizer.zero_grad(set_to_none=not (graphed is not None and accum))
+            if step_now:
+                if reader is not None:
+                    reader.push(loss)
+                    values = reader.ready()
+                else:
+                    values = [loss.item()]
+                for value in values:
+                    total_loss += value
+                    processed_batches += 1
+                    pbar.set_postfix({'loss': value, 'lr': optimizer.param_groups[0]['lr']})
+    finally:
+        if graphed is not None and accum:
+            graphed.unlink()                              # like the reference, gradients are None after the loop
     if reader is not None:
         for value in reader.drain():
             total_loss += value

@@ -255,6 +255,59 @@ def test_train_loop_graph_replay_equals_eager(monkeypatch, capsys):
     assert int(res["1"][1]["down1.doubleConvReLU.1.num_batches_tracked"]) == 15
 
 
+def test_train_loop_accumulation_replays_graphs_and_matches_the_reference_curve(golden, monkeypatch):
+    """The reference's real configuration is gradient accumulation (micro-batch 2 x 32, unet/unet.ipynb:41-42,64).  With a
+    capturable optimizer train_loop replays a micro-batch graph + an optimizer graph; oracle: (a) the golden curve_b of the
+    reference's own train_loop (accumulation 2; here all 40 micro-batches in ONE epoch, so the mean of the 20 logged
+    losses must equal the mean of the golden curve), (b) the eager loop on the same schedule, step by step."""
+    g = golden["curve"]
+    cfg = json.loads(str(g["cfg_b"]))
+    n, hw, accum, steps = cfg["n"], cfg["hw"], cfg["accum"], cfg["steps"]
+    batches = [make_batch(n, hw, hw, 3, 3, seed=100 + i, labels="learnable") for i in range(4)]
+    loader = [(batches[i % 4][0], batches[i % 4][1].to(torch.uint8)) for i in range(steps * accum)]
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("UNETK_TRAIN_GRAPH", mode)
+        m = build(3, 3, "fp32")
+        opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01, capturable=True)
+        fn = loss_for(3)
+        avg = train_loop(loader, m, fn, opt, accum, torch.device(DEV), None, hw)
+        graph = m._train_graph
+        assert (graph is not None) == (mode == "1")
+        if mode == "1":
+            from image_segmentation_b200.utils.graph import GraphedAccumulation
+            assert isinstance(graph[4], GraphedAccumulation)
+            assert all(p.grad is None for p in m.parameters())           # unlinked after the loop, like zero_grad()
+        out[mode] = avg
+        # a second epoch re-uses the cached graphs (and an odd number of micro-batches ends with a partial group)
+        avg2 = train_loop(loader[:7], m, fn, opt, accum, torch.device(DEV), None, hw)
+        assert np.isfinite(avg2)
+        if mode == "1":
+            assert m._train_graph[4] is graph[4]
+    ref_mean = float(np.mean(g["curve_b"]))
+    assert abs(out["0"] - ref_mean) < 5e-3, (out["0"], ref_mean)
+    assert abs(out["1"] - out["0"]) < 5e-3, out
+
+
+def test_train_loop_graph_with_device_tensor_lr_and_scheduler(monkeypatch):
+    """An LR scheduler no longer forces the eager loop when the learning rate is a device tensor: the scheduler updates it
+    in place and the captured step reads the new value."""
+    hw, n = 32, 2
+    loader = [(x, y.to(torch.uint8)) for x, y in (make_batch(n, hw, hw, 3, 3, seed=600 + i, labels="learnable") for i in range(6))]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("UNETK_TRAIN_GRAPH", mode)
+        m = build(3, 3, "fp32")
+        opt = torch.optim.AdamW(m.parameters(), lr=torch.tensor(1e-3, device=DEV), weight_decay=0.01, capturable=True)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=2, gamma=0.1)
+        fn = loss_for(3)
+        losses = [train_loop(loader, m, fn, opt, 1, torch.device(DEV), sched, hw) for _ in range(2)]
+        assert (m._train_graph is not None) == (mode == "1")
+        res[mode] = (losses, float(opt.param_groups[0]["lr"]))
+    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=0, atol=5e-3)
+    assert abs(res["1"][1] - 1e-9) < 1e-12 and abs(res["0"][1] - 1e-9) < 1e-12        # 12 scheduler steps: 1e-3 * 0.1^6
+
+
 def test_train_graph_cache_never_replays_into_stale_state(monkeypatch):
     """the captured step cached on the model must be dropped / re-captured when (a) the model is moved
     (model.to() at the top of every start() re-creates the engine whose buffers the graph replays into), (b) the
@@ -323,6 +376,8 @@ def test_blocks_are_callable_on_their_own_like_the_reference():
                   lambda m, x1, x2: m.doubleConv.doubleConvReLU(torch.cat([x1, m.upsample(x2)], dim=1))))
     first = DoubleConvReLU(3, 64).to(DEV).train()
     cases.append(("DoubleConvReLU(3,64)", first, [torch.rand(2, 3, 32, 32, generator=g)], lambda m, x: m.doubleConvReLU(x)))
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the torch reference must be real fp32 (cuDNN defaults to TF32 convolutions)
     for name, mod, xs, ref_fn in cases:
         ref_mod = copy.deepcopy(mod)
         for sub in [mod] + list(mod.modules()):
@@ -348,6 +403,7 @@ def test_blocks_are_callable_on_their_own_like_the_reference():
             sub.precision = "bf16"
         out16 = mod(*[x.to(DEV) for x in xs])
         assert rel_l2(out16, ref) < 3e-2, (name, rel_l2(out16, ref))
+    torch.backends.cudnn.allow_tf32 = tf32
 
 
 def test_forward_metrics_pipeline_matches_oracle():
