@@ -207,7 +207,9 @@ def run_gpu_arm(args):
     model = unet(3, 3)
     model.precision = "bf16"
     model = model.to(dev).train()
-    dp = DataParallelUNet(model) if world > 1 else None
+    # UNETK_DP_BUCKET_MB / UNETK_DP_COMPRESS: scaling experiments (defaults: 25 MB buckets, fp32 gradients on the wire)
+    dp_kw = dict(bucket_mb=float(os.environ.get("UNETK_DP_BUCKET_MB", "25")), compress=os.environ.get("UNETK_DP_COMPRESS") or None)
+    dp = DataParallelUNet(model, **dp_kw) if world > 1 else None
     # same update rule as the reference's AdamW; fused = one kernel, capturable = usable inside a CUDA graph
     opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01, fused=True, capturable=True)
     loss_fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor(CLASS_W3))
@@ -401,6 +403,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"unet(3,3) 256x256 training step, batch {B}/GPU, bf16 activations + fp32 master weights, "
                                    "WeightedDiceCELoss + AdamW + MetricsHistory",
                        "global_batch": B * world, "parallelism": f"dp{world}",
+                       **({"dp": dp_kw} if world > 1 else {}),
                        "launch": "one CUDA graph per step" if graphed is not None else "eager launches",
                        "e2e_path": "pinned host batch -> DevicePrefetcher (copy of batch i+1 overlaps step i) -> "
                                    + ("GraphedTrainStep" if graphed is not None else "eager step")

@@ -19,6 +19,7 @@ F32, BF16 = 0, 1
 ALGO_AUTO, ALGO_SIMT, ALGO_TC = 0, 1, 2
 # experiment switches of the tcgen05 path (include/unetk.h UNETK_TC_*), OR-ed into `algo`; the shared library itself
 # reads no environment variables -- tools set TC_FLAGS (or UNETK_TC_FLAGS="no_pair,no_halo,...") on the Python side
+TC_DETERMINISTIC = 1 << 14      # unetk_wgrad: ordered two-pass split reduction instead of fp32 atomics
 TC_FLAG_BITS = {"no_pair": 1 << 8, "no_halo": 1 << 9, "no_even_groups": 1 << 10, "no_halo_n256": 1 << 11,
                 "no_halo_pair": 1 << 12, "no_wgrad_c64": 1 << 13}
 TC_FLAGS = 0
@@ -42,7 +43,8 @@ class ConvArgs(C.Structure):
 
 
 class WgradArgs(C.Structure):
-    _fields_ = [("u", Tensor), ("s", Tensor), ("dw", C.c_void_p), ("mode", C.c_int32), ("algo", C.c_int32)]
+    _fields_ = [("u", Tensor), ("s", Tensor), ("dw", C.c_void_p), ("mode", C.c_int32), ("algo", C.c_int32),
+                ("partial", C.c_void_p), ("partial_bytes", C.c_int64)]
 
 
 class BnFinalizeArgs(C.Structure):
@@ -114,6 +116,8 @@ def lib():
         l.unetk_version.restype = C.c_int
         l.unetk_query_workspace.restype = C.c_int64
         l.unetk_query_workspace.argtypes = [C.c_int32] * 5
+        l.unetk_wgrad_partial_bytes.restype = C.c_int64
+        l.unetk_wgrad_partial_bytes.argtypes = [C.POINTER(WgradArgs)]
         l.unetk_last_error.restype = C.c_char_p
         vp = C.c_void_p
         P = C.POINTER
@@ -161,7 +165,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_query_workspace", "unetk_struct_size", "unetk_im2col3x3_first", "unetk_permute3",
     "unetk_weights_pack", "unetk_weights_unpack",
-    "unetk_conv", "unetk_wgrad", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
+    "unetk_conv", "unetk_wgrad", "unetk_wgrad_partial_bytes", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
     "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply", "unetk_bn_relu_head_fprop",
@@ -341,16 +345,27 @@ def conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALGO_AUT
     prep_conv(x, w, y, mode, bias, stat_sum, stat_sumsq, algo, algo_flops, bn_reduce)(stream_ptr())
 
 
-def prep_wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None, label=None) -> Call:
-    a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo | TC_FLAGS)
+def wgrad_partial_bytes(u, s, mode, algo=ALGO_AUTO) -> int:
+    """Scratch bytes unetk_wgrad needs in deterministic mode for this problem (needs a CUDA device: SM count)."""
+    a = WgradArgs(nhwc(u), nhwc(s), None, mode, algo | TC_FLAGS | TC_DETERMINISTIC, None, 0)
+    n = lib().unetk_wgrad_partial_bytes(C.byref(a))
+    if n < 0:
+        check(int(n))
+    return int(n)
+
+
+def prep_wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None, label=None, partial=None) -> Call:
+    """partial: scratch tensor (float32) => deterministic split reduction (UNETK_TC_DETERMINISTIC)."""
+    a = WgradArgs(nhwc(u), nhwc(s), dw.data_ptr(), mode, algo | TC_FLAGS | (TC_DETERMINISTIC if partial is not None else 0),
+                  ptr(partial), 0 if partial is None else partial.numel() * partial.element_size())
     if algo_flops is None:
         taps = (1, 9, 4)[mode]
         algo_flops = 2 * u.shape[0] * u.shape[1] * u.shape[2] * taps * u.shape[3] * s.shape[3]
-    return Call("wgrad", 1, algo_flops, lib().unetk_wgrad, (C.byref(a),), tag=mode, keep=(a, u, s, dw), label=label)
+    return Call("wgrad", 1, algo_flops, lib().unetk_wgrad, (C.byref(a),), tag=mode, keep=(a, u, s, dw, partial), label=label)
 
 
-def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None):
-    prep_wgrad(u, s, dw, mode, algo, algo_flops)(stream_ptr())
+def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None, partial=None):
+    prep_wgrad(u, s, dw, mode, algo, algo_flops, partial=partial)(stream_ptr())
 
 
 def prep_channel_sum(t, out=None, label=None) -> Call:

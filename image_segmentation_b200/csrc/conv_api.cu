@@ -124,6 +124,18 @@ int unetk_wgrad(const unetk_wgrad_args* a, void* stream) {
   return simt_wgrad(a, taps, (cudaStream_t)stream);
 }
 
+int64_t unetk_wgrad_partial_bytes(const unetk_wgrad_args* a) {
+  if (!a || !tensor_ok(a->u) || !tensor_ok(a->s) || a->mode < 0 || a->mode > 2) {
+    set_error("wgrad_partial_bytes: bad arguments");
+    return UNETK_ERR_INVALID;
+  }
+  int algo = a->algo & UNETK_ALGO_MASK;
+  if (algo == UNETK_ALGO_AUTO) algo = a->u.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  const char* why = "";
+  if (algo != UNETK_ALGO_TC || !tc_wgrad_supported(a, 0, &why)) return 0;   // the CUDA-core tier needs no partial buffer
+  return tc_wgrad_partial_bytes(a, a->mode == 0 ? 1 : (a->mode == 1 ? 9 : 4));
+}
+
 int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream) {
   UNETK_REQUIRE(t && out, "channel_sum: null argument");
   UNETK_REQUIRE(tensor_ok(*t) && vec8_ok(*t), "channel_sum: t must be NHWC with c%%8==0, ld%%8==0, 16B aligned");

@@ -20,5 +20,6 @@ bool tc_conv_supported(const unetk_conv_args* a, const ConvGeom& g, const char**
 int tc_conv(const unetk_conv_args* a, const ConvGeom& g, cudaStream_t stream);
 bool tc_wgrad_supported(const unetk_wgrad_args* a, int taps, const char** why);
 int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream);
+int64_t tc_wgrad_partial_bytes(const unetk_wgrad_args* a, int taps);
 
 }  // namespace unetk

@@ -1083,7 +1083,36 @@ struct WgradParams {
   int cu_tiles, cs_tiles;  // output tiles of BM x BN
   int cu, cs;
   float* dw;
+  // deterministic mode (UNETK_TC_DETERMINISTIC): every (output tile, split) work item STORES its partial sums to
+  // partial[split][...] (same element layout as dw) and wgrad_reduce_kernel adds the splits to dw in index order
+  float* partial;
+  int64_t out_elems;
 };
+
+__device__ __forceinline__ void st_global_v4(float* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gptr), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+// accumulate (atomics, default) or store (deterministic mode) four consecutive fp32 weight-gradient elements
+__device__ __forceinline__ void wgrad_out_v4(bool det, float* gptr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  if (det) st_global_v4(gptr, a, b, c, d); else red_add_v4(gptr, a, b, c, d);
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int64_t out_elems,
+                                                           float* __restrict__ dw) {
+  const int64_t n4 = out_elems / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(partial)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(partial + (int64_t)s * out_elems)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 d = reinterpret_cast<float4*>(dw)[i];
+    d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
+    reinterpret_cast<float4*>(dw)[i] = d;
+  }
+}
 
 template <int BM_SLABS, int BN_SLABS>
 struct WgradCfg {
@@ -1234,7 +1263,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
       tcgen05_fence_after();
       const int cu_idx = cu_t * (BM_SLABS * 64) + row;
       const bool valid = row < BM_SLABS * 64 && cu_idx < p.cu;
-      float* dst = p.dw + ((int64_t)cu_idx * p.taps + tap) * p.cs + cs_t * BLOCK_N;
+      const bool det = p.partial != nullptr;
+      float* dst = (det ? p.partial + (int64_t)split * p.out_elems : p.dw) + ((int64_t)cu_idx * p.taps + tap) * p.cs + cs_t * BLOCK_N;
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t r[32];
@@ -1242,7 +1272,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad_kernel(const __grid_c
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) red_add_v4(dst + c * 32 + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
+          for (int j = 0; j < 32; j += 4) wgrad_out_v4(det, dst + c * 32 + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
       }
       tcgen05_fence_before();
@@ -1407,9 +1437,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_kernel(const __gri
         tmem_ld_wait();
         if (valid) {
           const int s_tap = c >> 1;
-          float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + s_tap)) * p.cs + cs_t * 64 + (c & 1) * 32;
+          const bool det = p.partial != nullptr;
+          float* dst = (det ? p.partial + (int64_t)split * p.out_elems : p.dw) + ((int64_t)cu_idx * 9 + (r * 3 + s_tap)) * p.cs +
+                       cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
+          for (int j = 0; j < 32; j += 4) wgrad_out_v4(det, dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
         }
       }
       tcgen05_fence_before();
@@ -1547,7 +1579,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const _
     const int row = q * 32 + lane;
     int it = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const int cs_t = item / p.splits;
+      const int cs_t = item / p.splits, split = item % p.splits;
+      const bool det = p.partial != nullptr;
+      float* const out_base = det ? p.partial + (int64_t)split * p.out_elems : p.dw;
       mbar_wait(tmem_full_bar, (uint32_t)(it & 1));
       tcgen05_fence_after();
       // accumulator 1 (M = 128): lanes 0..63 = dw[r=1] of channel `lane`, lanes 64..127 = dw[r=0] of channel lane-64
@@ -1558,9 +1592,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const _
           uint32_t rg[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, rg);
           tmem_ld_wait();
-          float* dst = p.dw + ((int64_t)cu_idx * 9 + (r * 3 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
+          float* dst = out_base + ((int64_t)cu_idx * 9 + (r * 3 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
+          for (int j = 0; j < 32; j += 4) wgrad_out_v4(det, dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
         }
       }
       // accumulator 2 (M = 64): row m lives in TMEM lane (m/16)*32 + m%16 -> dw[r=2]
@@ -1572,9 +1606,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) tc_wgrad3x3_c64_kernel(const _
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 256 + c * 32, rg);
           tmem_ld_wait();
           if (lane < 16) {
-            float* dst = p.dw + ((int64_t)cu_idx * 9 + (6 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
+            float* dst = out_base + ((int64_t)cu_idx * 9 + (6 + (c >> 1))) * p.cs + cs_t * 64 + (c & 1) * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
+            for (int j = 0; j < 32; j += 4) wgrad_out_v4(det, dst + j, rg[j], rg[j + 1], rg[j + 2], rg[j + 3]);
           }
         }
       }
@@ -1873,6 +1907,55 @@ static void choose_splits(int64_t out_tiles, int num_ptiles, int* ptiles_per_spl
   *splits_out = (num_ptiles + per - 1) / per;
 }
 
+// Number of pixel splits the dispatcher below will choose for this problem (and whether it takes the 3x3 halo form).
+static int wgrad_splits(const unetk_wgrad_args* a, int taps) {
+  using namespace tc;
+  int per = 0, splits = 1;
+  if (a->mode == 1 && a->u.h >= 16 && a->u.w >= 8 && !(a->algo & UNETK_TC_NO_HALO)) {
+    const bool c64 = a->u.c == 64 && !(a->algo & UNETK_TC_NO_WGRAD_C64);
+    const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1;
+    const int64_t ptiles = (int64_t)((a->u.w + 7) / 8) * ((a->u.h + 15) / 16) * a->u.n;
+    const int64_t out_tiles = c64 ? (int64_t)(a->s.c / 64) : (int64_t)(a->u.c / (64 * bm_slabs)) * (a->s.c / 64) * 3;
+    choose_splits(out_tiles, (int)ptiles, &per, &splits);
+  } else {
+    const PixelTile pt = choose_pixel_tile(a->u.n, a->u.h, a->u.w);
+    const int bm_slabs = a->u.c % 128 == 0 ? 2 : 1, bn_slabs = a->s.c % 128 == 0 ? 2 : 1;
+    const int64_t out_tiles = (int64_t)(a->u.c / (64 * bm_slabs)) * (a->s.c / (64 * bn_slabs)) * taps;
+    choose_splits(out_tiles, (int)pt.num_tiles(), &per, &splits);
+  }
+  return splits;
+}
+
+int64_t tc_wgrad_partial_bytes(const unetk_wgrad_args* a, int taps) {
+  const int splits = wgrad_splits(a, taps);
+  return splits > 1 ? (int64_t)splits * a->u.c * taps * a->s.c * (int64_t)sizeof(float) : 0;
+}
+
+// deterministic mode: route the epilogues to the caller's partial buffer; returns 1 when active
+static int setup_deterministic(const unetk_wgrad_args* a, int taps, tc::WgradParams& p) {
+  p.out_elems = (int64_t)a->u.c * taps * a->s.c;
+  p.partial = nullptr;
+  if (!(a->algo & UNETK_TC_DETERMINISTIC) || p.splits <= 1) return 0;
+  const int64_t need = (int64_t)p.splits * p.out_elems * (int64_t)sizeof(float);
+  if (!a->partial || a->partial_bytes < need) {
+    set_error("wgrad(tc): UNETK_TC_DETERMINISTIC needs a partial buffer of %lld bytes (unetk_wgrad_partial_bytes), got %lld",
+              (long long)need, (long long)(a->partial ? a->partial_bytes : 0));
+    return -1;
+  }
+  p.partial = a->partial;
+  return 1;
+}
+
+static int finish_deterministic(const tc::WgradParams& p, cudaStream_t stream) {
+  const int64_t n4 = p.out_elems / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  tc::wgrad_reduce_kernel<<<(unsigned)(blocks > 0 ? blocks : 1), 256, 0, stream>>>(p.partial, p.splits, p.out_elems, p.dw);
+  UNETK_LAUNCH_CHECK();
+  return UNETK_OK;
+}
+
 static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   using namespace tc;
   WgradParams p;
@@ -1897,8 +1980,11 @@ static int tc_wgrad3x3_halo(const unetk_wgrad_args* a, cudaStream_t stream) {
   choose_splits(out_tiles, p.num_ptiles, &p.ptiles_per_split, &p.splits);
   UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
   p.dw = a->dw;
-  if (c64) return launch_wgrad3x3_c64(p, stream);
-  return bm_slabs == 2 ? launch_wgrad3x3<2>(p, stream) : launch_wgrad3x3<1>(p, stream);
+  const int det = setup_deterministic(a, 9, p);
+  if (det < 0) return UNETK_ERR_INVALID;
+  rc = c64 ? launch_wgrad3x3_c64(p, stream) : (bm_slabs == 2 ? launch_wgrad3x3<2>(p, stream) : launch_wgrad3x3<1>(p, stream));
+  if (rc || !det) return rc;
+  return finish_deterministic(p, stream);
 }
 
 int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
@@ -1929,10 +2015,14 @@ int tc_wgrad(const unetk_wgrad_args* a, int taps, cudaStream_t stream) {
   choose_splits(out_tiles, p.num_ptiles, &p.ptiles_per_split, &p.splits);
   UNETK_REQUIRE(out_tiles * p.splits < (1LL << 31), "wgrad(tc): too many work items");
   p.dw = a->dw;
-  if (bm_slabs == 2 && bn_slabs == 2) return launch_wgrad<2, 2>(p, stream);
-  if (bm_slabs == 2 && bn_slabs == 1) return launch_wgrad<2, 1>(p, stream);
-  if (bm_slabs == 1 && bn_slabs == 2) return launch_wgrad<1, 2>(p, stream);
-  return launch_wgrad<1, 1>(p, stream);
+  const int det = setup_deterministic(a, taps, p);
+  if (det < 0) return UNETK_ERR_INVALID;
+  if (bm_slabs == 2 && bn_slabs == 2) rc = launch_wgrad<2, 2>(p, stream);
+  else if (bm_slabs == 2 && bn_slabs == 1) rc = launch_wgrad<2, 1>(p, stream);
+  else if (bm_slabs == 1 && bn_slabs == 2) rc = launch_wgrad<1, 2>(p, stream);
+  else rc = launch_wgrad<1, 1>(p, stream);
+  if (rc || !det) return rc;
+  return finish_deterministic(p, stream);
 }
 
 }  // namespace unetk

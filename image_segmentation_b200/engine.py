@@ -226,7 +226,7 @@ class ConvSigmoidOut(Node):
         w = self.conv.weight
         if w.requires_grad:
             flops = 2 * self.z.shape[0] * self.z.shape[1] * self.z.shape[2] * 9 * self.cin * self.dout
-            ops.append(L.prep_wgrad(self.dz, self.src.t, self.ws, 1, algo=plan.algo, algo_flops=flops, label=self.name))
+            ops.append(plan.wgrad_call(self.dz, self.src.t, self.ws, 1, algo_flops=flops, label=self.name))
             o0 = plan._off_of[id(w)]
 
             def unpack(o0=o0, w=w):
@@ -280,7 +280,7 @@ class Conv1x1(Node):
         w, b = self.conv.weight, self.conv.bias
         if w.requires_grad:
             # dw[cout][1][cin] is the parameter layout itself: accumulate straight into the flat gradient buffer
-            call = L.prep_wgrad(_flat_rows(dy), _flat_rows(self.src.t), plan.ws, 0, algo=plan.algo, label=self.name)
+            call = plan.wgrad_call(_flat_rows(dy), _flat_rows(self.src.t), plan.ws, 0, label=self.name)
             call.patch_ptr(call.keep[0], "dw", plan._goff(w))
             ops.append(call)
         if b is not None and b.requires_grad:
@@ -357,6 +357,10 @@ class NetPlan:
         self.pair_first = False
         self.kpad = 0
         self.xcol = None
+        # model.deterministic = True: weight gradients use the ordered two-pass split reduction (bit-reproducible runs)
+        self.deterministic = bool(getattr(model, "deterministic", False)) or os.environ.get("UNETK_DETERMINISTIC", "0") == "1"
+        self._det_sites: list = []
+        self._partial = None
         self.fuse_head_enabled = os.environ.get("UNETK_FUSE_HEAD", "1") == "1"
         self.fuse_reduce_enabled = os.environ.get("UNETK_FUSE_BN_REDUCE", "1") == "1"
 
@@ -715,7 +719,9 @@ class NetPlan:
             if self._node_runs_backward(l):
                 l.dz = torch.empty_like(l.z)
         # 5. the launch list ---------------------------------------------------------------------------------------------
+        self._det_sites = []
         self._bwd = self._build_backward_calls(order_nodes)
+        self._attach_partial_scratch()
 
     def _node_runs_backward(self, nd) -> bool:
         if isinstance(nd, ConvBNReLU):
@@ -732,6 +738,25 @@ class NetPlan:
 
     def _bn_red(self, p: Optional[ConvBNReLU]):
         return (p.z, p.scale, p.shift, p.mean, p.invstd, p.bwd_sums) if p is not None else None
+
+    def wgrad_call(self, u, s, dw, mode, **kw) -> L.Call:
+        """Prepared unetk_wgrad launch; in deterministic mode the call site is recorded so that one shared partial-sum
+        scratch buffer (sized for the largest site; the launches run one after another) can be attached afterwards."""
+        call = L.prep_wgrad(u, s, dw, mode, algo=self.algo, **kw)
+        if self.deterministic and u.dtype == torch.bfloat16 and self.algo in (L.ALGO_AUTO, L.ALGO_TC):
+            self._det_sites.append((call.keep[0], L.wgrad_partial_bytes(u, s, mode, self.algo)))
+        return call
+
+    def _attach_partial_scratch(self):
+        need = max([n for _, n in self._det_sites], default=0)
+        if need == 0:
+            return
+        self._partial = torch.empty(need // 4, dtype=torch.float32, device=self.device)
+        for args, n in self._det_sites:
+            if n > 0:
+                args.partial = self._partial.data_ptr()
+                args.partial_bytes = need
+                args.algo |= L.TC_DETERMINISTIC
 
     def _dgrad_call(self, nd, mode, dy: torch.Tensor, label):
         """Data gradient of a conv3x3 / convT node into its source's gradient view; a source that is a concat of
@@ -825,18 +850,17 @@ class NetPlan:
                     if wreq:
                         if self.pair_first:
                             # dW' [2*cout][2*kpad] over pixel pairs; weights_unpack (kind 3) adds its two diagonal blocks
-                            ops.append(L.prep_wgrad(self._pairs(l.dz), self._pairs(l.src.t), l.ws, 0, algo=self.algo,
-                                                    algo_flops=flops, label=l.name))
+                            ops.append(self.wgrad_call(self._pairs(l.dz), self._pairs(l.src.t), l.ws, 0, algo_flops=flops, label=l.name))
                             jobs_pending.append((l.ws.data_ptr(), self._goff(l.conv.weight), None, 3, l.cout, l.cin, 2 * self.kpad))
                         else:
-                            ops.append(L.prep_wgrad(l.dz, l.src.t, l.ws, 0, algo=self.algo, algo_flops=flops, label=l.name))
+                            ops.append(self.wgrad_call(l.dz, l.src.t, l.ws, 0, algo_flops=flops, label=l.name))
                             jobs_pending.append((l.ws.data_ptr(), self._goff(l.conv.weight), None, 2, l.cout, l.cin, self.kpad))
                 else:
                     dg = self._dgrad_call(l, L.MODE_3X3, l.dz, l.name)
                     if dg is not None:
                         ops.append(dg)
                     if wreq:
-                        ops.append(L.prep_wgrad(l.dz, l.src.t, l.ws, 1, algo=self.algo, label=l.name))
+                        ops.append(self.wgrad_call(l.dz, l.src.t, l.ws, 1, label=l.name))
                         jobs_pending.append((l.ws.data_ptr(), self._goff(l.conv.weight), None, 0, l.cout, l.cin, 0))
                 # conv bias in front of train-mode BatchNorm: its gradient is identically zero (flat buffer is zeroed)
                 done_params += len([p for p in l.params() if p.requires_grad])
@@ -847,7 +871,7 @@ class NetPlan:
                 if dg is not None:
                     ops.append(dg)
                 if ct.mod.weight.requires_grad:
-                    ops.append(L.prep_wgrad(ct.src.t, g_out, ct.ws, 2, algo=self.algo, label=ct.name))
+                    ops.append(self.wgrad_call(ct.src.t, g_out, ct.ws, 2, label=ct.name))
                     jobs_pending.append((ct.ws.data_ptr(), self._goff(ct.mod.weight), None, 1, ct.cout, ct.cin, 0))
                 if ct.mod.bias is not None and ct.mod.bias.requires_grad:
                     cs = L.prep_channel_sum(g_out, None, label=ct.name)

@@ -27,13 +27,19 @@ class DataParallelUNet:
     """Attach bucketed gradient all-reduce to a ``unet`` instance (not a wrapper: the model object,
     its ``state_dict`` and the train loop stay exactly what they were)."""
 
-    def __init__(self, model, process_group=None, bucket_mb: float = 25.0, broadcast_from: int = 0):
+    def __init__(self, model, process_group=None, bucket_mb: float = 25.0, broadcast_from: int = 0, compress=None):
+        """``bucket_mb``: minimum size of an all-reduce (a huge value = ONE all-reduce after the last gradient).
+        ``compress="bf16"`` (opt-in, changes numerics): gradients travel as bf16 (half the bytes; the sum over ranks is
+        formed in bf16 by NCCL) and are widened back to fp32 afterwards -- stock DDP's bf16 compression hook."""
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("torch.distributed must be initialised (backend nccl) before DataParallelUNet")
         self.model = model
         self.group = process_group
         self.world = dist.get_world_size(process_group)
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        if compress not in (None, "bf16"):
+            raise ValueError("compress must be None or 'bf16'")
+        self.compress = compress
         self._works: List = []
         self._sent = 0
         self._enabled = True
@@ -58,15 +64,21 @@ class DataParallelUNet:
 
     def _launch(self, plan, end_offset):
         chunk = plan.flat_grad[self._sent:end_offset]
-        self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.compress == "bf16":
+            wire = chunk.to(torch.bfloat16)
+            self._works.append((dist.all_reduce(wire, op=dist.ReduceOp.SUM, group=self.group, async_op=True), chunk, wire))
+        else:
+            self._works.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True), None, None))
         self._sent = end_offset
 
     def _on_done(self, plan):
         if self._enabled and self.world > 1:
             if self._sent < plan.grad_total:
                 self._launch(plan, plan.grad_total)
-            for w in self._works:
+            for w, chunk, wire in self._works:
                 w.wait()          # current stream waits for NCCL; the host does not block
+                if wire is not None:
+                    chunk.copy_(wire)
         self._works = []
         self._sent = 0
         self._plan_generation = None

@@ -164,13 +164,25 @@ class GraphedAccumulation:
             self.accum.zero_()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
+        # The micro graph must NOT contain the weight (re)pack -- parameters change only in the step graph -- and the step
+        # graph must END with it: the warm-up above has just packed (so the capture below finds nothing to do), and the
+        # plan the capture runs on is identified by its generation counter.
+        eng = model._engine
+        plans = [pl for pool in eng.plans.values() for pl in pool]
+        before = [pl.generation for pl in plans]
         self.micro_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.micro_graph):
             self.loss = self._micro()
+        used = [pl for pl, g0 in zip(plans, before) if pl.generation != g0]
+        if len(used) != 1:
+            raise RuntimeError("could not identify the launch plan of the captured micro-batch step")
+        self.plan = used[0]
         self.step_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.step_graph, pool=self.micro_graph.pool()):
             optimizer.step()
             self.accum.zero_()
+            self.plan._pack_versions = None
+            self.plan.pack_weights()                      # operand packs of the updated parameters, once per optimizer step
         self.accum.zero_()
         torch.cuda.synchronize(dev)
         self._engine = getattr(model, "_engine", None)
@@ -184,6 +196,13 @@ class GraphedAccumulation:
     def unlink(self):
         for p in self.params:
             p.grad = None
+
+    def sync_packs(self):
+        """After an EAGER optimizer step (the first accumulation group of an epoch, a ragged last batch): the micro graph
+        carries no weight pack, so the captured plan's operand packs are refreshed here."""
+        with torch.cuda.device(self.params[0].device):
+            self.plan._pack_versions = None
+            self.plan.pack_weights()
 
     def _micro(self):
         pred = self.model(self.x)
@@ -212,4 +231,5 @@ class GraphedAccumulation:
         if eng is not None:
             for pool in eng.plans.values():
                 for plan in pool:
-                    plan._pack_versions = None
+                    if plan is not self.plan:             # the captured plan was re-packed by the step graph itself
+                        plan._pack_versions = None

@@ -163,6 +163,7 @@ def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device
                 graph_ok = graphed is not None
                 if graphed is not None and accum:
                     graphed.link()
+                    graphed.sync_packs()                  # the eager optimizer step just before changed the parameters
             use_graph = graphed is not None and tuple(X.shape) == tuple(graphed.x.shape)
             if use_graph and not accum:
                 loss = graphed(X, y)                     # optimizer.step() and zero_grad() are part of the graph
@@ -188,6 +189,8 @@ def train_loop(dataloader, model, loss_fn, optimizer, accumulation_steps, device
                         scheduler.step()
                     # with a live accumulation graph p.grad are views of its accumulator: zero them in place
                     optimizer.zero_grad(set_to_none=not (graphed is not None and accum))
+                    if graphed is not None and accum:
+                        graphed.sync_packs()
             if step_now:
                 if reader is not None:
                     reader.push(loss)

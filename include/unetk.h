@@ -60,6 +60,10 @@ extern "C" {
 #define UNETK_TC_NO_HALO_N256 (1 << 11)  /* halo reuse only for N tiles <= 128 */
 #define UNETK_TC_NO_HALO_PAIR (1 << 12)  /* halo kernel without CTA pairs */
 #define UNETK_TC_NO_WGRAD_C64 (1 << 13)  /* generic 3-tap weight-gradient kernel for 64-channel gradients */
+/* unetk_wgrad only: run-to-run reproducible weight gradients.  The pixel reduction is split over CTAs; by default the
+ * splits meet in dw through fp32 atomics (order varies run to run).  With this flag every split STORES its partial result
+ * to the caller's `partial` buffer and a second kernel adds the splits in index order. */
+#define UNETK_TC_DETERMINISTIC (1 << 14)
 
 typedef struct unetk_tensor {
   void* ptr;
@@ -181,8 +185,13 @@ typedef struct unetk_wgrad_args {
   float* dw;
   int32_t mode;
   int32_t algo;
+  float* partial;        /* UNETK_TC_DETERMINISTIC: scratch of unetk_wgrad_partial_bytes(a) bytes (else NULL) */
+  int64_t partial_bytes; /* size of `partial` */
 } unetk_wgrad_args;
 UNETK_API int unetk_wgrad(const unetk_wgrad_args* a, void* stream);
+/* Bytes of `partial` scratch unetk_wgrad needs for this problem under UNETK_TC_DETERMINISTIC (0: none -- one split, or the
+ * CUDA-core tier); depends on the device's SM count.  Negative on bad arguments. */
+UNETK_API int64_t unetk_wgrad_partial_bytes(const unetk_wgrad_args* a);
 
 /* per-channel sum over all pixels: out[c] += sum_p t[p, c]  (bias gradients of ConvTranspose2d) */
 UNETK_API int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream);

@@ -55,7 +55,7 @@ def test_struct_sizes_match_header():
     # POD structs are mirrored by hand in _lib.py: guard against drift with the sizes nvcc/gcc would produce
     assert ctypes.sizeof(L.Tensor) == 32
     assert ctypes.sizeof(L.ConvArgs) == 32 + 8 + 32 + 8 + 24 + 32 + 5 * 8
-    assert ctypes.sizeof(L.WgradArgs) == 32 + 32 + 8 + 8
+    assert ctypes.sizeof(L.WgradArgs) == 32 + 32 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(L.BnBwdArgs) == 3 * 32 + 5 * 8 + 32 + 24
     assert ctypes.sizeof(L.BnFinalizeArgs) == 8 * 2 + 8 + 4 + 4 + 6 * 8 + 8 + 4 * 8
     assert ctypes.sizeof(L.DiceCeArgs) == 8 * 2 + 16 + 8 + 8 + 8 + 16 + 8 * 6 + 8

