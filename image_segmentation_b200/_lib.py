@@ -130,6 +130,7 @@ def lib():
             "unetk_conv": [P(ConvArgs), vp],
             "unetk_wgrad": [P(WgradArgs), vp],
             "unetk_channel_sum": [P(Tensor), vp, vp],
+            "unetk_channel_sum_ordered": [P(Tensor), vp, vp, C.c_int64, vp],
             "unetk_bn_stats": [P(Tensor), vp, vp, vp],
             "unetk_bn_finalize": [P(BnFinalizeArgs), vp],
             "unetk_bn_relu_apply": [P(Tensor), vp, vp, P(Tensor), P(Tensor), vp, vp],
@@ -165,7 +166,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "unetk_version", "unetk_last_error", "unetk_device_query", "unetk_query_workspace", "unetk_struct_size", "unetk_im2col3x3_first", "unetk_permute3",
     "unetk_weights_pack", "unetk_weights_unpack",
-    "unetk_conv", "unetk_wgrad", "unetk_wgrad_partial_bytes", "unetk_channel_sum", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
+    "unetk_conv", "unetk_wgrad", "unetk_wgrad_partial_bytes", "unetk_channel_sum", "unetk_channel_sum_ordered", "unetk_bn_stats", "unetk_bn_finalize", "unetk_bn_relu_apply",
     "unetk_bn_relu_bwd_reduce", "unetk_bn_relu_bwd_apply", "unetk_head_fprop", "unetk_head_bwd",
     "unetk_dice_ce_fwd", "unetk_dice_ce_bwd", "unetk_argmax_confusion", "unetk_crop_resize", "unetk_eval_loss_metrics",
     "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply", "unetk_bn_relu_head_fprop",
@@ -368,9 +369,17 @@ def wgrad(u, s, dw, mode, algo=ALGO_AUTO, algo_flops=None, partial=None):
     prep_wgrad(u, s, dw, mode, algo, algo_flops, partial=partial)(stream_ptr())
 
 
-def prep_channel_sum(t, out=None, label=None) -> Call:
-    """out=None: the destination pointer is patched per call (``call.patch_ptr(...)`` is done by the caller)."""
+CHANNEL_SUM_BLOCKS = 512      # include/unetk.h UNETK_CHANNEL_SUM_BLOCKS
+
+
+def prep_channel_sum(t, out=None, label=None, scratch=None) -> Call:
+    """out=None: the destination pointer is patched per call (argument index 1).  scratch (float32, at least
+    CHANNEL_SUM_BLOCKS * C elements): ordered, run-to-run reproducible summation."""
     tt = nhwc(t)
+    if scratch is not None:
+        return Call("reduce", 2, 0, lib().unetk_channel_sum_ordered,
+                    (C.byref(tt), ptr(out), scratch.data_ptr(), scratch.numel() * scratch.element_size()),
+                    keep=(tt, t, out, scratch), label=label)
     return Call("reduce", 1, 0, lib().unetk_channel_sum, (C.byref(tt), ptr(out)), keep=(tt, t, out), label=label)
 
 

@@ -8,7 +8,8 @@ namespace unetk {
 
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ t, int64_t npix, int ld, int c,
-                                                          int pix_per_block, float* __restrict__ out) {
+                                                          int pix_per_block, float* __restrict__ out,
+                                                          float* __restrict__ partial) {
   // block = 256/cgb pixel rows x cgb channel groups (8 channels each)
   extern __shared__ float red[];
   const int cg = c / 8;
@@ -32,8 +33,20 @@ __global__ void __launch_bounds__(256) channel_sum_kernel(const T* __restrict__ 
   for (int ch = threadIdx.x; ch < width; ch += blockDim.x) {
     float s = 0.f;
     for (int r = 0; r < rows; ++r) s += red[r * width + ch];
-    atomicAdd(out + (size_t)blockIdx.x * width + ch, s);
+    if (partial)      // ordered mode: block partials are stored and summed in index order by channel_sum_finish_kernel
+      partial[(size_t)blockIdx.y * c + (size_t)blockIdx.x * width + ch] = s;
+    else
+      atomicAdd(out + (size_t)blockIdx.x * width + ch, s);
   }
+}
+
+__global__ void __launch_bounds__(256) channel_sum_finish_kernel(const float* __restrict__ partial, int nblocks, int c,
+                                                                 float* __restrict__ out) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * c + ch];
+  out[ch] += s;
 }
 
 }  // namespace unetk
@@ -136,7 +149,16 @@ int64_t unetk_wgrad_partial_bytes(const unetk_wgrad_args* a) {
   return tc_wgrad_partial_bytes(a, a->mode == 0 ? 1 : (a->mode == 1 ? 9 : 4));
 }
 
-int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream) {
+static int channel_sum_impl(const unetk_tensor* t, float* out, float* scratch, int64_t scratch_bytes, void* stream);
+
+int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream) { return channel_sum_impl(t, out, nullptr, 0, stream); }
+
+int unetk_channel_sum_ordered(const unetk_tensor* t, float* out, float* scratch, int64_t scratch_bytes, void* stream) {
+  UNETK_REQUIRE(scratch != nullptr, "channel_sum_ordered: scratch buffer missing");
+  return channel_sum_impl(t, out, scratch, scratch_bytes, stream);
+}
+
+static int channel_sum_impl(const unetk_tensor* t, float* out, float* scratch, int64_t scratch_bytes, void* stream) {
   UNETK_REQUIRE(t && out, "channel_sum: null argument");
   UNETK_REQUIRE(tensor_ok(*t) && vec8_ok(*t), "channel_sum: t must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
   const int cg = t->c / 8;
@@ -146,13 +168,23 @@ int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream) {
   const int64_t npix = pixels(*t);
   int ppb = rows * 32;
   if ((npix + ppb - 1) / ppb > 65535) ppb *= 16;
+  if (scratch) {
+    // ordered mode: at most UNETK_CHANNEL_SUM_BLOCKS block rows, whose partial sums fit the caller's scratch
+    while ((npix + ppb - 1) / ppb > UNETK_CHANNEL_SUM_BLOCKS) ppb *= 2;
+    UNETK_REQUIRE(scratch_bytes >= (int64_t)UNETK_CHANNEL_SUM_BLOCKS * t->c * (int64_t)sizeof(float),
+                  "channel_sum_ordered: scratch must hold UNETK_CHANNEL_SUM_BLOCKS * C floats");
+  }
   UNETK_REQUIRE((npix + ppb - 1) / ppb <= 65535, "channel_sum: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((npix + ppb - 1) / ppb));
   const size_t smem = (size_t)rows * cgb * 8 * sizeof(float);
   UNETK_DISPATCH_DTYPE(t->dtype, T, {
-    channel_sum_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)t->ptr, npix, t->ld, t->c, ppb, out);
+    channel_sum_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>((const T*)t->ptr, npix, t->ld, t->c, ppb, out, scratch);
   });
   UNETK_LAUNCH_CHECK();
+  if (scratch) {
+    channel_sum_finish_kernel<<<(t->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, (int)grid.y, t->c, out);
+    UNETK_LAUNCH_CHECK();
+  }
   return UNETK_OK;
 }
 }

@@ -284,7 +284,7 @@ class Conv1x1(Node):
             call.patch_ptr(call.keep[0], "dw", plan._goff(w))
             ops.append(call)
         if b is not None and b.requires_grad:
-            ops.append(_PatchedArg(L.prep_channel_sum(dy, None, label=self.name), 1, plan._goff(b)))
+            ops.append(_PatchedArg(plan.channel_sum_call(dy, self.name), 1, plan._goff(b)))
         return len([p for p in self.params() if p.requires_grad])
 
 
@@ -747,6 +747,15 @@ class NetPlan:
             self._det_sites.append((call.keep[0], L.wgrad_partial_bytes(u, s, mode, self.algo)))
         return call
 
+    def channel_sum_call(self, t, label) -> L.Call:
+        """Prepared per-channel sum (bias gradients) whose destination is patched per backward pass (argument 1)."""
+        scratch = None
+        if self.deterministic:
+            if getattr(self, "_csum_scratch", None) is None or self._csum_scratch.numel() < L.CHANNEL_SUM_BLOCKS * t.shape[3]:
+                self._csum_scratch = torch.empty(L.CHANNEL_SUM_BLOCKS * max(t.shape[3], 1024), dtype=torch.float32, device=self.device)
+            scratch = self._csum_scratch
+        return L.prep_channel_sum(t, None, label=label, scratch=scratch)
+
     def _attach_partial_scratch(self):
         need = max([n for _, n in self._det_sites], default=0)
         if need == 0:
@@ -874,8 +883,7 @@ class NetPlan:
                     ops.append(self.wgrad_call(ct.src.t, g_out, ct.ws, 2, label=ct.name))
                     jobs_pending.append((ct.ws.data_ptr(), self._goff(ct.mod.weight), None, 1, ct.cout, ct.cin, 0))
                 if ct.mod.bias is not None and ct.mod.bias.requires_grad:
-                    cs = L.prep_channel_sum(g_out, None, label=ct.name)
-                    ops.append(_PatchedArg(cs, 1, self._goff(ct.mod.bias)))
+                    ops.append(_PatchedArg(self.channel_sum_call(g_out, ct.name), 1, self._goff(ct.mod.bias)))
                 done_params += len([p for p in ct.params() if p.requires_grad])
             else:
                 done_params += nd.backward_calls(self, ops, jobs_pending)

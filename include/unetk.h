@@ -195,6 +195,10 @@ UNETK_API int64_t unetk_wgrad_partial_bytes(const unetk_wgrad_args* a);
 
 /* per-channel sum over all pixels: out[c] += sum_p t[p, c]  (bias gradients of ConvTranspose2d) */
 UNETK_API int unetk_channel_sum(const unetk_tensor* t, float* out, void* stream);
+/* The same with a run-to-run reproducible result: block partial sums go to `scratch` (at least
+ * UNETK_CHANNEL_SUM_BLOCKS * C floats) and are added in index order instead of with fp32 atomics. */
+#define UNETK_CHANNEL_SUM_BLOCKS 512
+UNETK_API int unetk_channel_sum_ordered(const unetk_tensor* t, float* out, float* scratch, int64_t scratch_bytes, void* stream);
 
 /* ---- BatchNorm + ReLU + MaxPool (unet/unet.py:17-18,20-21,40) ------------------------------- */
 UNETK_API int unetk_bn_stats(const unetk_tensor* z, double* sum, double* sumsq, void* stream);
