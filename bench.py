@@ -209,7 +209,10 @@ def run_gpu_arm(args):
     model = model.to(dev).train()
     # UNETK_DP_BUCKET_MB / UNETK_DP_COMPRESS: scaling experiments (defaults: 25 MB buckets, fp32 gradients on the wire)
     dp_kw = dict(bucket_mb=float(os.environ.get("UNETK_DP_BUCKET_MB", "25")), compress=os.environ.get("UNETK_DP_COMPRESS") or None)
-    dp = DataParallelUNet(model, **dp_kw) if world > 1 else None
+    # UNETK_DP_DISABLE=1: N independent replicas (no gradient exchange) -- isolates the straggler / shared-power effect of
+    # running N GPUs of one box at once from the cost of the all-reduce
+    dp_off = os.environ.get("UNETK_DP_DISABLE", "0") == "1"
+    dp = DataParallelUNet(model, **dp_kw) if (world > 1 and not dp_off) else None
     # same update rule as the reference's AdamW; fused = one kernel, capturable = usable inside a CUDA graph
     opt = torch.optim.AdamW(model.parameters(), weight_decay=0.01, fused=True, capturable=True)
     loss_fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor(CLASS_W3))
@@ -257,6 +260,7 @@ def run_gpu_arm(args):
         return out
 
     graphed = None
+    rank_ms = []          # per-rank ms/step of the last timed() call (world > 1)
 
     def barrier():
         if world > 1:
@@ -273,9 +277,10 @@ def run_gpu_arm(args):
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+            allms = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(allms, torch.tensor([ms], device=dev))
+            rank_ms[:] = [float(t.item()) / max(steps, 1) for t in allms]
+            ms = max(float(t.item()) for t in allms)
         return ms
 
     for _ in range(max(args.warmup, 3)):
@@ -305,6 +310,7 @@ def run_gpu_arm(args):
         ms = timed(step_resident, args.steps)
         launches = L.COUNTERS["launches"]
     clocks = sampler.stop() if rank == 0 else None
+    rank_ms_value = list(rank_ms)
     ms_per_step = ms / args.steps
     value = world * B * args.steps / (ms / 1e3)
 
@@ -403,7 +409,8 @@ def run_gpu_arm(args):
             "config": {"workload": f"unet(3,3) 256x256 training step, batch {B}/GPU, bf16 activations + fp32 master weights, "
                                    "WeightedDiceCELoss + AdamW + MetricsHistory",
                        "global_batch": B * world, "parallelism": f"dp{world}",
-                       **({"dp": dp_kw} if world > 1 else {}),
+                       **({"dp": dict(dp_kw, exchange="none (independent replicas)" if dp_off else "bucketed NCCL all-reduce"),
+                           "rank_ms_per_step": [round(v, 3) for v in rank_ms_value]} if world > 1 else {}),
                        "launch": "one CUDA graph per step" if graphed is not None else "eager launches",
                        "e2e_path": "pinned host batch -> DevicePrefetcher (copy of batch i+1 overlaps step i) -> "
                                    + ("GraphedTrainStep" if graphed is not None else "eager step")

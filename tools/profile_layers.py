@@ -16,21 +16,32 @@ from image_segmentation_b200.utils.weighted_loss import WeightedDiceCELoss  # no
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--workload", default="unet", help="unet | autoencoder_recon | autoencoder_seg | clip | prompt (bench.py workloads)")
 args = ap.parse_args()
 dev = torch.device("cuda")
 torch.manual_seed(0)
-m = unet(3, 3).to(dev).train()
-opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
-fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor([0.2, 1.0, 1.2]))
-x, y = make_batch(args.batch, 256, 256, 3, 3)
-x, y = x.to(dev), y.squeeze(1).to(dev)
+if args.workload == "unet":
+    m = unet(3, 3).to(dev).train()
+    opt = torch.optim.AdamW(m.parameters(), weight_decay=0.01)
+    fn = WeightedDiceCELoss(smooth_dice=1, class_weights=torch.tensor([0.2, 1.0, 1.2]))
+    x, y = make_batch(args.batch, 256, 256, 3, 3)
+    x, y = x.to(dev), y.squeeze(1).to(dev)
 
+    def step():
+        loss = fn(m(x), y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+else:
+    import bench
+    m, inputs, fwd, _ = bench.build_family(args.workload, args.batch, dev)
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], weight_decay=0.01)
 
-def step():
-    loss = fn(m(x), y)
-    loss.backward()
-    opt.step()
-    opt.zero_grad()
+    def step():
+        loss = fwd(m, *inputs)
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
 
 
 for _ in range(3):
