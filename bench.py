@@ -208,7 +208,8 @@ def run_gpu_arm(args):
     model.precision = "bf16"
     model = model.to(dev).train()
     # UNETK_DP_BUCKET_MB / UNETK_DP_COMPRESS: scaling experiments (defaults: 25 MB buckets, fp32 gradients on the wire)
-    dp_kw = dict(bucket_mb=float(os.environ.get("UNETK_DP_BUCKET_MB", "25")), compress=os.environ.get("UNETK_DP_COMPRESS") or None)
+    dp_kw = dict(bucket_mb=float(os.environ.get("UNETK_DP_BUCKET_MB", "25")), compress=os.environ.get("UNETK_DP_COMPRESS") or None,
+                 exchange=os.environ.get("UNETK_DP_EXCHANGE", "auto"))
     # UNETK_DP_DISABLE=1: N independent replicas (no gradient exchange) -- isolates the straggler / shared-power effect of
     # running N GPUs of one box at once from the cost of the all-reduce
     dp_off = os.environ.get("UNETK_DP_DISABLE", "0") == "1"
@@ -409,7 +410,9 @@ def run_gpu_arm(args):
             "config": {"workload": f"unet(3,3) 256x256 training step, batch {B}/GPU, bf16 activations + fp32 master weights, "
                                    "WeightedDiceCELoss + AdamW + MetricsHistory",
                        "global_batch": B * world, "parallelism": f"dp{world}",
-                       **({"dp": dict(dp_kw, exchange="none (independent replicas)" if dp_off else "bucketed NCCL all-reduce"),
+                       **({"dp": dict(dp_kw, exchange="none (independent replicas)" if dp_off else
+                                      ("NVLS multicast all-reduce kernel (unetk_nvls_allreduce_f32)" if (dp is not None and dp._nvls)
+                                       else "bucketed NCCL all-reduce")),
                            "rank_ms_per_step": [round(v, 3) for v in rank_ms_value]} if world > 1 else {}),
                        "launch": "one CUDA graph per step" if graphed is not None else "eager launches",
                        "e2e_path": "pinned host batch -> DevicePrefetcher (copy of batch i+1 overlaps step i) -> "

@@ -152,6 +152,7 @@ def lib():
             "unetk_bilinear_up_bwd": [P(Tensor), P(Tensor), vp],
             "unetk_prompt_compose_fwd": [vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp],
             "unetk_prompt_compose_bwd": [vp, vp, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp],
+            "unetk_nvls_allreduce_f32": [vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, vp],
             "unetk_nchw_to_nhwc": [vp, P(Tensor), vp],
             "unetk_nhwc_to_nchw": [P(Tensor), vp, vp],
         }
@@ -172,6 +173,7 @@ EXPORTED_SYMBOLS = (
     "unetk_head_bn_bwd_reduce", "unetk_head_bn_bwd_apply", "unetk_bn_relu_head_fprop",
     "unetk_bias_sigmoid_fwd", "unetk_bias_sigmoid_bwd", "unetk_bilinear_up_fwd", "unetk_bilinear_up_bwd",
     "unetk_prompt_compose_fwd", "unetk_prompt_compose_bwd", "unetk_nchw_to_nhwc", "unetk_nhwc_to_nchw",
+    "unetk_nvls_allreduce_f32",
 )
 
 
@@ -532,6 +534,11 @@ def prompt_compose_bwd(clip_logits, mask_logits, dfinal, dmask):
     n, _, h, w = clip_logits.shape
     _run("prompt", 1, 0, lib().unetk_prompt_compose_bwd, clip_logits.data_ptr(), mask_logits.data_ptr(), dfinal.data_ptr(), n, h, w,
          dmask.data_ptr(), stream_ptr())
+
+
+def nvls_allreduce(multicast_ptr: int, n_elems: int, rank: int, world: int, scale: float = 1.0):
+    """Two-shot NVLS all-reduce of a symmetric fp32 buffer (the caller brackets it with cross-rank barriers)."""
+    _run("allreduce", 1, 0, lib().unetk_nvls_allreduce_f32, multicast_ptr, n_elems, rank, world, scale, stream_ptr())
 
 
 def prep_nchw_to_nhwc(src, dst, label=None) -> Call:

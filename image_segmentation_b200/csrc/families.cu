@@ -86,39 +86,44 @@ __device__ __forceinline__ Lerp lerp_of(int dst, float scale, int in_size) {
   return r;
 }
 
+// forward: one block per destination row (img, y) -- no 64-bit index arithmetic in the inner loop, the row's vertical taps
+// are computed once; threads walk the row's (x, 8-channel group) items with consecutive threads on consecutive 16 bytes
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_up_fwd_kernel(const T* __restrict__ src, int sld, int n, int ih, int iw, int c,
                                                               T* __restrict__ dst, int dld, int oh, int ow, float sh, float sw) {
-  const int cg = c / 8;
-  const int64_t total = (int64_t)n * oh * ow * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    const int64_t p = i / cg;
-    const int x = (int)(p % ow), y = (int)((p / ow) % oh);
-    const int64_t img = p / ((int64_t)ow * oh);
-    const Lerp ly = lerp_of(y, sh, ih), lx = lerp_of(x, sw, iw);
-    const T* base = src + img * ih * iw * (int64_t)sld + g * 8;
+  const uint32_t cg = (uint32_t)c / 8;
+  const uint32_t row = blockIdx.x;                       // img * oh + y
+  const uint32_t y = row % (uint32_t)oh, img = row / (uint32_t)oh;
+  const Lerp ly = lerp_of((int)y, sh, ih);
+  const T* base0 = src + ((int64_t)img * ih + ly.i0) * iw * (int64_t)sld;
+  const T* base1 = src + ((int64_t)img * ih + ly.i1) * iw * (int64_t)sld;
+  T* drow = dst + (int64_t)row * ow * (int64_t)dld;
+  const uint32_t items = (uint32_t)ow * cg;
+  for (uint32_t i = threadIdx.x; i < items; i += blockDim.x) {
+    const uint32_t x = i / cg, g = i - x * cg;
+    const Lerp lx = lerp_of((int)x, sw, iw);
     float a[8], b[8], cc[8], d[8], o[8];
-    load8(base + ((int64_t)ly.i0 * iw + lx.i0) * sld, a);
-    load8(base + ((int64_t)ly.i0 * iw + lx.i1) * sld, b);
-    load8(base + ((int64_t)ly.i1 * iw + lx.i0) * sld, cc);
-    load8(base + ((int64_t)ly.i1 * iw + lx.i1) * sld, d);
+    load8(base0 + (int64_t)lx.i0 * sld + g * 8, a);
+    load8(base0 + (int64_t)lx.i1 * sld + g * 8, b);
+    load8(base1 + (int64_t)lx.i0 * sld + g * 8, cc);
+    load8(base1 + (int64_t)lx.i1 * sld + g * 8, d);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = ly.l0 * (lx.l0 * a[k] + lx.l1 * b[k]) + ly.l1 * (lx.l0 * cc[k] + lx.l1 * d[k]);
-    store8(dst + p * dld + g * 8, o);
+    store8(drow + (int64_t)x * dld + g * 8, o);
   }
 }
 
 // gather form of the transpose (no atomics): a warp owns one source pixel and `cgl` = min(C/8, 32) consecutive 8-channel
-// groups; its 32 / cgl lane rows walk the destination window whose interpolation footprint contains that source pixel
-// ((2/scale + 2)^2 positions: 34 x 34 for the 16x up-sampling of the last decoder block, where C/8 = 8 and four lane rows
-// share the walk) and are summed with shuffles.  Lanes of one row read consecutive 16-byte pieces of one pixel.
+// groups; its 32 / cgl lane rows share the walk over the destination window whose interpolation footprint contains that
+// source pixel ((2/scale + 2)^2 positions: 34 x 34 for the 16x up-sampling of the last decoder block, where C/8 = 8 and
+// four lane rows split every window row) and are summed with shuffles.  Lanes of one lane row read consecutive 16-byte
+// pieces of one pixel; the vertical weight is evaluated once per window row.
 template <typename T>
 __global__ void __launch_bounds__(256) bilinear_up_bwd_kernel(const T* __restrict__ dd, int dld, int n, int oh, int ow, int c,
                                                               T* __restrict__ ds, int sld, int ih, int iw, float sh, float sw,
                                                               int cgl) {
   const int cg = c / 8;
-  const int chunks = cg / cgl;                       // cgl divides cg (both powers-of-two multiples; checked by the host)
+  const int chunks = cg / cgl;                       // cgl: largest power of two <= 32 dividing cg
   const int rows = 32 / cgl;                         // lane rows sharing the window walk
   const int lane = threadIdx.x & 31;
   const int gl = lane % cgl, pr = lane / cgl;
@@ -139,20 +144,22 @@ __global__ void __launch_bounds__(256) bilinear_up_bwd_kernel(const T* __restric
     y1 = y1 > oh - 1 ? oh - 1 : y1; x1 = x1 > ow - 1 ? ow - 1 : x1;
     if (sy == 0) y0 = 0;                              // negative source coordinates clamp to row / column 0
     if (sx == 0) x0 = 0;
-    const int nx = x1 - x0 + 1, cnt = (y1 - y0 + 1) * nx;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const T* base = dd + img * oh * ow * (int64_t)dld + g * 8;
-    for (int q = pr; q < cnt; q += rows) {
-      const int y = y0 + q / nx, x = x0 + q % nx;
-      const Lerp ly = lerp_of(y, sh, ih), lx = lerp_of(x, sw, iw);
+    for (int y = y0; y <= y1; ++y) {
+      const Lerp ly = lerp_of(y, sh, ih);
       const float wy = (ly.i0 == sy ? ly.l0 : 0.f) + (ly.i1 == sy ? ly.l1 : 0.f);
-      const float wx = (lx.i0 == sx ? lx.l0 : 0.f) + (lx.i1 == sx ? lx.l1 : 0.f);
-      const float wgt = wy * wx;
-      if (wgt != 0.f) {
-        float v[8];
-        load8(base + ((int64_t)y * ow + x) * dld, v);
+      if (wy == 0.f) continue;                        // warp-uniform
+      const T* rowp = base + (int64_t)y * ow * dld;
+      for (int x = x0 + pr; x <= x1; x += rows) {
+        const Lerp lx = lerp_of(x, sw, iw);
+        const float wgt = wy * ((lx.i0 == sx ? lx.l0 : 0.f) + (lx.i1 == sx ? lx.l1 : 0.f));
+        if (wgt != 0.f) {
+          float v[8];
+          load8(rowp + (int64_t)x * dld, v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wgt, v[k], acc[k]);
+        }
       }
     }
     for (int o = cgl; o < 32; o <<= 1) {
@@ -306,9 +313,10 @@ int unetk_bilinear_up_fwd(const unetk_tensor* src, const unetk_tensor* dst, void
   int rc = check_bilinear(src, dst, "bilinear_up_fwd");
   if (rc) return rc;
   const float sh = (float)src->h / (float)dst->h, sw = (float)src->w / (float)dst->w;
-  const int64_t items = pixels(*dst) * (dst->c / 8);
+  const int64_t rows = (int64_t)dst->n * dst->h;
+  UNETK_REQUIRE(rows < (1LL << 31) && (int64_t)dst->w * (dst->c / 8) < (1LL << 31), "bilinear_up_fwd: tensor too large");
   UNETK_DISPATCH_DTYPE(src->dtype, T, {
-    bilinear_up_fwd_kernel<T><<<grid_1d(items, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+    bilinear_up_fwd_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(
         (const T*)src->ptr, src->ld, src->n, src->h, src->w, src->c, (T*)dst->ptr, dst->ld, dst->h, dst->w, sh, sw);
   });
   UNETK_LAUNCH_CHECK();

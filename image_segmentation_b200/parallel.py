@@ -27,8 +27,13 @@ class DataParallelUNet:
     """Attach bucketed gradient all-reduce to a ``unet`` instance (not a wrapper: the model object,
     its ``state_dict`` and the train loop stay exactly what they were)."""
 
-    def __init__(self, model, process_group=None, bucket_mb: float = 25.0, broadcast_from: int = 0, compress=None):
-        """``bucket_mb``: minimum size of an all-reduce (a huge value = ONE all-reduce after the last gradient).
+    def __init__(self, model, process_group=None, bucket_mb: float = 25.0, broadcast_from: int = 0, compress=None,
+                 exchange: str = "auto"):
+        """``exchange``: "nccl" = bucketed ``ncclAllReduce`` (any backend torch.distributed offers, also gloo in the CPU
+        tests); "nvls" = this package's two-shot multicast kernel (``unetk_nvls_allreduce_f32``: the gradients sit in
+        symmetric memory and the NVSwitch reduces them, one launch after the last gradient); "auto" = nvls when the
+        process group's devices support multicast, else nccl.
+        ``bucket_mb``: minimum size of an all-reduce (a huge value = ONE all-reduce after the last gradient).
         ``compress="bf16"`` (opt-in, changes numerics): gradients travel as bf16 (half the bytes; the sum over ranks is
         formed in bf16 by NCCL) and are widened back to fp32 afterwards -- stock DDP's bf16 compression hook."""
         if not (dist.is_available() and dist.is_initialized()):
@@ -40,6 +45,10 @@ class DataParallelUNet:
         if compress not in (None, "bf16"):
             raise ValueError("compress must be None or 'bf16'")
         self.compress = compress
+        if exchange not in ("auto", "nccl", "nvls"):
+            raise ValueError("exchange must be 'auto', 'nccl' or 'nvls'")
+        self.exchange = exchange
+        self._nvls = None            # (symmetric buffer, handle) once set up; False when unavailable
         self._works: List = []
         self._sent = 0
         self._enabled = True
@@ -51,9 +60,56 @@ class DataParallelUNet:
                 dist.broadcast(t.data, src=broadcast_from, group=process_group)
 
     # engine callbacks ----------------------------------------------------------------------------
+    # NVLS path ---------------------------------------------------------------------------------
+    def _setup_nvls(self, plan):
+        """Symmetric gradient buffer + multicast binding; collective (every rank gets here in its first backward pass).
+        Any failure (no multicast support, no symmetric-memory backend) falls back to NCCL for 'auto' and raises for 'nvls'."""
+        try:
+            if self.compress is not None or not plan.flat_grad.is_cuda:
+                raise RuntimeError("NVLS exchange needs CUDA tensors and fp32 gradients on the wire")
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            n = ((plan.grad_total + 3) // 4) * 4
+            buf = symm_mem.empty(n, dtype=torch.float32, device=plan.flat_grad.device)
+            hdl = symm_mem.rendezvous(buf, group)
+            ok = bool(getattr(hdl, "has_multicast_support", False)) and int(hdl.multicast_ptr) != 0
+            flag = torch.tensor([1 if ok else 0], device=buf.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)       # all ranks take the same path
+            if int(flag.item()) != 1:
+                raise RuntimeError("the devices of this process group do not support NVLink multicast")
+            buf.zero_()
+            self._nvls = (buf, hdl, n)
+        except Exception as e:
+            if self.exchange == "nvls":
+                raise RuntimeError(f"exchange='nvls' is not available here: {e}") from e
+            self._nvls = False
+
+    def _nvls_allreduce(self, plan):
+        from . import _lib as L
+        buf, hdl, n = self._nvls
+        total = plan.grad_total
+        buf[:total].copy_(plan.flat_grad)
+        hdl.barrier(channel=0)                       # every rank's gradients are in its symmetric buffer
+        L.nvls_allreduce(int(hdl.multicast_ptr), n, hdl.rank, hdl.world_size, 1.0)
+        hdl.barrier(channel=1)                       # every slice has been stored on every rank
+        plan.flat_grad.copy_(buf[:total])
+
+    def _use_nvls(self, plan) -> bool:
+        if self.exchange == "nccl" or self.world == 1:
+            return False
+        if self._nvls is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("run one eager data-parallel step before capturing a CUDA graph (the symmetric gradient "
+                                   "buffer is set up in the first backward pass)")
+            self._setup_nvls(plan)
+        return bool(self._nvls)
+
     def _on_bucket(self, plan, end_offset: int):
         if not self._enabled or self.world == 1:
             return
+        if self.exchange != "nccl" and self._nvls is not False and plan.flat_grad.is_cuda:
+            if self._use_nvls(plan):
+                return                               # one multicast all-reduce after the last gradient (_on_done)
         if getattr(self, "_plan_generation", None) != (id(plan), getattr(plan, "generation", 0)):
             # first bucket of a new backward pass: a previous pass that raised midway must not leave stale offsets / works
             self._plan_generation = (id(plan), getattr(plan, "generation", 0))
@@ -72,6 +128,10 @@ class DataParallelUNet:
         self._sent = end_offset
 
     def _on_done(self, plan):
+        if self._enabled and self.world > 1 and self.exchange != "nccl" and plan.flat_grad.is_cuda and self._use_nvls(plan):
+            self._nvls_allreduce(plan)
+            self._works, self._sent, self._plan_generation = [], 0, None
+            return
         if self._enabled and self.world > 1:
             if self._sent < plan.grad_total:
                 self._launch(plan, plan.grad_total)

@@ -393,6 +393,15 @@ UNETK_API int unetk_prompt_compose_bwd(const float* clip_logits, const float* ma
 UNETK_API int unetk_nchw_to_nhwc(const float* src_nchw, const unetk_tensor* dst, void* stream);
 UNETK_API int unetk_nhwc_to_nchw(const unetk_tensor* src, float* dst_nchw, void* stream);
 
+/* ---- data-parallel exchange step ---------------------------------------------------------
+ * In-place sum all-reduce of a fp32 buffer that every rank holds in SYMMETRIC memory bound to one NVSwitch multicast
+ * object (NVLS): rank r reduces and re-broadcasts the r-th slice with multimem.ld_reduce / multimem.st; `scale` is applied
+ * to the sum (1/world for a mean).  `multicast_ptr` is the multicast address of the buffer (16-byte aligned, n_elems a
+ * multiple of 4).  The CALLER provides the cross-rank barriers: one before the launch (every rank's buffer is written and
+ * visible system-wide) and one after it (every slice has been stored on every rank).                                    */
+UNETK_API int unetk_nvls_allreduce_f32(void* multicast_ptr, int64_t n_elems, int32_t rank, int32_t world, float scale,
+                                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,7 @@ torch.manual_seed(0)
 model = unet(3, 3)
 model.precision = "fp32"
 model = model.to(dev).train()
-dp = DataParallelUNet(model, bucket_mb=8)
+dp = DataParallelUNet(model, bucket_mb=8, exchange=os.environ.get("UNETK_DP_EXCHANGE", "auto"))
 shards = [make_batch(2, 64, 64, 3, 3, seed=50 + r) for r in range(world)]
 # (1) identical shards on every rank
 g_dp = grads(model, *shards[0])
@@ -102,6 +102,6 @@ assert err < 5e-2                             # 4 steps of chaotic dynamics (ReL
 dist.barrier()
 torch.cuda.synchronize()
 if rank == 0:
-    print("dp_check OK")
+    print("dp_check OK; exchange:", "nvls kernel" if dp._nvls else "nccl")
 sys.stdout.flush()
 os._exit(0)      # no destroy_process_group() while a graph with captured collectives is alive (it hangs)
