@@ -395,6 +395,13 @@ def run_gpu_arm(args):
                 "step_frac": step_tflops / peaks["sustained"],
                 "step_frac_of_burst": step_tflops / peaks["burst"]}
 
+    if dp is not None and dp._trace is not None:
+        # UNETK_DP_TRACE=1: ten eager steps back to back with CUDA events around the pieces of the gradient exchange
+        dp._trace.clear()
+        for _ in range(10):
+            step_resident()
+        torch.cuda.synchronize()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b, times, threads, kind = cpu_reference_steps(steps=3, warmup=1)
@@ -413,7 +420,8 @@ def run_gpu_arm(args):
                        **({"dp": dict(dp_kw, exchange="none (independent replicas)" if dp_off else
                                       ("NVLS multicast all-reduce kernel (unetk_nvls_allreduce_f32)" if (dp is not None and dp._nvls)
                                        else "bucketed NCCL all-reduce")),
-                           "rank_ms_per_step": [round(v, 3) for v in rank_ms_value]} if world > 1 else {}),
+                           "rank_ms_per_step": [round(v, 3) for v in rank_ms_value],
+                           **({"exchange_trace_ms": dp.trace_summary()} if (dp is not None and dp._trace) else {})} if world > 1 else {}),
                        "launch": "one CUDA graph per step" if graphed is not None else "eager launches",
                        "e2e_path": "pinned host batch -> DevicePrefetcher (copy of batch i+1 overlaps step i) -> "
                                    + ("GraphedTrainStep" if graphed is not None else "eager step")

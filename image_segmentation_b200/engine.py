@@ -913,16 +913,19 @@ class NetPlan:
         self._dlogits_slot.copy_(dlogits)
         stream = L.stream_ptr()
         base = flat.data_ptr()
+        # block-by-block un-pack + hook only when a data-parallel exchange wants early buckets; otherwise ONE batched
+        # un-pack after the last weight gradient (the per-block launches are latency-bound, 2-3 blocks per SM each)
+        per_segment = bucket_hook is not None and getattr(self.model, "_bucket_per_segment", True)
         for op in self._bwd:
             if isinstance(op, tuple):
                 kind, seg, end = op
-                if bucket_hook is not None:
+                if per_segment:
                     if kind == "bucket" and self._unpack_jobs[seg] is not None:
                         L.weights_unpack(self._unpack_jobs[seg], flat)
                     bucket_hook(self, end)
                 continue
             op(stream, base)
-        if bucket_hook is None and self._unpack_all is not None:
+        if not per_segment and self._unpack_all is not None:
             L.weights_unpack(self._unpack_all, flat)
         # gradients of NCHW feature-map inputs (block-level API)
         self.input_grads = {}

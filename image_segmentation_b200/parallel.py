@@ -49,6 +49,8 @@ class DataParallelUNet:
             raise ValueError("exchange must be 'auto', 'nccl' or 'nvls'")
         self.exchange = exchange
         self._nvls = None            # (symmetric buffer, handle) once set up; False when unavailable
+        import os
+        self._trace = [] if os.environ.get("UNETK_DP_TRACE", "0") == "1" else None
         self._works: List = []
         self._sent = 0
         self._enabled = True
@@ -79,6 +81,8 @@ class DataParallelUNet:
                 raise RuntimeError("the devices of this process group do not support NVLink multicast")
             buf.zero_()
             self._nvls = (buf, hdl, n)
+            # one exchange after the last gradient: the engine need not un-pack weight gradients block by block
+            self.model._bucket_per_segment = False
         except Exception as e:
             if self.exchange == "nvls":
                 raise RuntimeError(f"exchange='nvls' is not available here: {e}") from e
@@ -88,11 +92,35 @@ class DataParallelUNet:
         from . import _lib as L
         buf, hdl, n = self._nvls
         total = plan.grad_total
+        trace = self._trace is not None and not torch.cuda.is_current_stream_capturing()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)] if trace else None
+
+        def mark(i):
+            if trace:
+                ev[i].record()
+        mark(0)
         buf[:total].copy_(plan.flat_grad)
+        mark(1)
         hdl.barrier(channel=0)                       # every rank's gradients are in its symmetric buffer
+        mark(2)
         L.nvls_allreduce(int(hdl.multicast_ptr), n, hdl.rank, hdl.world_size, 1.0)
+        mark(3)
         hdl.barrier(channel=1)                       # every slice has been stored on every rank
+        mark(4)
         plan.flat_grad.copy_(buf[:total])
+        mark(5)
+        if trace:
+            self._trace.append(ev)
+
+    def trace_summary(self):
+        """Mean milliseconds of the pieces of the NVLS exchange over the traced (eager) steps: copy-in, barrier 0 (= how
+        long this rank waits for the slowest one), multicast kernel, barrier 1, copy-out.  UNETK_DP_TRACE=1."""
+        if not self._trace:
+            return None
+        torch.cuda.synchronize()
+        names = ("copy_in", "wait_for_slowest_rank", "nvls_kernel", "barrier_after", "copy_out")
+        rows = self._trace[len(self._trace) // 2:]          # skip warm-up
+        return {nm: round(sum(e[i].elapsed_time(e[i + 1]) for e in rows) / len(rows), 4) for i, nm in enumerate(names)}
 
     def _use_nvls(self, plan) -> bool:
         if self.exchange == "nccl" or self.world == 1:
@@ -154,7 +182,7 @@ class DataParallelUNet:
     # and each 124 MB all-reduce hides behind the backward kernels.
 
     def detach(self):
-        for name in ("_grad_scale", "_bucket_hook", "_backward_done_hook"):
+        for name in ("_grad_scale", "_bucket_hook", "_backward_done_hook", "_bucket_per_segment"):
             if hasattr(self.model, name):
                 delattr(self.model, name)
 

@@ -131,6 +131,6 @@ class unet(nn.Module):
         state = self.__dict__.copy()
         state["_engine"] = None
         state["_train_graph"] = None
-        for name in ("_bucket_hook", "_backward_done_hook", "_grad_scale"):
+        for name in ("_bucket_hook", "_backward_done_hook", "_grad_scale", "_bucket_per_segment"):
             state.pop(name, None)
         return state
