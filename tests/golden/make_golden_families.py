@@ -258,9 +258,42 @@ def gen_prompt(ref):
     np.savez_compressed(os.path.join(OUT, "prompt.npz"), **out)
 
 
+def gen_unet_bf16_noise(ref):
+    """The reference's OWN deviation under bf16 autocast (CPU) from its fp64 run, per parameter gradient and for the
+    logits, on the inputs of unet_step.npz (2x3x32x32, seed 1234) and at 2x3x256x256 (seed 7): the yardstick for the
+    end-to-end bf16 tolerances of tests/test_gpu_unet.py."""
+    out = {}
+    for tag, hw, seed in (("32", 32, 1234), ("256", 256, 7)):
+        x, y = make_batch(2, hw, hw, 3, 3, seed=seed)
+        res = {}
+        for mode in ("f64", "bf16"):
+            torch.manual_seed(0)
+            m = ref.unet(3, 3).train()
+            w = torch.tensor(CLASS_W4[:3])
+            loss_fn = ref.WeightedDiceCELoss(smooth_dice=1, class_weights=w)
+            if mode == "f64":
+                m = m.double()
+                logits = m(x.double())
+                loss = ref.WeightedDiceCELoss(smooth_dice=1, class_weights=w.double())(logits, y.squeeze(1))
+            else:
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    logits = m(x)
+                loss = loss_fn(logits.float(), y.squeeze(1))
+            loss.backward()
+            res[mode] = (logits.detach().double(), {k: p.grad.detach().double() for k, p in m.named_parameters()}, loss.item())
+        l64, g64, loss64 = res["f64"]
+        l16, g16, loss16 = res["bf16"]
+        out[f"names_{tag}"] = np.array(list(g64.keys()))
+        out[f"grad_rel_l2_{tag}"] = np.array([((g16[k] - g64[k]).norm() / g64[k].norm().clamp(min=1e-30)).item() for k in g64])
+        out[f"logits_rel_l2_{tag}"] = np.array(((l16 - l64).norm() / l64.norm()).item())
+        out[f"loss_{tag}"] = np.array([loss64, loss16])
+    np.savez_compressed(os.path.join(OUT, "unet_bf16_noise.npz"), **out)
+
+
 def main():
     ref = ref_shim.load()
     torch.set_num_threads(8)
+    gen_unet_bf16_noise(ref)
     gen_autoencoder(ref)
     gen_clip(ref)
     gen_prompt(ref)
