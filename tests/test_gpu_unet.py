@@ -110,16 +110,23 @@ def test_bf16_tier_end_to_end(golden, algo):
     print(f"bf16/{algo}: logits rel-L2 vs fp64 reference = {e:.3e}; loss {loss.item():.6f} vs {float(g['loss_33_f64']):.6f}")
     assert e < 5e-2
     assert abs(loss.item() - float(g["loss_33_f64"])) < 2e-2
+    # yardstick: the reference's OWN deviation under bf16 autocast from its fp64 run on these inputs
+    # (tests/golden/unet_bf16_noise.npz, generated from the unmodified reference): logits and every stored gradient must
+    # stay within 2x of it (+ a small floor for tensors where the reference happens to be unusually close)
+    noise = golden["unet_bf16_noise"]
+    ref_dev = dict(zip(list(noise["names_32"]), noise["grad_rel_l2_32"]))
+    assert e < 2 * float(noise["logits_rel_l2_32"])
     params = dict(m.named_parameters())
-    for k in ("output.weight", "output.bias", "up4.upsample.bias"):
+    for k in ("output.weight", "output.bias", "up4.upsample.bias", "down1.doubleConvReLU.0.weight",
+              "up4.doubleConv.doubleConvReLU.4.weight"):
         eg = rel_l2(params[k].grad, g[f"grad_33_f64:{k}"])
-        print(f"  grad {k}: rel-L2 {eg:.3e}")
-        assert eg < 0.5
+        print(f"  grad {k}: rel-L2 {eg:.3e} (reference under bf16 autocast: {ref_dev[k]:.3e})")
+        assert eg < 2 * ref_dev[k] + 5e-3, (k, eg, ref_dev[k])
     for p in m.parameters():
         assert torch.isfinite(p.grad).all()
 
 
-def test_tc_and_simt_bf16_paths_agree_at_training_resolution():
+def test_tc_and_simt_bf16_paths_agree_at_training_resolution(golden):
     """Same bf16 inputs, fp32 accumulation in both: only the summation order differs."""
     x, y = make_batch(2, 256, 256, 3, 3, seed=7)
     outs = {}
@@ -137,7 +144,9 @@ def test_tc_and_simt_bf16_paths_agree_at_training_resolution():
     # bf16 end-to-end gradients are chaotic (ReLU / max-pool flips after different roundings): the reference under
     # bf16 autocast deviates from fp64 by a median rel-L2 of 0.36.  The per-kernel tests in
     # test_gpu_ops.py hold each tcgen05 kernel to 2e-2 on identical inputs; here only gross disagreement is caught.
-    assert errs[len(errs) // 2][0] < 0.36
+    # Yardstick (tests/golden/unet_bf16_noise.npz): the reference's own median deviation on THESE inputs is 0.42.
+    ref_median = float(np.median(golden["unet_bf16_noise"]["grad_rel_l2_256"]))
+    assert errs[len(errs) // 2][0] < ref_median
     assert errs[-1][0] < 0.8
 
 
