@@ -55,6 +55,23 @@ elif a.op == "convt":
 
     def run():
         L.conv(x, wt, y, L.MODE_CONVT, bias=b)
+elif a.op == "convt_dgrad":
+    # data gradient of ConvTranspose2d(cin -> cout): gathers the hi-res gradient [N,2h,2w,cout] into [N,h,w,cin]
+    dyh = torch.randn(n, 2 * h, 2 * w, a.cout, device=dev).to(bf)
+    wt = (torch.randn(a.cin, 4, a.cout, device=dev) * 0.05).to(bf)
+    y = torch.empty(n, h, w, a.cin, device=dev, dtype=bf)
+    flops = 2 * n * h * w * a.cin * 4 * a.cout
+
+    def run():
+        L.conv(dyh, wt, y, L.MODE_CONVT_GATHER)
+elif a.op == "bilinear_fwd" or a.op == "bilinear_bwd":
+    # clip/clipunet.py:99-100 at the last decoder level by default: 14x14 -> hw x hw, cin channels
+    src = torch.randn(n, 14, 14, a.cin, device=dev).to(bf)
+    dst = torch.randn(n, h, w, a.cin, device=dev).to(bf)
+    flops = 0
+
+    def run():
+        L.bilinear_up(src, dst, backward=a.op.endswith("bwd"))
 else:
     raise SystemExit("unknown op")
 for _ in range(2):
@@ -68,6 +85,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.iters
 print(f"{a.op} cin={a.cin} cout={a.cout} hw={a.hw} batch={a.batch}: {ms:.3f} ms  {flops / ms / 1e9:.1f} TFLOP/s")
+if a.op.startswith("bilinear"):
+    print(f"  bytes (destination tensor once): {dst.numel() * 2 / 1e6:.1f} MB -> {dst.numel() * 2 / ms / 1e6:.0f} GB/s")
 if os.environ.get("UNETK_DBG") == "1":
     import ctypes
     buf = (ctypes.c_longlong * (148 * 8))()
