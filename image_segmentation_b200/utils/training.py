@@ -1,7 +1,7 @@
 """Drop-in for the reference's ``utils/training.py``: ``train_loop`` (:18-64), ``eval_loop`` (:67-121),
 ``trainReconstruction`` (:123-151), ``train_loop_prompt`` (:153-199), ``evalReconstruction`` (:202-239),
-``eval_loop_prompt`` (:242-296) and ``start`` (:453-617) with the same signatures, printed lines and
-checkpoint dictionary keys.  Model, loss and metrics objects are passed in, exactly as in the
+``eval_loop_prompt`` (:242-296), ``start_prompt`` (:299-450) and ``start`` (:453-617) with the same signatures, printed
+lines and checkpoint dictionary keys.  Model, loss and metrics objects are passed in, exactly as in the
 reference; with this package's ``unet`` / ``WeightedDiceCELoss`` / ``MetricsHistory`` every step runs on
 the CUDA kernels, and the loops themselves only sequence work (host code stays Python).
 
@@ -454,7 +454,7 @@ def eval_loop_prompt(dataloader, model, loss_fn, device, target_size, agg):
 
 def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, val_dataloader, accumulation_steps,
           device, train_loss_fn, val_loss_fn, target_size, scheduler=None, agg=None, load=True, save=True,
-          num_classes=4, ignore_index=3, epochs=100):
+          num_classes=4, ignore_index=3, epochs=100, _prompt=False):
     """Train/evaluate for ``epochs`` epochs with best-mIoU checkpointing and resume (reference :453-617).
 
     Same printed lines, files and checkpoint keys as the reference.  Deliberate differences: the model is moved to
@@ -473,7 +473,8 @@ def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, v
     os.makedirs(os.path.join(model_save_dir, "metrics"), exist_ok=True)
     if load and os.path.isfile(path):
         print(f"Loading checkpoint from: {path}")
-        ckpt = torch.load(path, map_location=device, weights_only=True)
+        # start_prompt() loads with pickle enabled: its checkpoints carry the MetricsHistory object (reference :351,:423)
+        ckpt = torch.load(path, map_location=device, weights_only=not _prompt)
         model.load_state_dict(ckpt["model_state_dict"])
         print(" -> Model state loaded.")
         for key, obj, what in (("optimizer_state_dict", optimizer, "Optimizer"), ("scheduler_state_dict", scheduler, "Scheduler")):
@@ -503,8 +504,9 @@ def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, v
     print("\nStarting Training...")
     for t in range(start_epoch, epochs):
         print(f"Epoch {t + 1}\n-------------------------------")
-        train_loop(train_dataloader, model, train_loss_fn, optimizer, accumulation_steps, device, scheduler, target_size)
-        val_loss, val_dice, val_miou = eval_loop(val_dataloader, model, val_loss_fn, device, target_size, agg)
+        train_fn, eval_fn = (train_loop_prompt, eval_loop_prompt) if _prompt else (train_loop, eval_loop)
+        train_fn(train_dataloader, model, train_loss_fn, optimizer, accumulation_steps, device, scheduler, target_size)
+        val_loss, val_dice, val_miou = eval_fn(val_dataloader, model, val_loss_fn, device, target_size, agg)
         if save:
             torch.save({"epoch": t + 1, "history": agg}, os.path.join(model_save_dir, "metrics", model_save_name))
         if val_miou > best["best_dev_miou"]:
@@ -516,9 +518,12 @@ def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, v
                         "notes": f"Model saved based on best Micro Dice. Ignored index for metric: {ignore_index}"}
                 if scheduler:
                     ckpt["scheduler_state_dict"] = scheduler.state_dict()
+                if _prompt:
+                    ckpt["history"] = agg                  # start_prompt keeps the history in the checkpoint, no MO_ copy
                 torch.save(ckpt, path)
-                torch.save({"epoch": t + 1, "model_state_dict": model.state_dict()},
-                           os.path.join(model_save_dir, f"MO_{model_save_name}"))
+                if not _prompt:
+                    torch.save({"epoch": t + 1, "model_state_dict": model.state_dict()},
+                               os.path.join(model_save_dir, f"MO_{model_save_name}"))
         else:
             print(f"Validation IoU score did not improve from {best['best_dev_miou']:.6f}")
     print("\n--- Training Finished! ---")
@@ -527,3 +532,14 @@ def start(model_save_dir, model_save_name, model, optimizer, train_dataloader, v
     print(f"Corresponding validation loss: {best['best_dev_loss']:.6f}")
     print(f"Best model saved to: {os.path.join(model_save_dir, model_save_name)}")
     return best
+
+
+def start_prompt(model_save_dir, model_save_name, model, optimizer, train_dataloader, val_dataloader, accumulation_steps,
+                 device, train_loss_fn, val_loss_fn, target_size, scheduler=None, agg=None, load=True, save=True,
+                 num_classes=4, ignore_index=3, epochs=100):
+    """``start`` for prompt-based models (reference utils/training.py:299-450): batches are (image, heat-map, label), the
+    loops are ``train_loop_prompt`` / ``eval_loop_prompt``, the checkpoint carries the metrics history and is loaded with
+    pickle enabled, and no weights-only ``MO_`` copy is written."""
+    return start(model_save_dir, model_save_name, model, optimizer, train_dataloader, val_dataloader, accumulation_steps,
+                 device, train_loss_fn, val_loss_fn, target_size, scheduler, agg, load, save, num_classes, ignore_index, epochs,
+                 _prompt=True)

@@ -376,3 +376,44 @@ def test_prompt_model_matches_reference_golden(golden):
                 assert abs(got - ref_norm) <= 3e-2 * ref_norm + 1e-7, (k, got, ref_norm)
             for key in ("output.weight", "output.bias"):
                 assert rel_max(gd[key].grad, g[f"grad_pm_mask:{key}"]) < 2e-3, key
+
+
+def test_start_prompt_trains_evaluates_and_checkpoints(tmp_path, capsys):
+    """start_prompt / train_loop_prompt / eval_loop_prompt (utils/training.py:153-199,242-450) on the tiny fixture: the mask
+    network trains (loss falls), the frozen CLIP branch does not move, the checkpoint carries the history object and there
+    is no MO_ weights copy; a second call resumes from the checkpoint."""
+    from image_segmentation_b200.clip.clipunet import ClipUNet
+    from image_segmentation_b200.prompt_based.prompt import PromptModel
+    from image_segmentation_b200.utils.MetricsHistory import MetricsHistory
+    from image_segmentation_b200.utils.training import start_prompt
+    mg = _mg()
+    torch.manual_seed(0)
+    pm = PromptModel(clip=ClipUNet(num_classes=4, decoder_channels=mg.TINY_DECODER, clip_vit=mg.tiny_vit()))
+    pm.clip.precision = pm.mask.precision = "fp32"
+    pm = pm.to(DEV)
+    clip_before = {k: v.detach().clone() for k, v in pm.clip.named_parameters()}
+    g = torch.Generator().manual_seed(4)
+    train = []
+    for _ in range(3):
+        x = torch.rand(2, 3, 64, 64, generator=g)
+        heat = torch.rand(2, 1, 64, 64, generator=g)
+        y = (x.mean(1, keepdim=True) * 3.999).floor().to(torch.uint8)
+        train.append((x, heat, y))
+    val = [([torch.rand(3, 50, 70, generator=g)], [torch.rand(1, 50, 70, generator=g)], [torch.randint(0, 4, (50, 70), generator=g)])]
+    opt = torch.optim.AdamW([p for p in pm.parameters() if p.requires_grad], lr=1e-3)
+    fn = WeightedDiceNLLLoss(apply_softmax=False, nll_nonlin=lambda t: torch.log(t + 1e-9), smooth_dice=1,
+                             class_weights=torch.tensor(CLASS_W4))
+    start_prompt(str(tmp_path), "pm.pt", pm, opt, train, val, 1, torch.device(DEV), fn, fn, 64, None, MetricsHistory(4, 3), True, True,
+                 4, 3, 2)
+    out = capsys.readouterr().out
+    losses = [float(v) for v in __import__("re").findall(r"Training Avg loss \(per effective batch\):\s*(-?\d+\.\d+)", out)]
+    assert len(losses) == 2 and losses[1] < losses[0]
+    for k, v in pm.clip.named_parameters():
+        assert torch.equal(v, clip_before[k]), k
+    files = sorted(os.listdir(tmp_path))
+    assert "pm.pt" in files and not any(f.startswith("MO_") for f in files)
+    ck = torch.load(tmp_path / "pm.pt", weights_only=False)
+    assert "history" in ck and ck["epoch"] in (1, 2)
+    start_prompt(str(tmp_path), "pm.pt", pm, opt, train, val, 1, torch.device(DEV), fn, fn, 64, None, None, True, True, 4, 3, 3)
+    out2 = capsys.readouterr().out
+    assert f"Resuming training from epoch {ck['epoch'] + 1}" in out2 and " -> Metrics History loaded." in out2
