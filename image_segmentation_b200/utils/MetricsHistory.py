@@ -52,10 +52,15 @@ class MetricsHistory:
         self._sync()
         return self._host[i]
 
-    total_tp = property(lambda self: self._totals(0))
-    total_fp = property(lambda self: self._totals(1))
-    total_fn = property(lambda self: self._totals(2))
-    total_tn = property(lambda self: self._totals(3))
+    def _set_totals(self, i, value):
+        """``agg.total_tp = tensor`` (plain attributes in the reference, :21-24): device counters are folded in first."""
+        self._sync()
+        self._host[i].copy_(torch.as_tensor(value, dtype=torch.float64).reshape(self.num_classes).cpu())
+
+    total_tp = property(lambda self: self._totals(0), lambda self, v: self._set_totals(0, v))
+    total_fp = property(lambda self: self._totals(1), lambda self, v: self._set_totals(1, v))
+    total_fn = property(lambda self: self._totals(2), lambda self, v: self._set_totals(2, v))
+    total_tn = property(lambda self: self._totals(3), lambda self, v: self._set_totals(3, v))
 
     def reset(self):
         """Resets the accumulated TP, FP, FN, TN counts."""
@@ -99,15 +104,21 @@ class MetricsHistory:
         per_class = {"iou": tp / union, "dice": (2 * tp) / (tp + union), "acc": (tp + tn) / (union + tn)}
         means = {}
         for kind, values in per_class.items():
-            means[kind] = values[self.mask].mean().item()
+            means[kind] = values[self.mask.cpu()].mean().item()
             getattr(self, f"epoch_mean_{kind}_history").append(means[kind])
             getattr(self, f"epoch_per_class_{kind}_history").append(values.numpy())
             setattr(self, f"last_per_class_{kind}", values)
         return means["dice"], means["iou"], means["acc"]
 
     def to(self, device):
-        """Kept for API parity; totals live on the host, counters follow the predictions' device."""
-        self.mask = self.mask.to("cpu")
+        """Moves what the reference moves that a caller can observe (:130-150): the class mask and the last per-class
+        metric tensors.  The count totals stay float64 host tensors fed by exact device counters that follow the
+        predictions' device (no per-image copies, unlike the reference's ``.cpu()`` x 4 per image, :83-86)."""
+        self.mask = self.mask.to(device)
+        for kind in ("iou", "dice", "acc"):
+            v = getattr(self, f"last_per_class_{kind}")
+            if v is not None:
+                setattr(self, f"last_per_class_{kind}", v.to(device))
 
     def all_reduce(self, group=None):
         """Data-parallel evaluation: sum the exact counts over ranks (one small collective)."""
