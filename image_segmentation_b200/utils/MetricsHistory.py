@@ -137,6 +137,13 @@ class MetricsHistory:
         state["_pending"] = {}
         return state
 
+    def __setstate__(self, state):
+        # torch.load(..., map_location=device) moves every pickled tensor (utils/training.py:351); the float64 totals
+        # are host tensors by construction
+        self.__dict__.update(state)
+        self._host = self._host.cpu()
+        self._pending = {}
+
     def get_ignore_index(self):
         return self.ignore_index
 
