@@ -339,7 +339,8 @@ def prep_conv(x, w, y, mode, bias=None, stat_sum=None, stat_sumsq=None, algo=ALG
                  bnz, bsc, bsh, bmu, bis, bsum)
     if algo_flops is None:
         algo_flops = conv_flops(x, y, mode)
-    simt = (algo & 0xff) == ALGO_SIMT or ((algo & 0xff) == ALGO_AUTO and x.dtype != torch.bfloat16)
+    simt = (algo & 0xff) == ALGO_SIMT or ((algo & 0xff) == ALGO_AUTO and (x.dtype != torch.bfloat16 or x.shape[3] % 64
+                                                                            or y.shape[3] % 64))
     return Call("conv", 2 if (simt and stat_sum is not None) else 1, algo_flops, lib().unetk_conv, (C.byref(a),), tag=mode,
                 keep=(a, x, w, y, bias, stat_sum, stat_sumsq, bn_reduce), label=label)
 

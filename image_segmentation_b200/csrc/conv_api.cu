@@ -87,7 +87,13 @@ int unetk_conv(const unetk_conv_args* a, void* stream) {
   }
 
   int algo = a->algo & UNETK_ALGO_MASK;
-  if (algo == UNETK_ALGO_AUTO) algo = a->x.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  if (algo == UNETK_ALGO_AUTO) {
+    // bf16 -> tensor cores whenever the shape allows it (channel counts multiples of 64); other bf16 shapes (e.g. a
+    // 32-channel layer) run on the CUDA-core kernels -- both are this library's own kernels, neither is a fallback to
+    // another backend.  UNETK_ALGO_TC requests the tcgen05 path explicitly and fails loudly when it cannot run.
+    const char* why = "";
+    algo = (a->x.dtype == UNETK_BF16 && tc_conv_supported(a, g, &why)) ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  }
   if (algo == UNETK_ALGO_TC) {
     const char* why = "";
     if (!tc_conv_supported(a, g, &why)) {
@@ -124,7 +130,10 @@ int unetk_wgrad(const unetk_wgrad_args* a, void* stream) {
   else
     UNETK_REQUIRE(a->s.n == a->u.n && a->s.h == 2 * a->u.h && a->s.w == 2 * a->u.w, "wgrad(mode 2): s must be [N,2h,2w,C]");
   int algo = a->algo & UNETK_ALGO_MASK;
-  if (algo == UNETK_ALGO_AUTO) algo = a->u.dtype == UNETK_BF16 ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  if (algo == UNETK_ALGO_AUTO) {
+    const char* why0 = "";
+    algo = (a->u.dtype == UNETK_BF16 && tc_wgrad_supported(a, taps, &why0)) ? UNETK_ALGO_TC : UNETK_ALGO_SIMT;
+  }
   if (algo == UNETK_ALGO_TC) {
     const char* why = "";
     if (!tc_wgrad_supported(a, taps, &why)) {

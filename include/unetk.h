@@ -48,7 +48,7 @@ extern "C" {
 #define UNETK_ERR_UNSUPPORTED (-3)
 
 /* algo selector for the contraction kernels */
-#define UNETK_ALGO_AUTO 0   /* bf16 -> tcgen05, f32 -> SIMT */
+#define UNETK_ALGO_AUTO 0   /* bf16 with channel counts multiple of 64 -> tcgen05; everything else -> SIMT */
 #define UNETK_ALGO_SIMT 1   /* CUDA-core FFMA kernels (any dtype; the fp32 parity tier) */
 #define UNETK_ALGO_TC 2     /* TMA + tcgen05.mma + TMEM (bf16 only) */
 #define UNETK_ALGO_MASK 0xff

@@ -195,11 +195,9 @@ def _tiny_clip(precision):
     torch.manual_seed(0)
     m = ClipUNet(num_classes=4, decoder_channels=mg.TINY_DECODER, clip_vit=mg.tiny_vit())
     m.precision = precision
-    if precision == "bf16":
-        # the tiny fixture has 32-channel layers (64 // 2); the tensor-core kernels need multiples of 64 (every layer of
-        # the real decoder [1024,512,256,128,64] is), so its bf16 run uses the CUDA-core kernels on bf16 tensors;
-        # the tcgen05 path is covered at the real geometry in test_clip_decoder_real_geometry_bf16_vs_oracle
-        m.conv_algo = "simt"
+    # (the tiny fixture has 32-channel layers (64 // 2); the tensor-core kernels need multiples of 64 -- every layer of the
+    # real decoder [1024,512,256,128,64] is -- so in its bf16 run UNETK_ALGO_AUTO sends those layers to the CUDA-core
+    # kernels on bf16 tensors; the tcgen05 path at the real geometry: test_clip_decoder_real_geometry_bf16_vs_oracle)
     return m.to(DEV).train()
 
 
@@ -353,8 +351,6 @@ def test_prompt_model_matches_reference_golden(golden):
         torch.manual_seed(0)
         pm = PromptModel(clip=ClipUNet(num_classes=4, decoder_channels=mg.TINY_DECODER, clip_vit=mg.tiny_vit()))
         pm.clip.precision = pm.mask.precision = precision
-        if precision == "bf16":
-            pm.clip.conv_algo = "simt"          # 32-channel layers of the tiny CLIP fixture (see _tiny_clip)
         pm = pm.to(DEV).train()
         probs = pm(x, heat)
         fn = WeightedDiceNLLLoss(apply_softmax=False, nll_nonlin=lambda t: torch.log(t + 1e-9), smooth_dice=1,
