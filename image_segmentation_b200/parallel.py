@@ -31,8 +31,8 @@ class DataParallelUNet:
                  exchange: str = "auto"):
         """``exchange``: "nccl" = bucketed ``ncclAllReduce`` (any backend torch.distributed offers, also gloo in the CPU
         tests); "nvls" = this package's two-shot multicast kernel (``unetk_nvls_allreduce_f32``: the gradients sit in
-        symmetric memory and the NVSwitch reduces them, one launch after the last gradient); "auto" = nvls when the
-        process group's devices support multicast, else nccl.
+        symmetric memory and the NVSwitch reduces them, one launch after the last gradient); "auto" = nvls from four ranks
+        on when the process group's devices support multicast, else nccl.
         ``bucket_mb``: minimum size of an all-reduce (a huge value = ONE all-reduce after the last gradient).
         ``compress="bf16"`` (opt-in, changes numerics): gradients travel as bf16 (half the bytes; the sum over ranks is
         formed in bf16 by NCCL) and are widened back to fp32 afterwards -- stock DDP's bf16 compression hook."""
@@ -124,6 +124,11 @@ class DataParallelUNet:
 
     def _use_nvls(self, plan) -> bool:
         if self.exchange == "nccl" or self.world == 1:
+            return False
+        if self.exchange == "auto" and self.world < 4:
+            # two ranks exchange halves point to point; the switch reduction pays from four ranks on (measured on 2 x B200:
+            # 21.31 ms/step with the multicast kernel, 21.07 with NCCL; a tie at 8 -- DESIGN.md section 6)
+            self._nvls = False
             return False
         if self._nvls is None:
             if torch.cuda.is_current_stream_capturing():
