@@ -2,20 +2,22 @@
 """bench.py -- U-Net 256x256 training throughput (images/s) on N B200s; one JSON line on stdout.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (bf16 tcgen05 tier)
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path on the host cores
+    python bench.py --workload autoencoder_recon|autoencoder_seg|clip|prompt   # the other model families (one GPU)
 
 Workload (BASELINE.json configs[1]): unet(3,3) bf16 training step, batch 64 per GPU at 256x256,
 WeightedDiceCELoss(smooth_dice=1, class weights), AdamW(lr 1e-3, wd 0.01), MetricsHistory.accumulate,
 synthetic U[0,1) images and i.i.d. 3-class labels, random-init weights.
 
-A step = forward + loss + backward (+ gradient all-reduce for N > 1) + optimizer.step + zero_grad + metrics.
+A step = forward + loss + backward (+ gradient exchange for N > 1) + optimizer.step + zero_grad + metrics.
 `value`  : images/s of the whole job with the batch already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with the batch in pinned HOST memory: H2D of X (fp32) and y (uint8)
            and a D2H read of the loss inside the timed region every step.
-`roofline`: tensor-pipe roofline of the tcgen05 contraction kernels (algorithmic FLOPs / CUDA-event time of those
-           launches, measured in extra instrumented steps right after the timed region).
-`cpu_baseline`: the oracle port (kind "port": the reference is Python and does not travel to the GPU box) timed on
-           the host cores for a bounded sample (batch 4 steps).
+`roofline`: tensor-pipe roofline of the tcgen05 contraction kernels: algorithmic FLOPs / CUDA-event time of those
+           launches in three instrumented eager steps, each enqueued behind a spin kernel so that the launches run back
+           to back (refused when they cover less than half of the step); plus the whole-step figures.
+`cpu_baseline`: the UNMODIFIED reference modules staged under oracle/_ref (kind "reference"; the oracle port, kind
+           "port", only if they did not travel) timed on the host cores for a bounded sample (batch 4 steps).
 """
 import argparse
 import json
