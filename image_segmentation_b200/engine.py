@@ -732,6 +732,22 @@ class NetPlan:
             return any(p.requires_grad for p in nd.params()) or nd.src.needs_grad
         return nd.runs_backward()
 
+    def _frozen_bn_scratch(self, c: int):
+        """(dgamma, dbeta) device pointers for a BatchNorm whose affine parameters are frozen while gradients still flow
+        through it: the kernels always write both vectors, so they get a throw-away buffer."""
+        buf = getattr(self, "_scratch_c", None)
+        if buf is None or buf.numel() < 2 * c:
+            buf = self._scratch_c = torch.empty(max(8192, 2 * c), dtype=torch.float32, device=self.device)
+        return buf.data_ptr(), buf.data_ptr() + 4 * c
+
+    def _patch_bn_grads(self, call, args, l):
+        """dgamma / dbeta of layer l land in the flat gradient buffer when trainable, in a throw-away buffer when frozen."""
+        args.dgamma, args.dbeta = self._frozen_bn_scratch(l.cout)
+        if l.bn.weight.requires_grad:
+            call.patch_ptr(args, "dgamma", self._goff(l.bn.weight))
+        if l.bn.bias.requires_grad:
+            call.patch_ptr(args, "dbeta", self._goff(l.bn.bias))
+
     def _goff(self, p) -> int:
         """Byte offset of parameter p's gradient in the flat buffer."""
         return 4 * self._off_of[id(p)]
@@ -812,7 +828,7 @@ class NetPlan:
                     hd.g_in = hd.src.grad
                     call, box = L.prep_head_bwd(self._dlogits_slot, hd.src.t, hd.conv.weight, hd.dout, hd.g_in, label=hd.name)
                     call.patch_ptr(box, "dw", self._goff(hd.conv.weight))
-                    if hd.conv.bias is not None:
+                    if hd.conv.bias is not None and hd.conv.bias.requires_grad:
                         call.patch_ptr(box, "db", self._goff(hd.conv.bias))
                     ops.append(call)
                     done_params += len([p for p in hd.params() if p.requires_grad])
@@ -827,14 +843,13 @@ class NetPlan:
                     args, calls = L.prep_head_bn_bwd(self._dlogits_slot, l.z, hd.conv.weight, hd.dout, l.scale, l.shift, l.mean,
                                                      l.invstd, self.head_sums, l.dz, label=l.name)
                     ap = calls[1]
-                    if l.bn.weight.requires_grad:
-                        ap.patch_ptr(args, "dgamma", self._goff(l.bn.weight))
-                        ap.patch_ptr(args, "dbeta", self._goff(l.bn.bias))
-                    else:
-                        self._scratch_c = getattr(self, "_scratch_c", None) or torch.empty(4096, dtype=torch.float32, device=self.device)
-                        args.dgamma, args.dbeta = self._scratch_c.data_ptr(), self._scratch_c.data_ptr() + 4 * l.cout
-                    ap.patch_ptr(args, "dw_head", self._goff(hd.conv.weight))
-                    if hd.conv.bias is not None:
+                    self._patch_bn_grads(ap, args, l)
+                    if hd.conv.weight.requires_grad:
+                        ap.patch_ptr(args, "dw_head", self._goff(hd.conv.weight))
+                    else:       # frozen classifier: the kernel still needs somewhere to put dW (dout x C floats)
+                        self._head_scratch = torch.empty(hd.dout * l.cout, dtype=torch.float32, device=self.device)
+                        args.dw_head = self._head_scratch.data_ptr()
+                    if hd.conv.bias is not None and hd.conv.bias.requires_grad:
                         ap.patch_ptr(args, "db_head", self._goff(hd.conv.bias))
                     ops += calls
                     ops.append(("bucket_only", None, self.grad_offsets[done_params]))
@@ -846,12 +861,7 @@ class NetPlan:
                     args, calls = L.prep_bn_relu_bwd(l.z, dy, dpool, l.scale, l.shift, l.mean, l.invstd, l.bwd_sums, l.dz,
                                                      pool_idx=l.pool_idx if dpool is not None else None,
                                                      reduced=l.reduced and dpool is None, label=l.name)
-                    if l.bn.weight.requires_grad:
-                        calls[-1].patch_ptr(args, "dgamma", self._goff(l.bn.weight))
-                        calls[-1].patch_ptr(args, "dbeta", self._goff(l.bn.bias))
-                    else:
-                        self._scratch_c = getattr(self, "_scratch_c", None) or torch.empty(4096, dtype=torch.float32, device=self.device)
-                        args.dgamma, args.dbeta = self._scratch_c.data_ptr(), self._scratch_c.data_ptr() + 4 * l.cout
+                    self._patch_bn_grads(calls[-1], args, l)
                     ops += calls
                 wreq = l.conv.weight.requires_grad
                 flops = 2 * self.n * l.z.shape[1] * l.z.shape[2] * 9 * l.cin * l.cout

@@ -440,6 +440,35 @@ def test_deterministic_mode_gives_bit_reproducible_gradients():
         assert rel_max(grads[True][k], grads[False][k]) < 1e-4, k
 
 
+def test_partially_frozen_parameters_get_no_gradient_and_do_not_disturb_the_others(golden):
+    """requires_grad=False on arbitrary parameters (BatchNorm affine only, a conv weight only, the head bias): frozen
+    tensors receive no gradient, every other gradient is what the fully trainable network gets (golden fp64 norms)."""
+    g = golden["unet_step"]
+    x, y = make_batch(2, 32, 32, 3, 3, seed=1234)
+    m = build(3, 3, "fp32")
+    frozen = set()
+    for k, p in m.named_parameters():
+        if (k.startswith("down2.") and ".1." in k.split("doubleConvReLU")[-1][:3]) or k.startswith("down2.maxpool_doubleConv.1.doubleConvReLU.4") \
+                or k == "up3.doubleConv.doubleConvReLU.0.weight" or k == "output.bias" or k == "down1.doubleConvReLU.0.weight":
+            p.requires_grad = False
+            frozen.add(k)
+    assert len(frozen) >= 6
+    loss = loss_for(3)(m(x.to(DEV)), y.squeeze(1).to(DEV))
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_33_f64"])) < 1e-4
+    names = list(g["grad_names_33"])
+    n64, n32 = g["grad_norms_33_f64"], g["grad_norms_33_f32"]
+    for k, p in m.named_parameters():
+        if k in frozen:
+            assert p.grad is None, k
+            continue
+        if k.endswith(".bias") and "doubleConvReLU" in k and k.split(".")[-2] in ("0", "3"):
+            continue
+        i = names.index(k)
+        got = p.grad.double().norm().item()
+        assert abs(got - n64[i]) <= 3 * abs(n32[i] - n64[i]) + 2e-4 * n64[i] + 1e-9, (k, got, n64[i])
+
+
 def test_forward_metrics_pipeline_matches_oracle():
     """argmax masks and confusion counts are bit-exact given identical logits."""
     x, y = make_batch(2, 32, 32, 3, 4, seed=9)
