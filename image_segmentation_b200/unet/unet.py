@@ -13,7 +13,6 @@ Extra, non-reference attributes of ``unet``:
   ``precision``  "bf16" (default; tcgen05 kernels, fp32 accumulation) or "fp32" (CUDA-core parity tier)
   ``conv_algo``  "auto" | "simt" | "tc"  -- which contraction kernels run (debug / cross-check knob)
 """
-import torch
 from torch import nn
 
 from ..engine import Engine, EngineModule, NhwcOutput
