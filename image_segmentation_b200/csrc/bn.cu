@@ -732,6 +732,123 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// bf16 tier: the same fusion with the 64 x dout dot products on the tensor cores (mma.sync m16n8k16, fp32 accumulate).
+// A warp owns 16 consecutive pixels per round.  Lane (gid = lane / 4, tig = lane % 4) loads, for pixels base + gid and
+// base + gid + 8, the two 16-byte channel groups tig and tig + 4 (every load instruction reads 64 contiguous bytes per
+// pixel row), applies BatchNorm + ReLU + bf16 rounding in registers and uses the packed words DIRECTLY as A fragments: the
+// K slots of each of the four MMAs are a permutation of channels chosen so that a thread's own words are its fragment
+// (slot 2*tig + {0,1} (+8) of MMA j  <->  channel 32*(j/2) + 8*tig + 2*(2*(j%2) + (slot >= 8)) + {0,1}); the B fragments
+// (the head weights, constant) are built once per thread with the same permutation.  fp32 weights are split into
+// hi + lo bf16 halves living in columns k and 4 + k of the N = 8 tile, so the product keeps fp32-level accuracy
+// (|w - hi - lo| <= 2^-17 |w|); the two halves are added with one shuffle.  ~8 instructions per pixel instead of ~20.
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                  uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int DOUT>
+__global__ void __launch_bounds__(kThreads)
+    bn_relu_head_mma_kernel(const __nv_bfloat16* __restrict__ z, int zld, const float* __restrict__ scale,
+                            const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int ald,
+                            const float* __restrict__ wh, const float* __restrict__ bh, float* __restrict__ logits,
+                            int64_t npix, uint32_t hw) {
+  constexpr int C = 64;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // this thread's 16 channels: groups tig (0..31) and tig + 4 (32..63)
+  float sc[2][8], sh[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    load8(scale + (tig + 4 * h) * 8, sc[h]);
+    load8(shift + (tig + 4 * h) * 8, sh[h]);
+  }
+  // B fragments: column n = gid (n < 4: hi half of Wh[n], n >= 4: lo half of Wh[n - 4]); MMA j, register r (K slots
+  // 2*tig + {0,1} + 8*r) <-> channels 32*(j/2) + 8*tig + 2*(2*(j%2) + r) + {0,1}
+  uint32_t bfrag[4][2];
+  {
+    const int k = gid & 3;
+    const bool lo_half = gid >= 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int ch = 32 * (j >> 1) + 8 * tig + 2 * (2 * (j & 1) + r);
+        float w0 = 0.f, w1 = 0.f;
+        if (k < DOUT) {
+          w0 = wh[(size_t)k * C + ch];
+          w1 = wh[(size_t)k * C + ch + 1];
+          if (lo_half) {
+            w0 -= __bfloat162float(__float2bfloat16_rn(w0));
+            w1 -= __bfloat162float(__float2bfloat16_rn(w1));
+          }
+        }
+        bfrag[j][r] = pack_bf16x2(w0, w1);
+      }
+    }
+  }
+  // after the hi + lo fold, lane tig 0 holds classes 0,1 and lane tig 1 classes 2,3
+  const float b0 = (bh && 2 * tig < DOUT) ? bh[2 * tig] : 0.f;
+  const float b1 = (bh && 2 * tig + 1 < DOUT) ? bh[2 * tig + 1] : 0.f;
+  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+    const int64_t p0 = base + gid, p1 = base + gid + 8;
+    uint4 raw[2][2];                                 // [pixel row][channel half]
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      raw[0][h] = p0 < npix ? *reinterpret_cast<const uint4*>(z + p0 * zld + (tig + 4 * h) * 8) : make_uint4(0, 0, 0, 0);
+      raw[1][h] = p1 < npix ? *reinterpret_cast<const uint4*>(z + p1 * zld + (tig + 4 * h) * 8) : make_uint4(0, 0, 0, 0);
+    }
+    uint32_t act[2][2][4];                           // [pixel row][channel half][word = channel pair]
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t u[4] = {raw[r][h].x, raw[r][h].y, raw[r][h].z, raw[r][h].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float lo = fmaxf(fmaf(__uint_as_float(u[i] << 16), sc[h][2 * i], sh[h][2 * i]), 0.f);
+          const float hi = fmaxf(fmaf(__uint_as_float(u[i] & 0xffff0000u), sc[h][2 * i + 1], sh[h][2 * i + 1]), 0.f);
+          act[r][h][i] = pack_bf16x2(lo, hi);
+        }
+      }
+    }
+    if (a) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (p0 < npix)
+          *reinterpret_cast<uint4*>(a + p0 * ald + (tig + 4 * h) * 8) = make_uint4(act[0][h][0], act[0][h][1], act[0][h][2], act[0][h][3]);
+        if (p1 < npix)
+          *reinterpret_cast<uint4*>(a + p1 * ald + (tig + 4 * h) * 8) = make_uint4(act[1][h][0], act[1][h][1], act[1][h][2], act[1][h][3]);
+      }
+    }
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int h = j >> 1, w0 = 2 * (j & 1);
+      mma_m16n8k16_bf16(c, act[0][h][w0], act[1][h][w0], act[0][h][w0 + 1], act[1][h][w0 + 1], bfrag[j][0], bfrag[j][1]);
+    }
+    // columns 4..7 (lanes tig 2,3) hold the lo-half products of classes 0..3: fold them onto lanes tig 0,1
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] += __shfl_down_sync(0xffffffffu, c[i], 2, 4);
+    if (tig < 2) {
+      const int k0 = 2 * tig;
+      if (p0 < npix) {
+        const uint32_t p32 = (uint32_t)p0, img = p32 / hw, off = p32 - img * hw;
+        if (k0 < DOUT) logits[((size_t)img * DOUT + k0) * hw + off] = c[0] + b0;
+        if (k0 + 1 < DOUT) logits[((size_t)img * DOUT + k0 + 1) * hw + off] = c[1] + b1;
+      }
+      if (p1 < npix) {
+        const uint32_t p32 = (uint32_t)p1, img = p32 / hw, off = p32 - img * hw;
+        if (k0 < DOUT) logits[((size_t)img * DOUT + k0) * hw + off] = c[2] + b0;
+        if (k0 + 1 < DOUT) logits[((size_t)img * DOUT + k0 + 1) * hw + off] = c[3] + b1;
+      }
+    }
+  }
+}
+
 static int check_head_bn(const unetk_head_bn_bwd_args* a) {
   UNETK_REQUIRE(a != nullptr, "head_bn_bwd: null args");
   UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "head_bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
@@ -938,13 +1055,21 @@ int unetk_bn_relu_head_fprop(const unetk_tensor* z, const float* scale, const fl
   UNETK_REQUIRE(pixels(*z) < (1LL << 31), "bn_relu_head_fprop: more than 2^31 pixels");
   const int64_t npix = pixels(*z);
   const int grid = grid_for(npix);   // one thread per pixel: a warp owns 32 pixels per round
-  UNETK_DISPATCH_DTYPE(z->dtype, T, {
+  if (z->dtype == UNETK_BF16) {
+    // tensor-core formulation of the dot products (16 pixels per warp and round)
+    const int grid_mma = grid_for((npix + 15) / 16 * 32);
     UNETK_DISPATCH_DOUT(dout, D, {
-      bn_relu_head_kernel<T, D><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-          (const T*)z->ptr, z->ld, scale, shift, store_a ? (T*)a->ptr : nullptr, store_a ? a->ld : 0, w_head, b_head,
+      bn_relu_head_mma_kernel<D><<<grid_mma, kThreads, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)z->ptr, z->ld, scale, shift, store_a ? (__nv_bfloat16*)a->ptr : nullptr, store_a ? a->ld : 0,
+          w_head, b_head, logits_nchw, npix, (uint32_t)(z->h * z->w));
+    });
+  } else {
+    UNETK_DISPATCH_DOUT(dout, D, {
+      bn_relu_head_kernel<float, D><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+          (const float*)z->ptr, z->ld, scale, shift, store_a ? (float*)a->ptr : nullptr, store_a ? a->ld : 0, w_head, b_head,
           logits_nchw, npix, (uint32_t)(z->h * z->w));
     });
-  });
+  }
   UNETK_LAUNCH_CHECK();
   return UNETK_OK;
 }
