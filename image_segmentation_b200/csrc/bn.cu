@@ -849,6 +849,126 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// bf16 tier, C = 64: head backward apply with da = dlogits . (scale * Wh) on the tensor cores.  Same thread <-> data mapping
+// idea as bn_relu_head_mma_kernel, transposed: here the MMA's M = 16 pixels, K = 16 holds the (class, hi/lo) terms and
+// N = 8 a permuted set of channels, chosen so that the C fragments a thread receives are exactly the two 16-byte channel
+// groups (tig and tig + 4) of the pixels (gid, gid + 8) it loads z for and stores dz to:
+//   column n of N tile i  <->  channel 8 * G(n) + i,  G(2t) = t, G(2t + 1) = t + 4
+//   K slots 0-3: hi(dl_k) * hi(W_k), 4-7: hi(dl_k) * lo(W_k), 8-11: lo(dl_k) * hi(W_k), 12-15: unused   (fp32-level accuracy)
+template <int DOUT>
+__global__ void __launch_bounds__(128, 3)
+    head_bn_bwd_apply_mma_kernel(const __nv_bfloat16* __restrict__ z, int zld, int64_t npix, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, const float* __restrict__ mean,
+                                 const float* __restrict__ invstd, const float* __restrict__ dl, uint32_t hw,
+                                 const float* __restrict__ wh, const double* __restrict__ sums, double inv_count,
+                                 __nv_bfloat16* __restrict__ dz, int dzld, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                 float* __restrict__ dwh, float* __restrict__ dbh) {
+  constexpr int C = 64;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  if (blockIdx.x == 0 && threadIdx.x < C) {
+    const int ch = threadIdx.x;
+    if (dgamma) dgamma[ch] = (float)sums[C + ch];
+    if (dbeta) dbeta[ch] = (float)sums[ch];
+#pragma unroll
+    for (int q = 0; q < DOUT; ++q) dwh[(size_t)q * C + ch] = (float)sums[(size_t)(2 + q) * C + ch];
+    if (ch < DOUT && dbh) dbh[ch] = (float)sums[(size_t)(2 + DOUT) * C + ch];
+  }
+  // per-channel constants of this thread's 16 channels (groups tig and tig + 4)
+  float sc[2][8], sh[2][8], cb[2][8], cc[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int g = tig + 4 * h;
+    float mu[8], is[8];
+    load8(scale + g * 8, sc[h]);
+    load8(shift + g * 8, sh[h]);
+    load8(mean + g * 8, mu);
+    load8(invstd + g * 8, is);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float m1 = (float)(sums[g * 8 + k] * inv_count);
+      const float m2 = (float)(sums[C + g * 8 + k] * inv_count);
+      cb[h][k] = -sc[h][k] * m2 * is[k];
+      cc[h][k] = sc[h][k] * (m2 * is[k] * mu[k] - m1);
+    }
+  }
+  // B fragments (constant): N tile i, column n = gid <-> channel 8 * G(gid) + i; register r covers K slots 2*tig + {0,1} + 8*r
+  uint32_t bfrag[8][2];
+  {
+    const int grp = (gid >> 1) + 4 * (gid & 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int ch = 8 * grp + i;
+      const float s_ch = scale[ch];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int slot = 2 * tig + e + 8 * r, k = slot & 3, part = slot >> 2;   // part 0: hi(W), 1: lo(W), 2: hi(W), 3: unused
+          float w = (k < DOUT && part < 3) ? wh[(size_t)k * C + ch] * s_ch : 0.f;
+          if (part == 1) w -= __bfloat162float(__float2bfloat16_rn(w));
+          v[e] = w;
+        }
+        bfrag[i][r] = pack_bf16x2(v[0], v[1]);
+      }
+    }
+  }
+  const int k0 = 2 * (tig & 1);                        // the two classes this thread feeds into the A fragments
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+    const int64_t p[2] = {base + gid, base + gid + 8};
+    uint4 raw[2][2];
+    float d[2][2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const bool ok = p[r] < npix;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        raw[r][h] = ok ? *reinterpret_cast<const uint4*>(z + p[r] * zld + (tig + 4 * h) * 8) : make_uint4(0, 0, 0, 0);
+      const uint32_t p32 = (uint32_t)(ok ? p[r] : 0), img = p32 / hw, off = p32 - img * hw;
+      const float* b = dl + ((size_t)img * DOUT) * hw + off;
+      d[r][0] = (ok && k0 < DOUT) ? __ldg(b + (size_t)k0 * hw) : 0.f;
+      d[r][1] = (ok && k0 + 1 < DOUT) ? __ldg(b + (size_t)(k0 + 1) * hw) : 0.f;
+    }
+    // A fragments: rows = pixels, K slots 2*tig + {0,1}: hi(dl) (slots 0-7); slots 8 + 2*tig + {0,1}: lo(dl) for tig < 2
+    uint32_t afr[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float h0 = __bfloat162float(__float2bfloat16_rn(d[r][0])), h1 = __bfloat162float(__float2bfloat16_rn(d[r][1]));
+      afr[r] = pack_bf16x2(h0, h1);
+      afr[2 + r] = tig < 2 ? pack_bf16x2(d[r][0] - h0, d[r][1] - h1) : 0u;
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+      mma_m16n8k16_bf16(acc[i], afr[0], afr[1], afr[2], afr[3], bfrag[i][0], bfrag[i][1]);
+    }
+    // acc[i][2*r + h] = da of pixel p[r], channel 8 * (tig + 4*h) + i
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (p[r] < npix) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t u[4] = {raw[r][h].x, raw[r][h].y, raw[r][h].z, raw[r][h].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float z0 = __uint_as_float(u[w] << 16), z1 = __uint_as_float(u[w] & 0xffff0000u);
+            const int i0 = 2 * w, i1 = 2 * w + 1;
+            float v0 = fmaf(cb[h][i0], z0, cc[h][i0]), v1 = fmaf(cb[h][i1], z1, cc[h][i1]);
+            if (fmaf(z0, sc[h][i0], sh[h][i0]) > act_threshold<__nv_bfloat16>()) v0 += acc[i0][2 * r + h];
+            if (fmaf(z1, sc[h][i1], sh[h][i1]) > act_threshold<__nv_bfloat16>()) v1 += acc[i1][2 * r + h];
+            o[w] = pack_bf16x2(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(dz + p[r] * dzld + (tig + 4 * h) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+}
+
 static int check_head_bn(const unetk_head_bn_bwd_args* a) {
   UNETK_REQUIRE(a != nullptr, "head_bn_bwd: null args");
   UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "head_bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
@@ -1026,6 +1146,21 @@ int unetk_head_bn_bwd_apply(const unetk_head_bn_bwd_args* a, void* stream) {
   UNETK_REQUIRE((npix + ipb - 1) / ipb <= 65535, "head_bn_bwd_apply: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((npix + ipb - 1) / ipb));
   const double inv_count = 1.0 / (double)npix;
+  if (a->z.dtype == UNETK_BF16 && a->z.c == 64) {
+    // tensor-core formulation (the U-Net head: 64 channels): 16 pixels per warp and round
+    const int64_t warps = (npix + 15) / 16;
+    int64_t blocks = (warps * 32 + 127) / 128;
+    const int64_t cap = (int64_t)sm_count() * 12;
+    if (blocks > cap) blocks = cap;
+    UNETK_DISPATCH_DOUT(a->dout, D, {
+      head_bn_bwd_apply_mma_kernel<D><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)a->z.ptr, a->z.ld, npix, a->scale, a->shift, a->mean, a->invstd, a->dlogits,
+          (uint32_t)(a->z.h * a->z.w), a->w_head, a->sums, inv_count, (__nv_bfloat16*)a->dz.ptr, a->dz.ld, a->dgamma, a->dbeta,
+          a->dw_head, a->db_head);
+    });
+    UNETK_LAUNCH_CHECK();
+    return UNETK_OK;
+  }
   UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
     UNETK_DISPATCH_DOUT(a->dout, D, {
       HeadGrad<D> hg;
