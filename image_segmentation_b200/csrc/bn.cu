@@ -969,6 +969,123 @@ __global__ void __launch_bounds__(128, 3)
   }
 }
 
+// bf16 tier, C = 64: the reduction pass with the per-class sums on the tensor cores.  M[k][c] = sum_p mask * dl[p][k] and
+// Z[k][c] = sum_p mask * dl[p][k] * z[p][c] are matrix products over the PIXEL dimension: A = dl^T (rows 0-3 hi(dl_k), rows 4-7
+// lo(dl_k): fp32-level accuracy), K = 16 pixels of a warp's block, B = mask (as 1.0 / 0) resp. mask * z (exact in bf16), N = 8
+// channels.  Lane (gid, tig) loads the 16-byte channel group `gid` of the four pixels 2*tig + {0,1,8,9} -- the K slots of its
+// B fragments -- so that element i of that group is the thread's value in column gid of N tile i (tile i <-> channels 8n + i);
+// two byte-permutes per tile build the fragments from the masked words.  32 accumulators per quantity stay in registers for
+// the whole grid-stride loop; hi + lo rows meet through one shuffle, warps through shared memory in a fixed order, blocks
+// through fp64 atomics as before.
+template <int DOUT>
+__global__ void __launch_bounds__(128, 3)
+    head_bn_bwd_reduce_mma_kernel(const __nv_bfloat16* __restrict__ z, int zld, int64_t npix, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const float* __restrict__ mean,
+                                  const float* __restrict__ invstd, const float* __restrict__ dl, uint32_t hw,
+                                  const float* __restrict__ wh, double* __restrict__ sums) {
+  constexpr int C = 64;
+  __shared__ float part[4][2 * DOUT + 1][C];           // [warp][M_k | Z_k | db][channel]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  const int k = gid & 3;
+  const bool lo_row = gid >= 4;
+  float sc[8], sh[8];
+  load8(scale + gid * 8, sc);
+  load8(shift + gid * 8, sh);
+  float accM[8][4], accZ[8][4], accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) accM[i][q] = accZ[i][q] = 0.f;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+    uint32_t zw[4][4], ow[4][4];                       // masked z words / mask-as-1.0 words, [pixel slot][channel pair]
+    float d[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t p = base + 2 * tig + (j & 1) + 8 * (j >> 1);
+      const bool ok = p < npix;
+      const uint4 raw = ok ? *reinterpret_cast<const uint4*>(z + p * zld + gid * 8) : make_uint4(0, 0, 0, 0);
+      const uint32_t p32 = (uint32_t)(ok ? p : 0), img = p32 / hw, off = p32 - img * hw;
+      d[j] = (ok && k < DOUT) ? __ldg(dl + ((size_t)img * DOUT + k) * hw + off) : 0.f;
+      const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const bool m0 = fmaf(__uint_as_float(u[w] << 16), sc[2 * w], sh[2 * w]) > act_threshold<__nv_bfloat16>();
+        const bool m1 = fmaf(__uint_as_float(u[w] & 0xffff0000u), sc[2 * w + 1], sh[2 * w + 1]) > act_threshold<__nv_bfloat16>();
+        zw[j][w] = (m0 ? (u[w] & 0x0000ffffu) : 0u) | (m1 ? (u[w] & 0xffff0000u) : 0u);
+        ow[j][w] = (m0 ? 0x00003f80u : 0u) | (m1 ? 0x3f800000u : 0u);
+      }
+    }
+    if (!lo_row) accb += (d[0] + d[1]) + (d[2] + d[3]);
+    // A fragments: row gid = (class k, hi / lo half of dl); K slots = this thread's four pixels
+    float f[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float h = __bfloat162float(__float2bfloat16_rn(d[j]));
+      f[j] = lo_row ? d[j] - h : h;
+    }
+    const uint32_t a0 = pack_bf16x2(f[0], f[1]), a2 = pack_bf16x2(f[2], f[3]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int w = i >> 1;
+      const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
+      mma_m16n8k16_bf16(accZ[i], a0, 0u, a2, 0u, __byte_perm(zw[0][w], zw[1][w], sel), __byte_perm(zw[2][w], zw[3][w], sel));
+      mma_m16n8k16_bf16(accM[i], a0, 0u, a2, 0u, __byte_perm(ow[0][w], ow[1][w], sel), __byte_perm(ow[2][w], ow[3][w], sel));
+    }
+  }
+  // rows gid (hi) and gid + 4 (lo) of the same class: fold; the C fragment of tile i holds columns 2*tig + {0,1} <-> channels
+  // 16*tig + i and 16*tig + 8 + i
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      accM[i][q] += __shfl_down_sync(0xffffffffu, accM[i][q], 16);
+      accZ[i][q] += __shfl_down_sync(0xffffffffu, accZ[i][q], 16);
+    }
+  }
+  // bias gradient: sum over the four tig lanes of a class row (only the hi rows counted their pixels)
+  accb += __shfl_xor_sync(0xffffffffu, accb, 1);
+  accb += __shfl_xor_sync(0xffffffffu, accb, 2);
+  if (gid < 4 && gid < DOUT) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int ch = 16 * tig + 8 * q + i;
+        part[warp][gid][ch] = accM[i][q];
+        part[warp][DOUT + gid][ch] = accZ[i][q];
+      }
+    }
+    if (tig == 0) part[warp][2 * DOUT][gid] = accb;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int ch = threadIdx.x;
+    float M[DOUT], Z[DOUT];
+#pragma unroll
+    for (int q = 0; q < DOUT; ++q) {
+      M[q] = (part[0][q][ch] + part[1][q][ch]) + (part[2][q][ch] + part[3][q][ch]);
+      Z[q] = (part[0][DOUT + q][ch] + part[1][DOUT + q][ch]) + (part[2][DOUT + q][ch] + part[3][DOUT + q][ch]);
+    }
+    const float scc = scale[ch], shc = shift[ch], mu = mean[ch], is = invstd[ch];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < DOUT; ++q) {
+      const float w = wh[(size_t)q * C + ch];
+      s1 = fmaf(w, M[q], s1);
+      s2 = fmaf(w, Z[q], s2);
+      atomicAdd(sums + (size_t)(2 + q) * C + ch, (double)fmaf(scc, Z[q], shc * M[q]));
+    }
+    atomicAdd(sums + ch, (double)s1);
+    atomicAdd(sums + C + ch, (double)(is * (s2 - mu * s1)));
+    if (ch < DOUT) {
+      const float db = (part[0][2 * DOUT][ch] + part[1][2 * DOUT][ch]) + (part[2][2 * DOUT][ch] + part[3][2 * DOUT][ch]);
+      atomicAdd(sums + (size_t)(2 + DOUT) * C + ch, (double)db);
+    }
+  }
+}
+
 static int check_head_bn(const unetk_head_bn_bwd_args* a) {
   UNETK_REQUIRE(a != nullptr, "head_bn_bwd: null args");
   UNETK_REQUIRE(tensor_ok(a->z) && vec8_ok(a->z), "head_bn_bwd: z must be NHWC with c%%8==0, ld%%8==0, 16B aligned");
@@ -1117,6 +1234,20 @@ int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream) {
   if ((npix + ipb - 1) / ipb > 65535) ipb *= 16;
   UNETK_REQUIRE((npix + ipb - 1) / ipb <= 65535, "head_bn_bwd_reduce: tensor too large");
   dim3 grid(cg / cgb, (unsigned)((npix + ipb - 1) / ipb));
+  if (a->z.dtype == UNETK_BF16 && a->z.c == 64) {
+    // tensor-core formulation (the U-Net head: 64 channels): persistent grid, 16 pixels per warp and round
+    const int64_t warps = (npix + 15) / 16;
+    int64_t blocks = (warps + 3) / 4;
+    const int64_t cap = (int64_t)sm_count() * 3;
+    if (blocks > cap) blocks = cap;
+    UNETK_DISPATCH_DOUT(a->dout, D, {
+      head_bn_bwd_reduce_mma_kernel<D><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)a->z.ptr, a->z.ld, npix, a->scale, a->shift, a->mean, a->invstd, a->dlogits,
+          (uint32_t)(a->z.h * a->z.w), a->w_head, a->sums);
+    });
+    UNETK_LAUNCH_CHECK();
+    return UNETK_OK;
+  }
   UNETK_DISPATCH_DTYPE(a->z.dtype, T, {
     UNETK_DISPATCH_DOUT(a->dout, D, {
       HeadGrad<D> hg;
