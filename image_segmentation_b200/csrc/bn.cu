@@ -749,8 +749,37 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, ui
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// (image, offset) of a warp's 16-pixel block inside the NCHW planes of hw pixels, advanced from round to round of a
+// grid-stride loop without a division (the divisions by the runtime hw were half the instructions of the head loops).
+struct BlockCursor {
+  uint32_t img, off, step_img, step_off, hw;
+  __device__ __forceinline__ BlockCursor(int64_t base, int64_t stride, uint32_t hw_) : hw(hw_) {
+    img = (uint32_t)(base / hw_);
+    off = (uint32_t)(base - (int64_t)img * hw_);
+    step_img = (uint32_t)(stride / hw_);
+    step_off = (uint32_t)(stride - (int64_t)step_img * hw_);
+  }
+  __device__ __forceinline__ void advance() {
+    img += step_img;
+    off += step_off;
+    if (off >= hw) {
+      off -= hw;
+      ++img;
+    }
+  }
+  // pixel (block base + t), t < 16
+  __device__ __forceinline__ void at(uint32_t t, uint32_t& i, uint32_t& o) const {
+    i = img;
+    o = off + t;
+    while (o >= hw) {
+      o -= hw;
+      ++i;
+    }
+  }
+};
+
 template <int DOUT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
     bn_relu_head_mma_kernel(const __nv_bfloat16* __restrict__ z, int zld, const float* __restrict__ scale,
                             const float* __restrict__ shift, __nv_bfloat16* __restrict__ a, int ald,
                             const float* __restrict__ wh, const float* __restrict__ bh, float* __restrict__ logits,
@@ -793,7 +822,8 @@ __global__ void __launch_bounds__(kThreads)
   // after the hi + lo fold, lane tig 0 holds classes 0,1 and lane tig 1 classes 2,3
   const float b0 = (bh && 2 * tig < DOUT) ? bh[2 * tig] : 0.f;
   const float b1 = (bh && 2 * tig + 1 < DOUT) ? bh[2 * tig + 1] : 0.f;
-  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+  BlockCursor cur(warp_id * 16, nwarps * 16, hw);
+  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16, cur.advance()) {
     const int64_t p0 = base + gid, p1 = base + gid + 8;
     uint4 raw[2][2];                                 // [pixel row][channel half]
 #pragma unroll
@@ -835,13 +865,14 @@ __global__ void __launch_bounds__(kThreads)
     for (int i = 0; i < 4; ++i) c[i] += __shfl_down_sync(0xffffffffu, c[i], 2, 4);
     if (tig < 2) {
       const int k0 = 2 * tig;
+      uint32_t img, off;
       if (p0 < npix) {
-        const uint32_t p32 = (uint32_t)p0, img = p32 / hw, off = p32 - img * hw;
+        cur.at(gid, img, off);
         if (k0 < DOUT) logits[((size_t)img * DOUT + k0) * hw + off] = c[0] + b0;
         if (k0 + 1 < DOUT) logits[((size_t)img * DOUT + k0 + 1) * hw + off] = c[1] + b1;
       }
       if (p1 < npix) {
-        const uint32_t p32 = (uint32_t)p1, img = p32 / hw, off = p32 - img * hw;
+        cur.at(gid + 8, img, off);
         if (k0 < DOUT) logits[((size_t)img * DOUT + k0) * hw + off] = c[2] + b0;
         if (k0 + 1 < DOUT) logits[((size_t)img * DOUT + k0 + 1) * hw + off] = c[3] + b1;
       }
@@ -916,7 +947,8 @@ __global__ void __launch_bounds__(128, 3)
   const int k0 = 2 * (tig & 1);                        // the two classes this thread feeds into the A fragments
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+  BlockCursor cur(warp_id * 16, nwarps * 16, hw);
+  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16, cur.advance()) {
     const int64_t p[2] = {base + gid, base + gid + 8};
     uint4 raw[2][2];
     float d[2][2];
@@ -926,7 +958,8 @@ __global__ void __launch_bounds__(128, 3)
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         raw[r][h] = ok ? *reinterpret_cast<const uint4*>(z + p[r] * zld + (tig + 4 * h) * 8) : make_uint4(0, 0, 0, 0);
-      const uint32_t p32 = (uint32_t)(ok ? p[r] : 0), img = p32 / hw, off = p32 - img * hw;
+      uint32_t img, off;
+      cur.at(gid + 8 * r, img, off);
       const float* b = dl + ((size_t)img * DOUT) * hw + off;
       d[r][0] = (ok && k0 < DOUT) ? __ldg(b + (size_t)k0 * hw) : 0.f;
       d[r][1] = (ok && k0 + 1 < DOUT) ? __ldg(b + (size_t)(k0 + 1) * hw) : 0.f;
@@ -970,95 +1003,202 @@ __global__ void __launch_bounds__(128, 3)
 }
 
 // bf16 tier, C = 64: the reduction pass with the per-class sums on the tensor cores.  M[k][c] = sum_p mask * dl[p][k] and
-// Z[k][c] = sum_p mask * dl[p][k] * z[p][c] are matrix products over the PIXEL dimension: A = dl^T (rows 0-3 hi(dl_k), rows 4-7
-// lo(dl_k): fp32-level accuracy), K = 16 pixels of a warp's block, B = mask (as 1.0 / 0) resp. mask * z (exact in bf16), N = 8
-// channels.  Lane (gid, tig) loads the 16-byte channel group `gid` of the four pixels 2*tig + {0,1,8,9} -- the K slots of its
-// B fragments -- so that element i of that group is the thread's value in column gid of N tile i (tile i <-> channels 8n + i);
-// two byte-permutes per tile build the fragments from the masked words.  32 accumulators per quantity stay in registers for
-// the whole grid-stride loop; hi + lo rows meet through one shuffle, warps through shared memory in a fixed order, blocks
-// through fp64 atomics as before.
+// Z[k][c] = sum_p mask * dl[p][k] * z[p][c] are matrix products over the PIXEL dimension (K = the 16 pixels of a warp's
+// block): A = the mask as 1.0 / 0 resp. mask * z (both exact in bf16) with 16 channels as rows, B = dl with the 8 columns
+// (class k, hi / lo half of the fp32 value: fp32-level accuracy).  Lane (gid, tig) reads the 16-byte channel group `gid` of
+// the four pixels 2*tig + {0,1,8,9} -- exactly the K slots of its fragments -- and M tile t takes channels 8*gid + 2t (row
+// gid) and 8*gid + 2t + 1 (row gid + 8), so two byte-permutes per register build the A fragments from the masked words.
+// The 32 accumulators live in registers for the whole grid-stride loop; hi + lo columns meet through one shuffle, warps
+// through shared memory in a fixed order, blocks through fp64 atomics.  z and dl reach the warp through a private
+// 4-stage cp.async ring (a 16-pixel block = 2 KB of z + 16 * dout floats), so three blocks per warp are in flight while one
+// is being reduced: the loop is issue-bound, not latency-bound.
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
+               "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct HeadStage {
+  uint4 z[16][8];                                      // [pixel][channel group ^ swizzle]
+  float d[4][16];                                      // [class][pixel]
+};
+constexpr int kHeadStages = 4;
+
+// Producer side of the ring: the warp copies one 16-pixel block per round.  Lane l moves the 16-byte chunks l + 32 r
+// (pixel (l >> 3) + 4 r, channel group l & 7) and the dl values of pixel l & 15 for the classes (l >> 4) and (l >> 4) + 2.
+// Whole blocks that do not straddle two images (hw % 16 == 0: every real head) take the short path: a running source
+// pointer and per-lane destination offsets fixed before the loop; the tail block and odd plane sizes take the general one.
 template <int DOUT>
-__global__ void __launch_bounds__(128, 3)
+struct HeadFill {
+  const char* zsrc;                                    // this lane's first chunk of the block to fetch next
+  int64_t zstep, base, stride, npix;
+  uint32_t zrow4, zdst[4], ddst;                       // bytes between the chunks of a lane; offsets inside a stage
+  const float* dl;
+  const __nv_bfloat16* z;
+  int zld, lane;
+  bool aligned;
+  BlockCursor cur;
+  __device__ __forceinline__ HeadFill(const __nv_bfloat16* z_, int zld_, const float* dl_, int64_t base_, int64_t stride_,
+                                      int64_t npix_, uint32_t hw, int lane_)
+      : base(base_), stride(stride_), npix(npix_), dl(dl_), z(z_), zld(zld_), lane(lane_), cur(base_, stride_, hw) {
+    zsrc = reinterpret_cast<const char*>(z_ + (base_ + (lane_ >> 3)) * zld_ + (lane_ & 7) * 8);
+    zstep = stride_ * zld_ * 2;
+    zrow4 = 4u * (uint32_t)zld_ * 2u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int px = (lane_ >> 3) + 4 * r, g = lane_ & 7;
+      zdst[r] = (uint32_t)(px * 128 + ((g ^ (2 * ((px >> 1) & 3))) * 16));
+    }
+    ddst = (uint32_t)(sizeof(uint4) * 16 * 8 + ((lane_ >> 4) * 16 + (lane_ & 15)) * 4);
+    aligned = (hw & 15u) == 0;
+  }
+  __device__ __forceinline__ void issue(uint32_t stage_addr) {
+    if (base < npix) {
+      if (aligned && base + 16 <= npix) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(stage_addr + zdst[r]), "l"(zsrc + (size_t)r * zrow4));
+        const float* src = dl + ((size_t)cur.img * DOUT + (lane >> 4)) * cur.hw + cur.off + (lane & 15);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(stage_addr + ddst), "l"(src));
+        if ((lane >> 4) + 2 < DOUT)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(stage_addr + ddst + 128u), "l"(src + 2 * (size_t)cur.hw));
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int64_t p = base + (lane >> 3) + 4 * r;
+          const bool ok = p < npix;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(stage_addr + zdst[r]),
+                       "l"(z + (ok ? p : 0) * zld + (lane & 7) * 8), "r"(ok ? 16 : 0));
+        }
+        const int t = lane & 15;
+        const bool ok = base + t < npix;
+        uint32_t img = 0, off = 0;
+        if (ok) cur.at(t, img, off);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int k = (lane >> 4) + 2 * r;
+          if (k < DOUT)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(stage_addr + ddst + 128u * r),
+                         "l"(dl + ((size_t)img * DOUT + k) * cur.hw + off), "r"(ok ? 4 : 0));
+        }
+      }
+    }
+    cp_async_commit();
+    base += stride;
+    zsrc += zstep;
+    cur.advance();
+  }
+};
+
+template <int DOUT>
+__global__ void __launch_bounds__(128, 4)
     head_bn_bwd_reduce_mma_kernel(const __nv_bfloat16* __restrict__ z, int zld, int64_t npix, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const float* __restrict__ mean,
                                   const float* __restrict__ invstd, const float* __restrict__ dl, uint32_t hw,
                                   const float* __restrict__ wh, double* __restrict__ sums) {
-  constexpr int C = 64;
-  __shared__ float part[4][2 * DOUT + 1][C];           // [warp][M_k | Z_k | db][channel]
+  constexpr int C = 64, S = kHeadStages;
+  __shared__ __align__(16) HeadStage ring_mem[4 * S];
+  static_assert(sizeof(HeadStage) * 4 * S >= sizeof(float) * 4 * (2 * 4 + 1) * C, "the warp partials reuse the ring");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  HeadStage* ring = ring_mem + warp * S;
   const int k = gid & 3;
-  const bool lo_row = gid >= 4;
+  const bool lo_col = gid >= 4;
   float sc[8], sh[8];
   load8(scale + gid * 8, sc);
   load8(shift + gid * 8, sh);
-  float accM[8][4], accZ[8][4], accb = 0.f;
+  float accM[4][4], accZ[4][4], accb = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int t = 0; t < 4; ++t)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) accM[i][q] = accZ[i][q] = 0.f;
+    for (int q = 0; q < 4; ++q) accM[t][q] = accZ[t][q] = 0.f;
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = warp_id * 16; base < npix; base += nwarps * 16) {
+  const int64_t stride = nwarps * 16;
+  // producer side of the ring runs S - 1 blocks ahead of the consumer
+  HeadFill<DOUT> fill(z, zld, dl, warp_id * 16, stride, npix, hw, lane);
+  const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring);
+#pragma unroll
+  for (int s = 0; s < S - 1; ++s) fill.issue(ring_addr + s * (uint32_t)sizeof(HeadStage));
+  int stage = 0;
+  for (int64_t base = warp_id * 16; base < npix; base += stride) {
+    // refill the stage the previous round finished reading
+    fill.issue(ring_addr + (uint32_t)(stage == 0 ? S - 1 : stage - 1) * (uint32_t)sizeof(HeadStage));
+    cp_async_wait<S - 1>();
+    __syncwarp();
+    const HeadStage& st = ring[stage];
     uint32_t zw[4][4], ow[4][4];                       // masked z words / mask-as-1.0 words, [pixel slot][channel pair]
     float d[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t p = base + 2 * tig + (j & 1) + 8 * (j >> 1);
-      const bool ok = p < npix;
-      const uint4 raw = ok ? *reinterpret_cast<const uint4*>(z + p * zld + gid * 8) : make_uint4(0, 0, 0, 0);
-      const uint32_t p32 = (uint32_t)(ok ? p : 0), img = p32 / hw, off = p32 - img * hw;
-      d[j] = (ok && k < DOUT) ? __ldg(dl + ((size_t)img * DOUT + k) * hw + off) : 0.f;
+      const int px = 2 * tig + (j & 1) + 8 * (j >> 1);
+      const uint4 raw = st.z[px][gid ^ (2 * tig)];
+      d[j] = k < DOUT ? st.d[k][px] : 0.f;
       const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
         const bool m0 = fmaf(__uint_as_float(u[w] << 16), sc[2 * w], sh[2 * w]) > act_threshold<__nv_bfloat16>();
         const bool m1 = fmaf(__uint_as_float(u[w] & 0xffff0000u), sc[2 * w + 1], sh[2 * w + 1]) > act_threshold<__nv_bfloat16>();
-        zw[j][w] = (m0 ? (u[w] & 0x0000ffffu) : 0u) | (m1 ? (u[w] & 0xffff0000u) : 0u);
-        ow[j][w] = (m0 ? 0x00003f80u : 0u) | (m1 ? 0x3f800000u : 0u);
+        const uint32_t mb = (m0 ? 0x0000ffffu : 0u) | (m1 ? 0xffff0000u : 0u);
+        zw[j][w] = u[w] & mb;
+        ow[j][w] = 0x3f803f80u & mb;
       }
     }
-    if (!lo_row) accb += (d[0] + d[1]) + (d[2] + d[3]);
-    // A fragments: row gid = (class k, hi / lo half of dl); K slots = this thread's four pixels
+    if (!lo_col) accb += (d[0] + d[1]) + (d[2] + d[3]);
+    // B fragment: column gid = (class k, hi / lo half of dl); K slots = this thread's four pixels
     float f[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float h = __bfloat162float(__float2bfloat16_rn(d[j]));
-      f[j] = lo_row ? d[j] - h : h;
+      f[j] = lo_col ? d[j] - h : h;
     }
-    const uint32_t a0 = pack_bf16x2(f[0], f[1]), a2 = pack_bf16x2(f[2], f[3]);
+    const uint32_t b0 = pack_bf16x2(f[0], f[1]), b1 = pack_bf16x2(f[2], f[3]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int w = i >> 1;
-      const uint32_t sel = (i & 1) ? 0x7632u : 0x5410u;
-      mma_m16n8k16_bf16(accZ[i], a0, 0u, a2, 0u, __byte_perm(zw[0][w], zw[1][w], sel), __byte_perm(zw[2][w], zw[3][w], sel));
-      mma_m16n8k16_bf16(accM[i], a0, 0u, a2, 0u, __byte_perm(ow[0][w], ow[1][w], sel), __byte_perm(ow[2][w], ow[3][w], sel));
+    for (int t = 0; t < 4; ++t) {
+      mma_m16n8k16_bf16(accZ[t], __byte_perm(zw[0][t], zw[1][t], 0x5410u), __byte_perm(zw[0][t], zw[1][t], 0x7632u),
+                        __byte_perm(zw[2][t], zw[3][t], 0x5410u), __byte_perm(zw[2][t], zw[3][t], 0x7632u), b0, b1);
+      mma_m16n8k16_bf16(accM[t], __byte_perm(ow[0][t], ow[1][t], 0x5410u), __byte_perm(ow[0][t], ow[1][t], 0x7632u),
+                        __byte_perm(ow[2][t], ow[3][t], 0x5410u), __byte_perm(ow[2][t], ow[3][t], 0x7632u), b0, b1);
+    }
+    __syncwarp();                                      // every lane is done with this stage before it is refilled
+    stage = stage + 1 == S ? 0 : stage + 1;
+  }
+  cp_async_wait<0>();
+  // columns 2*tig + {0,1}: tig 0,1 hold the hi halves of classes (0,1) / (2,3), tig 2,3 the lo halves: fold
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      accM[t][q] += __shfl_down_sync(0xffffffffu, accM[t][q], 2);
+      accZ[t][q] += __shfl_down_sync(0xffffffffu, accZ[t][q], 2);
     }
   }
-  // rows gid (hi) and gid + 4 (lo) of the same class: fold; the C fragment of tile i holds columns 2*tig + {0,1} <-> channels
-  // 16*tig + i and 16*tig + 8 + i
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      accM[i][q] += __shfl_down_sync(0xffffffffu, accM[i][q], 16);
-      accZ[i][q] += __shfl_down_sync(0xffffffffu, accZ[i][q], 16);
-    }
-  }
-  // bias gradient: sum over the four tig lanes of a class row (only the hi rows counted their pixels)
+  // bias gradient: sum over the four tig lanes of a class column (only the hi columns counted their pixels)
   accb += __shfl_xor_sync(0xffffffffu, accb, 1);
   accb += __shfl_xor_sync(0xffffffffu, accb, 2);
-  if (gid < 4 && gid < DOUT) {
+  __syncthreads();                                     // all warps are done with their rings: reuse them for the partials
+  float(*part)[2 * DOUT + 1][C] = reinterpret_cast<float(*)[2 * DOUT + 1][C]>(ring_mem);   // [warp][M_k | Z_k | db][channel]
+  if (tig < 2) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int t = 0; t < 4; ++t) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int ch = 16 * tig + 8 * q + i;
-        part[warp][gid][ch] = accM[i][q];
-        part[warp][DOUT + gid][ch] = accZ[i][q];
+      for (int q = 0; q < 4; ++q) {
+        const int ch = 8 * gid + 2 * t + (q >> 1), kk = 2 * tig + (q & 1);
+        if (kk < DOUT) {
+          part[warp][kk][ch] = accM[t][q];
+          part[warp][DOUT + kk][ch] = accZ[t][q];
+        }
       }
     }
-    if (tig == 0) part[warp][2 * DOUT][gid] = accb;
   }
+  if (gid < DOUT && tig == 0) part[warp][2 * DOUT][gid] = accb;
   __syncthreads();
   if (threadIdx.x < C) {
     const int ch = threadIdx.x;
@@ -1238,7 +1378,7 @@ int unetk_head_bn_bwd_reduce(const unetk_head_bn_bwd_args* a, void* stream) {
     // tensor-core formulation (the U-Net head: 64 channels): persistent grid, 16 pixels per warp and round
     const int64_t warps = (npix + 15) / 16;
     int64_t blocks = (warps + 3) / 4;
-    const int64_t cap = (int64_t)sm_count() * 3;
+    const int64_t cap = (int64_t)sm_count() * 4;
     if (blocks > cap) blocks = cap;
     UNETK_DISPATCH_DOUT(a->dout, D, {
       head_bn_bwd_reduce_mma_kernel<D><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
