@@ -251,7 +251,10 @@ def test_head_forward_backward(dt, dout):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 12, 20, 64), (4, 3, 6, 10, 128), (3, 1, 64, 64, 64)])
+@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 12, 20, 64), (4, 3, 6, 10, 128), (3, 1, 64, 64, 64),
+                                          # planes that are not multiples of the 16-pixel block / ragged last block /
+                                          # more than one round of the persistent grid with blocks straddling two images
+                                          (3, 2, 5, 7, 64), (2, 3, 37, 3, 64), (4, 1, 3, 3, 64), (3, 3, 150, 101, 64)])
 def test_fused_head_and_batchnorm_backward(dt, dout, n, h, w, c):
     """unetk_head_bn_bwd_reduce/apply against autograd (float64) through  z -> BN(batch stats) -> ReLU -> 1x1 head."""
     z = rnd((n, h, w, c), dt, 60)
@@ -293,7 +296,8 @@ def test_fused_head_and_batchnorm_backward(dt, dout, n, h, w, c):
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
-@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 5, 7, 64), (4, 1, 3, 3, 64), (3, 1, 64, 64, 64), (2, 3, 37, 3, 64)])
+@pytest.mark.parametrize("dout,n,h,w,c", [(1, 2, 16, 8, 64), (3, 2, 5, 7, 64), (4, 1, 3, 3, 64), (3, 1, 64, 64, 64), (2, 3, 37, 3, 64),
+                                          (3, 3, 150, 101, 64)])
 def test_fused_bn_relu_head_forward(dt, dout, n, h, w, c):
     """unetk_bn_relu_head_fprop == unetk_bn_relu_apply followed by unetk_head_fprop (same stored activation)."""
     z = rnd((n, h, w, c), dt, 70).to(DEV)
