@@ -58,6 +58,104 @@ __device__ __forceinline__ void store2(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(a, b);
 }
 
+// One 32 x 32 channel tile of a 3x3 conv (TAPS = 9) or 2x2 ConvT (TAPS = 4) weight.  Every loop has a compile-time trip
+// count and compile-time divisors, so the loads of a phase are all in flight before the first use; the parameter side moves
+// as float4 when its tile rows are 16-byte aligned.
+template <typename T, bool PACK, int TAPS>
+__device__ __forceinline__ void weights_tile(const unetk_wjob& j, int a0, int b0, int tid, float (&sm)[kWT][kWT * 9 + 1]) {
+  constexpr int RUN = kWT * TAPS;                   // contiguous floats per `a` row of the parameter tile
+  constexpr int kVecIters = kWT * RUN / 4 / 256;    // 9 (3x3) / 4 (ConvT)
+  static_assert(kWT * RUN % (4 * 256) == 0, "tile must split into whole float4 rounds");
+  // parameter layout: [a][b][taps] with a = co (conv) / ci (convT);  A = rows, B = columns
+  const int B = TAPS == 9 ? j.cin : j.cout;
+  if (PACK) {
+    const float* param = reinterpret_cast<const float*>(j.src);
+    if ((reinterpret_cast<uintptr_t>(param) & 15) == 0 && ((size_t)B * TAPS) % 4 == 0) {
+      float4 v[kVecIters];
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        const int i = tid + it * 256, al = i / (RUN / 4), e4 = i % (RUN / 4);
+        v[it] = *reinterpret_cast<const float4*>(param + ((size_t)(a0 + al) * B + b0) * TAPS + 4 * e4);
+      }
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        const int i = tid + it * 256, al = i / (RUN / 4), e4 = i % (RUN / 4);
+        sm[al][4 * e4] = v[it].x;
+        sm[al][4 * e4 + 1] = v[it].y;
+        sm[al][4 * e4 + 2] = v[it].z;
+        sm[al][4 * e4 + 3] = v[it].w;
+      }
+    } else {
+#pragma unroll 12
+      for (int i = tid; i < kWT * RUN; i += 256) {
+        const int al = i / RUN, e = i % RUN;
+        sm[al][e] = param[((size_t)(a0 + al) * B + b0) * TAPS + e];
+      }
+    }
+    __syncthreads();
+    T* wf = reinterpret_cast<T*>(j.dst0);
+    T* wd = reinterpret_cast<T*>(j.dst1);
+    // two adjacent elements per store (4 bytes of bf16 / 8 bytes of fp32)
+#pragma unroll
+    for (int i = tid; i < kWT * TAPS * (kWT / 2); i += 256) {
+      const int cp = i % (kWT / 2), t = (i / (kWT / 2)) % TAPS, row = i / (TAPS * (kWT / 2));
+      if (TAPS == 9) {
+        // wf[co][t][ci]: consecutive threads -> consecutive ci pairs
+        store2(wf + ((size_t)(a0 + row) * 9 + t) * j.cin + b0 + 2 * cp, sm[row][(2 * cp) * 9 + t], sm[row][(2 * cp + 1) * 9 + t]);
+        // wd[ci][8-t][co]: consecutive threads -> consecutive co pairs
+        store2(wd + ((size_t)(b0 + row) * 9 + (8 - t)) * j.cout + a0 + 2 * cp, sm[2 * cp][row * 9 + t], sm[2 * cp + 1][row * 9 + t]);
+      } else {
+        // convT: sm[ci][co*4 + ab];  wf[(ab*cout + co)][ci]: consecutive threads -> consecutive ci pairs
+        store2(wf + ((size_t)t * j.cout + b0 + row) * j.cin + a0 + 2 * cp, sm[2 * cp][row * 4 + t], sm[2 * cp + 1][row * 4 + t]);
+        // wd[ci][ab][co]: consecutive threads -> consecutive co pairs
+        store2(wd + ((size_t)(a0 + row) * 4 + t) * j.cout + b0 + 2 * cp, sm[row][(2 * cp) * 4 + t], sm[row][(2 * cp + 1) * 4 + t]);
+      }
+    }
+  } else {
+    const float* ws = reinterpret_cast<const float*>(j.src);
+    // packed gradient: ws[co][t][ci] (conv) / ws[ci][ab][co] (ConvT): 32 contiguous floats per (row, tap)
+    const int pitch = TAPS == 9 ? j.cin : j.cout;
+    if ((reinterpret_cast<uintptr_t>(ws) & 15) == 0 && pitch % 4 == 0) {
+      float4 v[kVecIters];
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        const int i = tid + it * 256, c4 = i % (kWT / 4), t = (i / (kWT / 4)) % TAPS, row = i / (TAPS * (kWT / 4));
+        v[it] = *reinterpret_cast<const float4*>(ws + ((size_t)(a0 + row) * TAPS + t) * pitch + b0 + 4 * c4);
+      }
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        const int i = tid + it * 256, c4 = i % (kWT / 4), t = (i / (kWT / 4)) % TAPS, row = i / (TAPS * (kWT / 4));
+        sm[row][(4 * c4) * TAPS + t] = v[it].x;
+        sm[row][(4 * c4 + 1) * TAPS + t] = v[it].y;
+        sm[row][(4 * c4 + 2) * TAPS + t] = v[it].z;
+        sm[row][(4 * c4 + 3) * TAPS + t] = v[it].w;
+      }
+    } else {
+#pragma unroll 12
+      for (int i = tid; i < kWT * RUN; i += 256) {
+        const int c = i % kWT, t = (i / kWT) % TAPS, row = i / RUN;
+        sm[row][c * TAPS + t] = ws[((size_t)(a0 + row) * TAPS + t) * pitch + b0 + c];
+      }
+    }
+    __syncthreads();
+    float* grad = reinterpret_cast<float*>(j.dst0);
+    if ((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && ((size_t)B * TAPS) % 4 == 0) {
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        const int i = tid + it * 256, al = i / (RUN / 4), e4 = i % (RUN / 4);
+        *reinterpret_cast<float4*>(grad + ((size_t)(a0 + al) * B + b0) * TAPS + 4 * e4) =
+            make_float4(sm[al][4 * e4], sm[al][4 * e4 + 1], sm[al][4 * e4 + 2], sm[al][4 * e4 + 3]);
+      }
+    } else {
+#pragma unroll 12
+      for (int i = tid; i < kWT * RUN; i += 256) {
+        const int al = i / RUN, e = i % RUN;
+        grad[((size_t)(a0 + al) * B + b0) * TAPS + e] = sm[al][e];
+      }
+    }
+  }
+}
+
 template <typename T, bool PACK>
 __global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restrict__ jobs, const int32_t* __restrict__ tiles,
                                                       uint8_t* dst_base) {
@@ -97,56 +195,7 @@ __global__ void __launch_bounds__(256) weights_kernel(const unetk_wjob* __restri
     }
     return;
   }
-  const int taps = j.kind == 0 ? 9 : 4;
-  const int run = kWT * taps;                       // contiguous floats per `a` row of the parameter tile
-  // parameter layout: [a][b][taps] with a = co (conv) / ci (convT);  A = rows, B = columns
-  const int B = j.kind == 0 ? j.cin : j.cout;
-  const float* param = PACK ? reinterpret_cast<const float*>(j.src) : nullptr;
-  if (PACK) {
-    for (int i = tid; i < kWT * run; i += 256) {
-      const int al = i / run, e = i % run;
-      sm[al][e] = param[((size_t)(a0 + al) * B + b0) * taps + e];
-    }
-    __syncthreads();
-    T* wf = reinterpret_cast<T*>(j.dst0);
-    T* wd = reinterpret_cast<T*>(j.dst1);
-    // two adjacent elements per store (4 bytes of bf16 / 8 bytes of fp32); tap counts are compile-time in each branch
-    if (j.kind == 0) {
-      for (int i = tid; i < kWT * 9 * (kWT / 2); i += 256) {
-        const int cp = i % (kWT / 2), t = (i / (kWT / 2)) % 9, row = i / (9 * (kWT / 2));
-        // wf[co][t][ci]: consecutive threads -> consecutive ci pairs
-        store2(wf + ((size_t)(a0 + row) * 9 + t) * j.cin + b0 + 2 * cp, sm[row][(2 * cp) * 9 + t], sm[row][(2 * cp + 1) * 9 + t]);
-        // wd[ci][8-t][co]: consecutive threads -> consecutive co pairs
-        store2(wd + ((size_t)(b0 + row) * 9 + (8 - t)) * j.cout + a0 + 2 * cp, sm[2 * cp][row * 9 + t], sm[2 * cp + 1][row * 9 + t]);
-      }
-    } else {
-      for (int i = tid; i < kWT * 4 * (kWT / 2); i += 256) {
-        const int cp = i % (kWT / 2), t = (i / (kWT / 2)) % 4, row = i / (4 * (kWT / 2));
-        // convT: sm[ci][co*4 + ab];  wf[(ab*cout + co)][ci]: consecutive threads -> consecutive ci pairs
-        store2(wf + ((size_t)t * j.cout + b0 + row) * j.cin + a0 + 2 * cp, sm[2 * cp][row * 4 + t], sm[2 * cp + 1][row * 4 + t]);
-        // wd[ci][ab][co]: consecutive threads -> consecutive co pairs
-        store2(wd + ((size_t)(a0 + row) * 4 + t) * j.cout + b0 + 2 * cp, sm[row][(2 * cp) * 4 + t], sm[row][(2 * cp + 1) * 4 + t]);
-      }
-    }
-  } else {
-    const float* ws = reinterpret_cast<const float*>(j.src);
-    for (int i = tid; i < kWT * run; i += 256) {
-      const int t = (i / kWT) % taps;
-      if (j.kind == 0) {
-        const int co = i / run, ci = i % kWT;          // ws[co][t][ci]
-        sm[co][ci * 9 + t] = ws[((size_t)(a0 + co) * 9 + t) * j.cin + b0 + ci];
-      } else {
-        const int ci = i / run, co = i % kWT;          // ws[ci][ab][co]
-        sm[ci][co * 4 + t] = ws[((size_t)(a0 + ci) * 4 + t) * j.cout + b0 + co];
-      }
-    }
-    __syncthreads();
-    float* grad = reinterpret_cast<float*>(j.dst0);
-    for (int i = tid; i < kWT * run; i += 256) {
-      const int al = i / run, e = i % run;
-      grad[((size_t)(a0 + al) * B + b0) * taps + e] = sm[al][e];
-    }
-  }
+  if (j.kind == 0) weights_tile<T, PACK, 9>(j, a0, b0, tid, sm); else weights_tile<T, PACK, 4>(j, a0, b0, tid, sm);
 }
 
 // NCHW fp32 image -> NHWC im2col operand, 8 consecutive K values per thread with the (tap, channel) decoding hoisted
