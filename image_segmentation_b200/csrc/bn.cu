@@ -1002,6 +1002,12 @@ __global__ void __launch_bounds__(128, 3)
   }
 }
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // bf16 tier, C = 64: the reduction pass with the per-class sums on the tensor cores.  M[k][c] = sum_p mask * dl[p][k] and
 // Z[k][c] = sum_p mask * dl[p][k] * z[p][c] are matrix products over the PIXEL dimension (K = the 16 pixels of a warp's
 // block): A = the mask as 1.0 / 0 resp. mask * z (both exact in bf16) with 16 channels as rows, B = dl with the 8 columns
@@ -1012,20 +1018,6 @@ __global__ void __launch_bounds__(128, 3)
 // through shared memory in a fixed order, blocks through fp64 atomics.  z and dl reach the warp through a private
 // 4-stage cp.async ring (a 16-pixel block = 2 KB of z + 16 * dout floats), so three blocks per warp are in flight while one
 // is being reduced: the loop is issue-bound, not latency-bound.
-__device__ __forceinline__ void cp_async_16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
-               "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_4(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src),
-               "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
 struct HeadStage {
   uint4 z[16][8];                                      // [pixel][channel group ^ swizzle]
   float d[4][16];                                      // [class][pixel]
@@ -1067,7 +1059,8 @@ struct HeadFill {
         for (int r = 0; r < 4; ++r)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(stage_addr + zdst[r]), "l"(zsrc + (size_t)r * zrow4));
         const float* src = dl + ((size_t)cur.img * DOUT + (lane >> 4)) * cur.hw + cur.off + (lane & 15);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(stage_addr + ddst), "l"(src));
+        if ((lane >> 4) < DOUT)                          // dout = 1: the upper half-warp has no class to fetch
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(stage_addr + ddst), "l"(src));
         if ((lane >> 4) + 2 < DOUT)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(stage_addr + ddst + 128u), "l"(src + 2 * (size_t)cur.hw));
       } else {
