@@ -101,6 +101,37 @@ __global__ void bn_finalize_kernel(unetk_bn_finalize_args a) {
   }
 }
 
+// Two-level index (img, off) of a linear item index over rows of `hw` items, advanced by a fixed stride from round to round
+// of a loop without a division: (image, pixel offset) of a warp's 16-pixel block inside NCHW planes in the head kernels
+// (the divisions by the runtime plane size were a third of their loops), (image row, pixel pair) / (pooled row, window) in
+// the pooling variants of the BatchNorm kernels.
+struct BlockCursor {
+  uint32_t img, off, step_img, step_off, hw;
+  __device__ __forceinline__ BlockCursor(int64_t base, int64_t stride, uint32_t hw_) : hw(hw_) {
+    img = (uint32_t)(base / hw_);
+    off = (uint32_t)(base - (int64_t)img * hw_);
+    step_img = (uint32_t)(stride / hw_);
+    step_off = (uint32_t)(stride - (int64_t)step_img * hw_);
+  }
+  __device__ __forceinline__ void advance() {
+    img += step_img;
+    off += step_off;
+    if (off >= hw) {
+      off -= hw;
+      ++img;
+    }
+  }
+  // pixel (block base + t), t < 16
+  __device__ __forceinline__ void at(uint32_t t, uint32_t& i, uint32_t& o) const {
+    i = img;
+    o = off + t;
+    while (o >= hw) {
+      o -= hw;
+      ++i;
+    }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(kThreads)
@@ -110,9 +141,15 @@ __global__ void __launch_bounds__(kThreads)
   // work item = (pixel or 2x2 window, channel group)
   const int hh = POOL ? h / 2 : h, ww = POOL ? w / 2 : w;
   const int64_t total = (int64_t)n * hh * ww * cg;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)((uint32_t)i % (uint32_t)cg);
-    int64_t p = (int64_t)((uint32_t)i / (uint32_t)cg);
+  // POOL with cg | blockDim (every power-of-two channel count): the thread's channel group is fixed and its window index
+  // advances by a constant, so (pooled row, window) come from a cursor instead of four divisions per item
+  const bool fixed_g = POOL && (blockDim.x % cg) == 0;
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  BlockCursor cur(fixed_g ? first / cg : 0, fixed_g ? ((int64_t)gridDim.x * blockDim.x) / cg : 1, (uint32_t)ww);
+  const int g_fixed = (int)(first % cg);
+  for (int64_t i = first; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = fixed_g ? g_fixed : (int)((uint32_t)i % (uint32_t)cg);
+    int64_t p = fixed_g ? 0 : (int64_t)((uint32_t)i / (uint32_t)cg);
     float sc[8], sh[8];
     load8(scale + g * 8, sc);
     load8(shift + g * 8, sh);
@@ -123,19 +160,24 @@ __global__ void __launch_bounds__(kThreads)
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(fmaf(v[k], sc[k], sh[k]), 0.f);
       store8(a + p * ald + g * 8, v);
     } else {
-      const uint32_t p32 = (uint32_t)p, uww = (uint32_t)ww, uhh = (uint32_t)hh;
-      const uint32_t line = p32 / uww;
-      const int x = (int)(p32 - line * uww);
-      const uint32_t img_u = line / uhh;
-      const int y = (int)(line - img_u * uhh);
-      const int img = (int)img_u;
+      // line = img * hh + y (pooled row); the full-resolution rows are 2 * line and 2 * line + 1 because h == 2 * hh
+      uint32_t line, x;
+      if (fixed_g) {
+        line = cur.img;
+        x = cur.off;
+        cur.advance();
+      } else {
+        const uint32_t p32 = (uint32_t)p;
+        line = p32 / (uint32_t)ww;
+        x = p32 - line * (uint32_t)ww;
+      }
       float mx[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) mx[k] = -1.f;  // ReLU output is >= 0: position 0 always wins the first comparison
       uint32_t arg = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int64_t pix = ((int64_t)img * h + (2 * y + (q >> 1))) * w + (2 * x + (q & 1));
+        const int64_t pix = ((int64_t)(2 * line + (q >> 1))) * w + (2 * x + (q & 1));
         float v[8];
         load8(z + pix * zld + g * 8, v);
 #pragma unroll
@@ -148,7 +190,7 @@ __global__ void __launch_bounds__(kThreads)
         }
         store8(a + pix * ald + g * 8, v);
       }
-      const int64_t win = ((int64_t)img * hh + y) * ww + x;
+      const int64_t win = (int64_t)line * ww + x;
       store8(pooled + win * pld + g * 8, mx);
       if (pool_idx) pool_idx[win * cg + g] = (uint16_t)arg;
     }
@@ -207,15 +249,15 @@ __device__ __forceinline__ void load_pixel(const BwdSrc<T>& s, int64_t pix, int 
 // POOL: two horizontally adjacent pixels (2*xp, 2*xp+1) of one pooling window share the window's pooled gradient and
 // arg-max word: one index decode, one dpool load and one idx load per pair.
 template <typename T>
-__device__ __forceinline__ void load_pixel_pair(const BwdSrc<T>& s, int64_t pair, int g, const float (&sc)[8],
+__device__ __forceinline__ void load_pixel_pair(const BwdSrc<T>& s, uint32_t line, uint32_t xp, int g, const float (&sc)[8],
                                                 const float (&sh)[8], int64_t& pix0, float (&za)[8], float (&ya)[8],
                                                 float (&zb)[8], float (&yb)[8]) {
-  const uint32_t p32 = (uint32_t)pair, hw2 = (uint32_t)s.w >> 1, uh = (uint32_t)s.h;
-  const uint32_t line = p32 / hw2, xp = p32 - line * hw2;
-  const uint32_t img = line / uh, y = line - img * uh;
+  // line = img * h + y (image row), xp = pixel pair inside the row.  h is even, so the row's parity is y's and the pooled
+  // row of the window is line / 2: no further decoding is needed.
+  const uint32_t hw2 = (uint32_t)s.w >> 1;
   pix0 = (int64_t)line * s.w + 2 * xp;
-  const int64_t win = ((int64_t)(img * (uh >> 1) + (y >> 1))) * hw2 + xp;
-  const uint32_t q0 = (y & 1u) * 2u;
+  const int64_t win = (int64_t)(line >> 1) * hw2 + xp;
+  const uint32_t q0 = (line & 1u) * 2u;
   const uint32_t arg = s.pidx[win * s.cg + g];
   float dp[8], da[8], db[8];
   load8(s.dp + win * s.dpld + g * 8, dp);
@@ -258,10 +300,11 @@ __global__ void __launch_bounds__(kThreads, 3)
   for (int k = 0; k < 8; ++k) acc[0][k] = acc[1][k] = 0.f;
   if (POOL) {
     // items are horizontal pixel pairs
-    for (int64_t it = i0 + row; it < i1; it += rows) {
+    BlockCursor cur(i0 + row, rows, (uint32_t)s.w >> 1);   // (image row, pixel pair) of item `it`
+    for (int64_t it = i0 + row; it < i1; it += rows, cur.advance()) {
       float za[8], ya[8], zb[8], yb[8];
       int64_t pix0;
-      load_pixel_pair<T>(s, it, g, sc, sh, pix0, za, ya, zb, yb);
+      load_pixel_pair<T>(s, cur.img, cur.off, g, sc, sh, pix0, za, ya, zb, yb);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         acc[0][k] += ya[k] + yb[k];
@@ -338,10 +381,11 @@ __global__ void __launch_bounds__(kThreads, 3)
     }
   }
   if (POOL) {
-    for (int64_t it = i0 + row; it < i1; it += rows) {
+    BlockCursor cur(i0 + row, rows, (uint32_t)s.w >> 1);   // (image row, pixel pair) of item `it`
+    for (int64_t it = i0 + row; it < i1; it += rows, cur.advance()) {
       float za[8], ya[8], zb[8], yb[8], oa[8], ob[8];
       int64_t pix0;
-      load_pixel_pair<T>(s, it, g, sc, sh, pix0, za, ya, zb, yb);
+      load_pixel_pair<T>(s, cur.img, cur.off, g, sc, sh, pix0, za, ya, zb, yb);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         oa[k] = fmaf(sc[k], ya[k], fmaf(cb[k], za[k], cc[k]));
@@ -748,35 +792,6 @@ __device__ __forceinline__ void mma_m16n8k16_bf16(float (&c)[4], uint32_t a0, ui
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-
-// (image, offset) of a warp's 16-pixel block inside the NCHW planes of hw pixels, advanced from round to round of a
-// grid-stride loop without a division (the divisions by the runtime hw were half the instructions of the head loops).
-struct BlockCursor {
-  uint32_t img, off, step_img, step_off, hw;
-  __device__ __forceinline__ BlockCursor(int64_t base, int64_t stride, uint32_t hw_) : hw(hw_) {
-    img = (uint32_t)(base / hw_);
-    off = (uint32_t)(base - (int64_t)img * hw_);
-    step_img = (uint32_t)(stride / hw_);
-    step_off = (uint32_t)(stride - (int64_t)step_img * hw_);
-  }
-  __device__ __forceinline__ void advance() {
-    img += step_img;
-    off += step_off;
-    if (off >= hw) {
-      off -= hw;
-      ++img;
-    }
-  }
-  // pixel (block base + t), t < 16
-  __device__ __forceinline__ void at(uint32_t t, uint32_t& i, uint32_t& o) const {
-    i = img;
-    o = off + t;
-    while (o >= hw) {
-      o -= hw;
-      ++i;
-    }
-  }
-};
 
 template <int DOUT>
 __global__ void __launch_bounds__(kThreads, 3)
