@@ -104,3 +104,38 @@ def test_batch_helpers_identity_at_training_resolution():
     assert [m["original_size"] for m in metas] == [(20, 30), (32, 16)]
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         process_batch_reverse(out, metas)            # the reverse transform is a CUDA kernel, there is no CPU path
+
+
+def _run_bench(*args, timeout=600):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    return subprocess.run([sys.executable, os.path.join(root, "bench.py"), *args], capture_output=True, text=True,
+                          timeout=timeout, env=env, cwd=root)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the contract's keys,
+    timed on host cores, never touching the product."""
+    import json
+    r = _run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "unet256_train_images_per_sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["steps"] == 1 and d["value"] > 0
+    assert "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_product_arm_fails_loudly_without_a_gpu():
+    r = _run_bench("--steps", "1", "--warmup", "1", timeout=300)
+    assert r.returncode != 0
+    assert "needs a CUDA device" in r.stderr and "{\"metric\"" not in r.stdout
